@@ -1,0 +1,101 @@
+"""ctypes binding of libchs_b200.so (include/chs_b200.h).  There is no CPU fallback: if
+the CUDA library is missing it is built with nvcc, and if that fails the import error
+is raised to the caller."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libchs_b200.so")
+SOURCES = ("chs_api.cu", "chs_kernels.cuh", "dct_core.cuh", "chs_rt.h")
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("RT", "BRT", "B", "A0", "A1", "Amr", "kappa_tilde", "L", "delx", "delt", "delt_max",
+                 "M_tilde", "threshold", "time_limit_s", "jitter")] + [("full_sim", C.c_int32),
+                                                                        ("adaptive_time", C.c_int32)]
+
+
+class State(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("delt", "time_delta_sum", "time_passed", "tau0", "t0")] + \
+               [("computed_steps", C.c_int64), ("skip_check", C.c_int32), ("stop_reason", C.c_int32)]
+
+
+STOP_NAMES = {0: 'None', 1: 'energy', 2: 'time-limit', 3: 'nan'}
+
+# every symbol include/chs_b200.h declares: name -> (restype, argtypes)
+PROTOTYPES = {
+    "chs_abi_version": (C.c_int32, []),
+    "chs_last_error": (C.c_char_p, []),
+    "chs_supports_n": (C.c_int32, [C.c_int32]),
+    "chs_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "chs_create": (C.c_void_p, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "chs_destroy": (None, [C.c_void_p]),
+    "chs_set_params": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Params)]),
+    "chs_set_state": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(State)]),
+    "chs_get_state": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(State)]),
+    "chs_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "chs_begin": (C.c_int, [C.c_void_p]),
+    "chs_steps": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
+    "chs_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chs_rewind_rows": (C.c_int, [C.c_void_p]),
+    "chs_end": (C.c_int, [C.c_void_p]),
+    "chs_dctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chs_idctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chs_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+
+def _stale(lib_path):
+    if not os.path.exists(lib_path):
+        return True
+    t = os.path.getmtime(lib_path)
+    return any(os.path.getmtime(os.path.join(CSRC, s)) > t for s in SOURCES if os.path.exists(os.path.join(CSRC, s)))
+
+
+def build(force=False, verbose=False):
+    """Compiles csrc/chs_api.cu for sm_100a into chsimpy_b200/libchs_b200.so (in-tree)."""
+    if not force and not _stale(LIB_PATH):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "chs_api.cu")]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libchs_b200.so:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+def bind(lib):
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def load():
+    """Returns the bound CUDA library, building it on first use.  Never falls back."""
+    global _lib
+    if _lib is None:
+        path = build()
+        _lib = bind(C.CDLL(path))
+        if _lib.chs_abi_version() != 1:
+            raise RuntimeError("libchs_b200.so ABI mismatch")
+    return _lib
+
+
+def check(lib, rc, what):
+    if rc is None or (isinstance(rc, int) and rc < 0):
+        raise RuntimeError(f"{what} failed: {lib.chs_last_error().decode()}")
+    return rc

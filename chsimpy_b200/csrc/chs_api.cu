@@ -1,0 +1,402 @@
+// C ABI of libchs_b200.so (see include/chs_b200.h).  Host-side orchestration only: every
+// number is produced by the kernels in chs_kernels.cuh.  Compiled by nvcc for sm_100a, or
+// by g++ with -DCHS_EMU as the host test harness (chs_rt.h).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "chs_kernels.cuh"
+
+using namespace chs;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+
+#define CHS_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+struct chs_solver {
+    int device, N, batch;
+    double *U, *hatU, *T, *rows;
+    long long rows_cap;
+    cudaStream_t stream;
+    // carved from the caller's workspace
+    Sim* sims;
+    double* part;
+    double* colpart;
+    double2* tw;
+    double2* om;
+    double* lam;
+    int* index;
+    double* mean;
+    // host mirrors
+    std::vector<Sim> hsims;
+    std::vector<int> hindex;
+    int n_running;
+    long long launches;
+    bool attrs_set;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Layout {
+    size_t sims, part, colpart, tw, om, lam, index, mean, total;
+};
+static Layout layout(int N, int batch) {
+    Layout L;
+    size_t o = 0;
+    const int ntiles = N / 16;
+    L.sims = o; o = align_up(o + sizeof(Sim) * (size_t)batch);
+    L.part = o; o = align_up(o + sizeof(double) * (size_t)batch * P_NSLOT * ntiles);
+    L.colpart = o; o = align_up(o + sizeof(double) * (size_t)batch * ntiles * N);
+    L.tw = o; o = align_up(o + sizeof(double2) * (size_t)(N / 2));
+    L.om = o; o = align_up(o + sizeof(double2) * (size_t)N);
+    L.lam = o; o = align_up(o + sizeof(double) * (size_t)N);
+    L.index = o; o = align_up(o + sizeof(int) * (size_t)batch);
+    L.mean = o; o = align_up(o + sizeof(double) * (size_t)batch);
+    L.total = o;
+    return L;
+}
+
+extern "C" int32_t chs_abi_version(void) { return CHS_ABI_VERSION; }
+extern "C" const char* chs_last_error(void) { return g_err.c_str(); }
+
+extern "C" int32_t chs_supports_n(int32_t N) {
+    return (N == 32 || N == 64 || N == 128 || N == 256 || N == 512 || N == 1024) ? 1 : 0;
+}
+
+extern "C" int64_t chs_workspace_bytes(int32_t N, int32_t batch) {
+    if (!chs_supports_n(N) || batch < 1) return -1;
+    return (int64_t)layout(N, batch).total;
+}
+
+// ---- dispatch on N ---------------------------------------------------------------------
+#define CHS_FOR_N(N_, CALL)                  \
+    switch (N_) {                            \
+        case 32: { CALL(32); } break;        \
+        case 64: { CALL(64); } break;        \
+        case 128: { CALL(128); } break;      \
+        case 256: { CALL(256); } break;      \
+        case 512: { CALL(512); } break;      \
+        case 1024: { CALL(1024); } break;    \
+        default: return fail("unsupported N"); \
+    }
+
+template <int N>
+static int set_attrs() {
+    const int b = Geo<N>::SMEM_BYTES;
+    CHS_CUDA(cudaFuncSetAttribute(k_col<N, COL_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_col<N, COL_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_col<N, COL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_FWD_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_FWD_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_PREPARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_JITTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    return 0;
+}
+
+static KArgs base_args(chs_solver* s) {
+    KArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.sims = s->sims; a.sim_index = nullptr;
+    a.U = s->U; a.hatU = s->hatU; a.T = s->T;
+    a.rows = s->rows; a.rows_cap = s->rows_cap;
+    a.part = s->part; a.colpart = s->colpart;
+    a.tw = s->tw; a.om = s->om; a.lam = s->lam;
+    a.mean_host = s->mean;
+    return a;
+}
+
+extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, double* U, double* hat_U, double* T,
+                                  double* rows, int64_t rows_cap, void* workspace, int64_t workspace_bytes,
+                                  const double* lambda_host, void* stream) {
+    if (!chs_supports_n(N)) { fail("chs_create: N must be a power of two in [32, 1024]"); return nullptr; }
+    if (batch < 1 || rows_cap < 1) { fail("chs_create: bad batch/rows_cap"); return nullptr; }
+    const Layout L = layout(N, batch);
+    if (workspace_bytes < (int64_t)L.total) { fail("chs_create: workspace too small"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail("chs_create: cudaSetDevice failed"); return nullptr; }
+    chs_solver* s = new chs_solver();
+    s->device = device; s->N = N; s->batch = batch;
+    s->U = U; s->hatU = hat_U; s->T = T; s->rows = rows; s->rows_cap = rows_cap;
+    s->stream = (cudaStream_t)stream;
+    unsigned char* w = (unsigned char*)workspace;
+    s->sims = (Sim*)(w + L.sims);
+    s->part = (double*)(w + L.part);
+    s->colpart = (double*)(w + L.colpart);
+    s->tw = (double2*)(w + L.tw);
+    s->om = (double2*)(w + L.om);
+    s->lam = (double*)(w + L.lam);
+    s->index = (int*)(w + L.index);
+    s->mean = (double*)(w + L.mean);
+    s->hsims.assign(batch, Sim());
+    std::memset(s->hsims.data(), 0, sizeof(Sim) * batch);
+    s->hindex.resize(batch);
+    for (int i = 0; i < batch; ++i) s->hindex[i] = i;
+    s->n_running = batch;
+    s->launches = 0;
+    // twiddle tables in extended precision, rounded once
+    const int M = N / 2;
+    std::vector<double2> tw(M), om(N);
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int m = 0; m < M; ++m) {
+        const long double a = -2.0L * pi * m / M;
+        tw[m] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    for (int m = 0; m < N; ++m) {
+        const long double a = -pi * m / (2.0L * N);
+        om[m] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    bool ok = true;
+    ok &= cudaMemsetAsync(workspace, 0, L.total, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->tw, tw.data(), sizeof(double2) * M, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->om, om.data(), sizeof(double2) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->index, s->hindex.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaStreamSynchronize(s->stream) == cudaSuccess;
+    int rc = 0;
+#define CALL(NN) rc = set_attrs<NN>();
+    switch (N) {
+        case 32: CALL(32) break; case 64: CALL(64) break; case 128: CALL(128) break;
+        case 256: CALL(256) break; case 512: CALL(512) break; case 1024: CALL(1024) break;
+    }
+#undef CALL
+    if (!ok || rc != 0) {
+        if (ok) { /* g_err set by set_attrs */ } else fail("chs_create: table upload failed");
+        delete s;
+        return nullptr;
+    }
+    return s;
+}
+
+extern "C" void chs_destroy(chs_solver* s) { delete s; }
+
+extern "C" int chs_set_params(chs_solver* s, int32_t sim, const chs_params* p) {
+    if (!s || sim < 0 || sim >= s->batch || !p) return fail("chs_set_params: bad argument");
+    Sim& h = s->hsims[sim];
+    h.p = *p;
+    h.delt = p->delt;
+    h.delt_coef = p->delt;
+    CHS_CUDA(cudaMemcpyAsync(s->sims + sim, &h, sizeof(Sim), cudaMemcpyHostToDevice, s->stream));
+    CHS_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int pull(chs_solver* s) {
+    CHS_CUDA(cudaMemcpyAsync(s->hsims.data(), s->sims, sizeof(Sim) * s->batch, cudaMemcpyDeviceToHost, s->stream));
+    CHS_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int chs_set_state(chs_solver* s, int32_t sim, const chs_state* st) {
+    if (!s || sim < 0 || sim >= s->batch || !st) return fail("chs_set_state: bad argument");
+    if (pull(s)) return -1;
+    Sim& h = s->hsims[sim];
+    h.delt = st->delt; h.time_delta_sum = st->time_delta_sum; h.time_passed = st->time_passed;
+    h.tau0 = st->tau0; h.t0 = st->t0; h.computed_steps = st->computed_steps;
+    h.skip_check = st->skip_check; h.stop_reason = st->stop_reason;
+    CHS_CUDA(cudaMemcpyAsync(s->sims + sim, &h, sizeof(Sim), cudaMemcpyHostToDevice, s->stream));
+    CHS_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int chs_get_state(chs_solver* s, int32_t sim, chs_state* st) {
+    if (!s || sim < 0 || sim >= s->batch || !st) return fail("chs_get_state: bad argument");
+    if (pull(s)) return -1;
+    const Sim& h = s->hsims[sim];
+    st->delt = h.delt; st->time_delta_sum = h.time_delta_sum; st->time_passed = h.time_passed;
+    st->tau0 = h.tau0; st->t0 = h.t0; st->computed_steps = h.computed_steps;
+    st->skip_check = h.skip_check; st->stop_reason = h.stop_reason;
+    return 0;
+}
+
+static int refresh_index(chs_solver* s) {
+    s->hindex.clear();
+    for (int i = 0; i < s->batch; ++i)
+        if (!s->hsims[i].halted) s->hindex.push_back(i);
+    s->n_running = (int)s->hindex.size();
+    if (s->n_running > 0)
+        CHS_CUDA(cudaMemcpyAsync(s->index, s->hindex.data(), sizeof(int) * s->n_running, cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+template <int N>
+static int do_prepare(chs_solver* s) {
+    using G = Geo<N>;
+    KArgs a = base_args(s);
+    CHS_LAUNCH((k_diag<N, DIAG_PREPARE>), dim3(G::NTILES, s->batch), dim3(G::NT), G::SMEM_BYTES, s->stream, a);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chs_prepare(chs_solver* s, const double* mean_U_host) {
+    if (!s || !mean_U_host) return fail("chs_prepare: bad argument");
+    CHS_CUDA(cudaMemcpyAsync(s->mean, mean_U_host, sizeof(double) * s->batch, cudaMemcpyHostToDevice, s->stream));
+    CHS_CUDA(cudaStreamSynchronize(s->stream));        // mean_U_host may be pageable and short-lived
+#define CALL(NN) if (do_prepare<NN>(s)) return -1;
+    CHS_FOR_N(s->N, CALL)
+#undef CALL
+    return 0;
+}
+
+template <int N>
+static int do_begin(chs_solver* s) {
+    using G = Geo<N>;
+    KArgs a = base_args(s);
+    const dim3 grid(G::NTILES, s->batch), block(G::NT);
+    CHS_LAUNCH(k_begin, dim3((s->batch + 127) / 128), dim3(128), 0, s->stream, s->sims, s->batch);
+    CHS_LAUNCH((k_row<N, ROW_FWD_U>), grid, block, G::SMEM_BYTES, s->stream, a);      // U -> T
+    CHS_LAUNCH((k_col<N, COL_FWD>), grid, block, G::SMEM_BYTES, s->stream, a);        // T -> hat_U
+    CHS_LAUNCH((k_row<N, ROW_FWD_MU>), grid, block, G::SMEM_BYTES, s->stream, a);     // mu(U) -> T, pre-part
+    s->launches += 4;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chs_begin(chs_solver* s) {
+    if (!s) return fail("chs_begin: null handle");
+#define CALL(NN) if (do_begin<NN>(s)) return -1;
+    CHS_FOR_N(s->N, CALL)
+#undef CALL
+    // the prologue's control step may already halt a sim (time limit); the index list is
+    // compacted at the first chs_poll
+    s->hindex.resize(s->batch);
+    for (int i = 0; i < s->batch; ++i) s->hindex[i] = i;
+    s->n_running = s->batch;
+    CHS_CUDA(cudaMemcpyAsync(s->index, s->hindex.data(), sizeof(int) * s->batch, cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+template <int N>
+static int do_steps(chs_solver* s, long long n_iters, const double* noise, const double* noise_mean, int last) {
+    using G = Geo<N>;
+    if (s->n_running <= 0) return 0;
+    KArgs a = base_args(s);
+    a.sim_index = (s->n_running == s->batch) ? nullptr : s->index;
+    const dim3 grid(G::NTILES, s->n_running), block(G::NT);
+    for (long long it = 0; it < n_iters; ++it) {
+        a.last = (last && it == n_iters - 1) ? 1 : 0;
+        a.iter_in_call = (int)it;
+        if (noise) {
+            a.noise = noise + (size_t)it * N * N;
+            a.noise_mean = noise_mean + it;
+            a.store_U = 1;
+        }
+        CHS_LAUNCH((k_col<N, COL_STEP>), grid, block, G::SMEM_BYTES, s->stream, a);
+        CHS_LAUNCH((k_row<N, ROW_STEP>), grid, block, G::SMEM_BYTES, s->stream, a);
+        s->launches += 2;
+        if (noise) {
+            CHS_LAUNCH((k_diag<N, DIAG_JITTER>), grid, block, G::SMEM_BYTES, s->stream, a);
+            s->launches += 1;
+        }
+    }
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chs_steps(chs_solver* s, int64_t n_iters, const double* noise, const double* noise_mean, int32_t last) {
+    if (!s || n_iters < 0) return fail("chs_steps: bad argument");
+    if (noise && !noise_mean) return fail("chs_steps: noise without noise_mean");
+#define CALL(NN) if (do_steps<NN>(s, n_iters, noise, noise_mean, last)) return -1;
+    CHS_FOR_N(s->N, CALL)
+#undef CALL
+    return 0;
+}
+
+extern "C" int chs_poll(chs_solver* s, int32_t* stop_reason, int64_t* computed_steps, int64_t* rows_written) {
+    if (!s) return fail("chs_poll: null handle");
+    if (pull(s)) return -1;
+    for (int i = 0; i < s->batch; ++i) {
+        if (stop_reason) stop_reason[i] = s->hsims[i].stop_reason;
+        if (computed_steps) computed_steps[i] = s->hsims[i].computed_steps;
+        if (rows_written) rows_written[i] = s->hsims[i].rows_written;
+    }
+    if (refresh_index(s)) return -1;
+    return s->n_running;
+}
+
+extern "C" int chs_rewind_rows(chs_solver* s) {
+    if (!s) return fail("chs_rewind_rows: null handle");
+    CHS_LAUNCH(k_rewind, dim3((s->batch + 127) / 128), dim3(128), 0, s->stream, s->sims, s->batch);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int N>
+static int do_end(chs_solver* s) {
+    using G = Geo<N>;
+    if (pull(s)) return -1;
+    std::vector<int> stale;
+    for (int i = 0; i < s->batch; ++i)
+        if (s->hsims[i].u_stale && s->hsims[i].p.jitter == 0.0) stale.push_back(i);
+    for (int i = 0; i < s->batch; ++i) s->hsims[i].u_stale = 0;
+    if (!stale.empty()) {
+        CHS_CUDA(cudaMemcpyAsync(s->index, stale.data(), sizeof(int) * stale.size(), cudaMemcpyHostToDevice, s->stream));
+        KArgs a = base_args(s);
+        a.sim_index = s->index;
+        const dim3 grid(G::NTILES, (unsigned)stale.size()), block(G::NT);
+        CHS_LAUNCH((k_col<N, COL_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // hat_U -> T
+        CHS_LAUNCH((k_row<N, ROW_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // T -> U
+        s->launches += 2;
+        CHS_CUDA(cudaGetLastError());
+    }
+    // clear the stale flags on the device too
+    CHS_CUDA(cudaMemcpyAsync(s->sims, s->hsims.data(), sizeof(Sim) * s->batch, cudaMemcpyHostToDevice, s->stream));
+    CHS_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int chs_end(chs_solver* s) {
+    if (!s) return fail("chs_end: null handle");
+#define CALL(NN) if (do_end<NN>(s)) return -1;
+    CHS_FOR_N(s->N, CALL)
+#undef CALL
+    return 0;
+}
+
+template <int N>
+static int do_dctn(chs_solver* s, const double* in, double* out, bool inverse) {
+    using G = Geo<N>;
+    KArgs a = base_args(s);
+    const dim3 grid(G::NTILES, s->batch), block(G::NT);
+    if (!inverse) {
+        a.src = in; a.dst = nullptr;
+        CHS_LAUNCH((k_row<N, ROW_FWD_U>), grid, block, G::SMEM_BYTES, s->stream, a);  // in -> T
+        a.src = nullptr; a.dst = out;
+        CHS_LAUNCH((k_col<N, COL_FWD>), grid, block, G::SMEM_BYTES, s->stream, a);    // T -> out
+    } else {
+        a.src = in; a.dst = nullptr;
+        CHS_LAUNCH((k_col<N, COL_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // in -> T
+        a.src = nullptr; a.dst = out;
+        CHS_LAUNCH((k_row<N, ROW_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // T -> out
+    }
+    s->launches += 2;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chs_dctn(chs_solver* s, const double* in, double* out) {
+    if (!s || !in || !out) return fail("chs_dctn: bad argument");
+#define CALL(NN) if (do_dctn<NN>(s, in, out, false)) return -1;
+    CHS_FOR_N(s->N, CALL)
+#undef CALL
+    return 0;
+}
+extern "C" int chs_idctn(chs_solver* s, const double* in, double* out) {
+    if (!s || !in || !out) return fail("chs_idctn: bad argument");
+#define CALL(NN) if (do_dctn<NN>(s, in, out, true)) return -1;
+    CHS_FOR_N(s->N, CALL)
+#undef CALL
+    return 0;
+}
+
+extern "C" int64_t chs_launch_count(const chs_solver* s) { return s ? s->launches : 0; }

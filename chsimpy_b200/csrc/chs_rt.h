@@ -1,0 +1,20 @@
+// Runtime shim: the kernels in chs_kernels.cuh are written once and compiled either by
+// nvcc for sm_100a (the product) or -- with -DCHS_EMU -- by g++ for the host, where
+// every CUDA thread of a block becomes an OS thread and __syncthreads() a barrier.
+// The host build exists ONLY so that the index logic of the kernels can be unit-tested
+// in the GPU-less build container (tests/, via tests/emu_lib.py); the Python package
+// never loads it and has no CPU fallback.
+#pragma once
+
+#ifdef CHS_EMU
+#include "emu.h"
+#else
+#include <cuda_runtime.h>
+#define CHS_DEV __device__ __forceinline__
+#define CHS_HD __host__ __device__ __forceinline__
+#define CHS_KERNEL __global__
+#define CHS_CX __host__ __device__
+#define CHS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define CHS_SMEM_DECL extern __shared__ __align__(16) unsigned char chs_smem_raw[];
+#define CHS_SMEM_PTR (chs_smem_raw)
+#endif

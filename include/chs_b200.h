@@ -1,0 +1,138 @@
+/*
+ * chs_b200.h -- C ABI of libchs_b200.so, the B200-native (sm_100a) replacement for the
+ * hot path of uncertaintyhub/chsimpy: the semi-implicit spectral Cahn-Hilliard stepper
+ * (reference chsimpy/solver.py:84-252 + chsimpy/timedata.py + chsimpy/utils.py:34-49)
+ * for one simulation or a batch of independent simulations (the A0/A1 ensemble of
+ * chsimpy/experiment.py:84-126).
+ *
+ * The reference is pure Python and has no FFI seam of its own; the
+ * narrowest seam is the `Solver` class.  Each entry point below names the reference
+ * lines it stands in for.  Plain pointers and sizes only: the caller (PyTorch, in
+ * chsimpy_b200/solver.py) owns every device buffer and passes raw device addresses;
+ * the library owns no persistent device memory.
+ *
+ * Threading: a handle is single-owner (not thread-safe); all work of a handle is
+ * issued on the one CUDA stream given at creation.  Return value: 0 on success,
+ * negative on error (see chs_last_error()).
+ */
+#ifndef CHS_B200_H
+#define CHS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHS_ABI_VERSION 1
+
+/* stop reasons -- chsimpy/solver.py:132,198,246 ('None' | 'time-limit' | 'energy');
+ * CHS_STOP_NAN is the device image of the AssertionError of chsimpy/timedata.py:10. */
+enum { CHS_STOP_NONE = 0, CHS_STOP_ENERGY = 1, CHS_STOP_TIME = 2, CHS_STOP_NAN = 3 };
+
+/* TimeData column order, chsimpy/timedata.py:8-9 */
+enum { CHS_COL_IT = 0, CHS_COL_E, CHS_COL_E2, CHS_COL_SA, CHS_COL_DOMTIME, CHS_COL_RA,
+       CHS_COL_L2, CHS_COL_PS, CHS_COL_DELT, CHS_NCOLS };
+
+/* Per-simulation constants: chsimpy/parameters.py:24-64 and the derived scalars of
+ * chsimpy/solution.py:25-50 (computed by the host exactly as the reference does). */
+typedef struct chs_params {
+    double RT, BRT, B, A0, A1;       /* R*T, B*R*T, B, Redlich-Kister A0(T), A1(T) */
+    double Amr, kappa_tilde, L;      /* 1/Am, gradient-energy parameter, domain length */
+    double delx;                     /* L/(N-1)  (quirk Q1) */
+    double delt, delt_max;           /* initial / maximum time step */
+    double M_tilde, threshold;       /* mobility factor; SA threshold */
+    double time_limit_s;             /* params.time_max*60, <= 0: no limit */
+    double jitter;                   /* 0: off; else amplitude in (0, 0.1) */
+    int32_t full_sim, adaptive_time;
+} chs_params;
+
+/* Mutable per-simulation solver state that the reference keeps in Solver/Solution
+ * attributes (chsimpy/solver.py:50-54,128-135). */
+typedef struct chs_state {
+    double delt, time_delta_sum, time_passed, tau0, t0;
+    int64_t computed_steps;
+    int32_t skip_check, stop_reason;
+} chs_state;
+
+typedef struct chs_solver chs_solver;   /* opaque */
+
+/* Size in bytes of the device workspace the caller must provide for `batch` sims. */
+int64_t chs_workspace_bytes(int32_t N, int32_t batch);
+
+/* Supported N for the FFT path (powers of two, 32..16384).  Returns 1/0. */
+int32_t chs_supports_n(int32_t N);
+
+/* Creates a solver for `batch` independent N x N simulations on CUDA device `device`.
+ * Buffers (device pointers, row-major, contiguous, owned by the caller):
+ *   U      [batch][N][N]  concentration field           (Solution.U)
+ *   hat_U  [batch][N][N]  its 2-D orthonormal DCT-II    (local `hat_U`, solver.py:159)
+ *   T      [batch][N][N]  row/column intermediate
+ *   rows   [batch][rows_cap][9]  TimeData rows written by the device since chs_begin
+ *   workspace  chs_workspace_bytes(N, batch) bytes
+ * `lambda_host[N]` (host) = 2*cos(pi*k/(N-1)) - 2, the 1-D Laplacian spectrum exactly as
+ * the caller's numpy evaluates chsimpy/utils.py:34-36 (so the multipliers are bit-identical).
+ * `stream` is a cudaStream_t (0 = default stream).  Stands in for Solver.__init__
+ * (solver.py:45-57) minus the host-side initial-condition generators. */
+chs_solver* chs_create(int32_t device, int32_t N, int32_t batch,
+                       double* U, double* hat_U, double* T,
+                       double* rows, int64_t rows_cap,
+                       void* workspace, int64_t workspace_bytes,
+                       const double* lambda_host, void* stream);
+void chs_destroy(chs_solver*);
+
+int chs_set_params(chs_solver*, int32_t sim, const chs_params*);
+int chs_set_state(chs_solver*, int32_t sim, const chs_state*);
+int chs_get_state(chs_solver*, int32_t sim, chs_state*);       /* synchronises the stream */
+
+/* Solver.prepare(), solver.py:84-135: row 0 of TimeData (E, E2, PS, Ra of the U
+ * currently in the U buffer; SA = L2 = domtime = 0) is written to rows[sim][0], and
+ * computed_steps=1, tau0=t0=0, stop_reason=None.  delt / time_delta_sum / skip_check
+ * are left alone (quirk Q16).  `mean_U[batch]` (host) = np.mean of each field. */
+int chs_prepare(chs_solver*, const double* mean_U_host);
+
+/* Entry of Solver.solve_or_resume, solver.py:158-163: hat_U = dctn(U, 'ortho') for
+ * every simulation, multipliers reset to the initial delt (solver.py:151-152), and the
+ * chemical potential of U staged for the first iteration.  Resets the TimeData write
+ * cursor of every sim to 0. */
+int chs_begin(chs_solver*);
+
+/* `n_iters` iterations of the loop body solver.py:165-249 for every simulation that
+ * has not stopped; nothing synchronises with the host (device-side stop flags).
+ *   noise       NULL, or device pointer to [n_iters][N][N] uniform [0,1) draws (the
+ *               host-precomputed per-step jitter, solver.py:210-211), shared by all sims
+ *   noise_mean  NULL, or device pointer to [n_iters] means of those draws
+ *   last        non-zero if the reference's `for` ends after these iterations (the
+ *               "pre" part of the following iteration -- adaptive dt, time accounting,
+ *               time-limit test, solver.py:177-199 -- is then NOT run ahead) */
+int chs_steps(chs_solver*, int64_t n_iters, const double* noise, const double* noise_mean, int32_t last);
+
+/* Non-blocking-ish poll: copies per-sim stop reasons, computed_steps and the number of
+ * TimeData rows written since chs_begin to host arrays of length batch (any may be
+ * NULL); returns the number of simulations still running, or <0 on error.
+ * Synchronises the handle's stream. */
+int chs_poll(chs_solver*, int32_t* stop_reason, int64_t* computed_steps, int64_t* rows_written);
+
+/* Sets the TimeData write cursor of every simulation back to 0 (the caller has copied the
+ * rows out); lets an arbitrarily long run reuse a rows buffer of rows_cap rows. */
+int chs_rewind_rows(chs_solver*);
+
+/* Exit of solve_or_resume (solver.py:251): materialises U = idctn(hat_U) in the U
+ * buffer for every sim whose U is stale (no-jitter runs never store U per step). */
+int chs_end(chs_solver*);
+
+/* Stand-alone transforms on [batch][N][N] device arrays (in -> out, T is scratch):
+ * scipy.fftpack.dctn / idctn with norm='ortho' as called at solver.py:159,201,208. */
+int chs_dctn(chs_solver*, const double* in, double* out);
+int chs_idctn(chs_solver*, const double* in, double* out);
+
+/* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
+int64_t chs_launch_count(const chs_solver*);
+
+const char* chs_last_error(void);
+int32_t chs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,199 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / public Solver API) against
+the golden fixtures frozen from the unmodified reference, and against the CPU oracle.
+
+Tolerances: U max-abs <= 1e-11; E/E2 and the other TimeData columns
+rel <= 1e-9 per row; tau0 / computed_steps / stop_reason exact; t0 rel <= 1e-12;
+SA within 2/N^2 (threshold ties)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.fftpack as fp
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+U_TOL = 1e-11
+ROW_RTOL = 1e-9
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+def make_params(meta):
+    import chsimpy_b200 as ch
+    p = ch.Parameters()
+    p.no_gui = True
+    for k, v in meta["params"].items():
+        setattr(p, k, v)
+    if meta["kappa_override"] is not None:
+        p.kappa_tilde = meta["kappa_override"]
+    if meta["fac"] is not None:
+        f0, f1 = meta["fac"]
+        p.func_A0 = lambda T: ch.utils.A0(T) * f0
+        p.func_A1 = lambda T: ch.utils.A1(T) * f1
+    return p
+
+
+def check_rows(rows, ref, N):
+    assert rows.shape == ref.shape, (rows.shape, ref.shape)
+    for c, name in enumerate(("it", "E", "E2", "SA", "domtime", "Ra", "L2", "PS", "delt")):
+        a, b = rows[:, c], ref[:, c]
+        if name == "SA":
+            assert np.abs(a - b).max() <= 2.0 / N ** 2 + 1e-15, name
+        else:
+            err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+            err[b == 0] = np.abs(a[b == 0])
+            assert err.max() <= ROW_RTOL, (name, float(err.max()), int(err.argmax()))
+
+
+def run_case(name):
+    import chsimpy_b200 as ch
+    z, m = load(name)
+    p = make_params(m)
+    s = ch.Solver(p)
+    assert abs(s.U_init.sum() - m["U_init_sum"]) < 1e-9
+    s.prepare()
+    nan_raised = False
+    try:
+        if m["chunks"]:
+            for i, c in enumerate(m["chunks"]):
+                sol = s.solve_or_resume(c)
+                key = f"U_chunk{i}"
+                if key in z:
+                    assert np.abs(sol.U - z[key]).max() <= U_TOL
+                elif key + "_sample" in z:
+                    st = max(1, p.N // 64)
+                    assert np.abs(sol.U[::st, ::st] - z[key + "_sample"]).max() <= U_TOL
+        else:
+            sol = s.solve_or_resume(p.ntmax)
+    except AssertionError:
+        if m["nan_row"] < 0:
+            raise
+        nan_raised = True
+        sol = s.solution
+    rows, ref = sol.timedata.data(), z["rows"]
+    if m["nan_row"] >= 0:
+        assert nan_raised
+        assert rows.shape[0] == ref.shape[0] and rows.shape[0] - 1 == m["nan_row"]
+        check_rows(rows[:-1], ref[:-1], p.N)
+        assert np.isnan(rows[-1]).any()
+        return s, sol, z, m
+    check_rows(rows, ref, p.N)
+    assert sol.stop_reason == m["stop_reason"]
+    assert sol.computed_steps == m["computed_steps"]
+    assert sol.tau0 == m["tau0"]
+    assert abs(sol.t0 - m["t0"]) <= 1e-12 * max(1.0, abs(m["t0"]))
+    assert int(np.argmax(sol.E2)) == m["argmax_E2"]
+    assert abs(s.time_passed - m["time_passed"]) <= 1e-12 * max(1.0, m["time_passed"])
+    assert abs(s.delt - m["delt_final"]) <= 1e-12 * m["delt_final"]
+    assert bool(s.skip_check) == m["skip_check"]
+    st = max(1, p.N // 64)
+    assert np.abs(sol.U[::st, ::st] - z["U_sample"]).max() <= U_TOL
+    assert np.abs(sol.U.sum(axis=1) - z["U_rowsum"]).max() <= U_TOL * p.N
+    if "U" in z:
+        d = np.abs(sol.U - z["U"])
+        rel_l2 = np.linalg.norm(sol.U - z["U"]) / np.linalg.norm(z["U"])
+        assert d.max() <= U_TOL and rel_l2 <= 1e-12, (float(d.max()), float(rel_l2))
+    return s, sol, z, m
+
+
+@pytest.mark.parametrize("N", [32, 64, 128, 256, 512, 1024])
+def test_dctn_matches_scipy(N):
+    from chsimpy_b200 import _lib
+    from chsimpy_b200.solver import BatchStepper
+    ps = _lib.Params(RT=1, BRT=1, B=1, A0=1, A1=1, Amr=1, kappa_tilde=1, L=2, delx=2 / (N - 1), delt=1e-8,
+                     delt_max=1e-8, M_tilde=1, threshold=0.5, time_limit_s=0, jitter=0, full_sim=1, adaptive_time=0)
+    b = 3
+    st = BatchStepper(N, [ps] * b)
+    x = np.random.default_rng(N).random((b, N, N)) - 0.3
+    y = st.dctn(x)
+    ref = np.stack([fp.dctn(x[i], norm="ortho") for i in range(b)])
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 1e-13
+    back = st.dctn(ref, inverse=True)
+    assert np.abs(back - x).max() <= 1e-13
+
+
+SMALL = ["n32_k60", "n64_k200", "n128_k200", "n256_k200", "n64_lcg_k100", "n128_sobol_k100",
+         "n256_T900_k300", "n64_cinit089_stop", "n128_chunked_jitter", "n256_chunked_adaptive", "n1024_k50"]
+N512 = ["n512_stop", "n512_full2000", "n512_jitter700", "n512_adaptive1200", "n512_adaptive_default_nan",
+        "n512_jitter_adaptive1200", "n512_jitter_stop", "n512_chunked_3x100", "n512_timelimit",
+        "n512_corner_lo_lo", "n512_corner_lo_hi", "n512_corner_hi_lo", "n512_corner_hi_hi"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_golden_small(name):
+    run_case(name)
+
+
+@pytest.mark.parametrize("name", N512)
+def test_golden_n512(name):
+    run_case(name)
+
+
+def test_default_stop_matches_survey_values():
+    """The headline numbers of SURVEY.md 6 (config 2): stop at 1674, t0, argmax(E2)."""
+    s, sol, z, m = run_case("n512_stop")
+    assert sol.stop_reason == "energy" and sol.computed_steps == 1674 and sol.tau0 == 1674
+    assert abs(sol.t0 - 2935.0877192982052) < 1e-9
+    assert int(np.argmax(sol.E2)) == 1672
+
+
+def test_against_oracle_seeded():
+    """CUDA path vs oracle on fresh seeded inputs (not in the fixtures)."""
+    import ch_oracle as orc
+    import chsimpy_b200 as ch
+    for N, seed, steps in ((64, 7, 120), (128, 11, 80), (256, 5, 40)):
+        p = ch.Parameters()
+        p.N, p.seed, p.ntmax, p.full_sim, p.no_gui, p.kappa_tilde = N, seed, steps, True, True, 2.5e-4
+        s = ch.Solver(p)
+        s.prepare()
+        sol = s.solve_or_resume(steps)
+        o = orc.run_default(N=N, nsteps=steps, seed=seed, kappa_tilde=2.5e-4, full_sim=True)
+        check_rows(sol.timedata.data(), o.rows, N)
+        assert np.abs(sol.U - o.U).max() <= U_TOL
+
+
+def test_user_field_and_wrong_shape():
+    import chsimpy_b200 as ch
+    p = ch.Parameters()
+    p.N, p.no_gui, p.kappa_tilde, p.full_sim = 64, True, 3e-4, True
+    U0 = 0.875 + 0.004 * (np.random.default_rng(3).random((64, 64)) - 0.5)
+    s = ch.Solver(p, U_init=U0)
+    assert s.create_rand is None
+    s.prepare()
+    sol = s.solve_or_resume(10)
+    assert sol.computed_steps == 10
+    with pytest.raises(SystemExit):
+        ch.Solver(p, U_init=np.zeros((8, 8)))
+
+
+def test_properties_full_size():
+    """Size-independent properties at N=512, batch 8: mean conservation (quirk Q4),
+    dctn/idctn round trip, lock-step batch == single run, determinism."""
+    import chsimpy_b200 as ch
+    from chsimpy_b200.solver import BatchStepper, make_params_struct
+    p = ch.Parameters()
+    p.no_gui, p.full_sim, p.ntmax = True, True, 60
+    single = ch.Solver(p)
+    single.prepare()
+    sol = single.solve_or_resume(60)
+    assert abs(sol.U.mean() - single.U_init.mean()) < 1e-14
+    ps = make_params_struct(p, single.solution)
+    st = BatchStepper(512, [ps] * 8)
+    st.set_U(single.U_init)
+    st.prepare()
+    rows, done = st.run(59)
+    for i in range(8):
+        assert np.array_equal(rows[i], sol.timedata.data()[1:]), i      # bit-identical across the batch
+    U = st.get_U()
+    for i in range(8):
+        assert np.array_equal(U[i], sol.U)
+    y = st.dctn(U)
+    back = st.dctn(y, inverse=True)
+    assert np.abs(back - U).max() < 1e-14
+    # Parseval: orthonormal transform keeps the Frobenius norm
+    assert abs(np.linalg.norm(y[0]) - np.linalg.norm(U[0])) < 1e-10
