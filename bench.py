@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 Cahn-Hilliard stepper.
+
+Metric (BASELINE.json): CH steps/sec at N=512 per B200 (aggregated over an ensemble of
+independent simulations; whole-job value over all GPUs).  One bench "step" = one CH time
+step (reference solver.py:165-249) of EVERY member of a batch of `--batch` N=512
+simulations per GPU -- the experiment.py A0/A1 ensemble with the fixed-length (`full_sim`)
+variant of SURVEY.md 8d config 3 so that no member drops out during the timed region.
+`value` = sim-steps/s with state resident in HBM; `e2e` = the same through the public
+BatchStepper API from HOST buffers (upload of the initial field, K steps, download of the
+TimeData rows and final fields inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRID = 512
+ALGO_BYTES_PER_SIM_STEP = 32 * N_GRID * N_GRID      # read+write U-equivalent and hat_U, fp64
+# kappa_tilde at the (fac_A0, fac_A1) corners and centre, from the reference (tests/golden/n512_corner_*.npz)
+_KAPPA = {(0.995, 0.995): 2.8527824637628903e-4, (0.995, 1.005): 4.088183715201557e-4,
+          (1.005, 0.995): 2.053833366570028e-4, (1.005, 1.005): 3.127937637279922e-4}
+
+
+def member_scalars(runs, seed=85972):
+    """A0/A1 factors exactly as experiment.py:157-160; kappa_tilde by bilinear interpolation of
+    the reference's corner values (synthetic stand-in for the 0.5 s/member sympy solve)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    fac = rng.uniform(0.995, 1.005, size=(runs, 2))
+    u = (fac[:, 0] - 0.995) / 0.01
+    v = (fac[:, 1] - 0.995) / 0.01
+    k = ((1 - u) * (1 - v) * _KAPPA[(0.995, 0.995)] + (1 - u) * v * _KAPPA[(0.995, 1.005)]
+         + u * (1 - v) * _KAPPA[(1.005, 0.995)] + u * v * _KAPPA[(1.005, 1.005)])
+    return fac, k
+
+
+def workload_text(members):
+    return (f"A0/A1 ensemble (BASELINE configs[2] shape): {members} independent N={N_GRID} simulations per GPU, "
+            f"each the configs[1] stepper with full_sim (fixed length); one bench step = one CH time step of "
+            f"every member")
+
+
+def physical_cores():
+    try:
+        import psutil
+        return psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+# ------------------------------------------------------------------------------- CPU legs
+def _oracle_member(args):
+    """One ensemble member on one host core with the oracle port; returns seconds for `steps`."""
+    fac0, fac1, kappa, warm, steps = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ch_oracle as orc
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=1):
+        k = orc.Consts.from_params(N=N_GRID, A0=orc.redlich_kister_A0(923.15) * fac0,
+                                   A1=orc.redlich_kister_A1(923.15) * fac1, kappa_tilde=kappa)
+        U0, draw = orc.initial_field(N_GRID, 0.875, "uniform", 2023)
+        s = orc.OracleSolver(k, U0, full_sim=True, create_rand=draw)
+        s.prepare()
+        s.run(1 + warm)
+        t = time.perf_counter()
+        s.run(steps)
+        return time.perf_counter() - t
+
+
+def cpu_baseline(sample_steps=300):
+    """Oracle port, one core, default config (BASELINE config 1 shape), bounded sample."""
+    dt = _oracle_member((1.0, 1.0, 2.989112919661156e-4, 20, sample_steps))
+    return {"value": round(sample_steps / dt, 2), "unit": "sim-steps/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/ch_oracle.py (numpy+scipy.fftpack restatement of solver.py), 1 sim N={N_GRID}, "
+                      f"{sample_steps} steps after 20 warm-up, single thread"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure
+    Python and cannot travel to the GPU box) on all physical host cores, experiment.py-style
+    process pool, one member per core, `sample` CH steps per bench step."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = physical_cores()
+    sample = 2                                   # CH steps per member per bench step
+    fac, kap = member_scalars(cores)
+    jobs = [(fac[i, 0], fac[i, 1], kap[i], args.warmup * sample, args.steps * sample) for i in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        secs = pool.map(_oracle_member, jobs)
+    wall = max(secs)
+    value = cores * args.steps * sample / wall
+    line = {"impl": "reference", "metric": "ch_steps_per_sec_n512", "value": round(value, 2), "unit": "sim-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(wall / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_text(cores) + f" [CPU arm: one member per physical host core, "
+                                   f"{sample} CH steps per bench step]", "members_per_gpu": cores, "N": N_GRID},
+            "cpu_baseline": {"value": round(value, 2), "unit": "sim-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{cores} members x {args.steps * sample} steps, mp.Pool({cores}), "
+                                       f"BLAS/FFT single-threaded per process as in the reference"},
+            "e2e": {"value": round(value, 2), "unit": "sim-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "setup_s": round(time.perf_counter() - t0 - wall, 2)}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for t, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= t <= t1 + 0.05):
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample inside the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import chsimpy_b200 as ch
+    from chsimpy_b200.solver import BatchStepper, make_params_struct
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 stepper has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, W = args.batch, args.steps, args.warmup
+
+    # ---- members of this rank (weak scaling: B per GPU, run ids rank*B .. rank*B+B-1)
+    fac_all, kap_all = member_scalars(B * world)
+    sl = slice(rank * B, (rank + 1) * B)
+    base = ch.Parameters()
+    base.no_gui, base.full_sim, base.kappa_tilde = True, True, 1.0
+    structs = []
+    for f, kap in zip(fac_all[sl], kap_all[sl]):
+        p = base.deepcopy()
+        p.kappa_tilde = float(kap)
+        p.func_A0 = (lambda f0: (lambda T: ch.utils.A0(T) * f0))(float(f[0]))
+        p.func_A1 = (lambda f1: (lambda T: ch.utils.A1(T) * f1))(float(f[1]))
+        structs.append(make_params_struct(p, ch.Solution(p)))
+    rng = np.random.Generator(np.random.PCG64(2023))
+    U0 = 0.875 + 0.875 * 0.01 * (rng.random((N_GRID, N_GRID)) - 0.5)          # solver.py:78-82, seed 2023
+
+    st = BatchStepper(N_GRID, structs, rows_cap=max(K + 8, W + 8))
+    st.set_U(U0)
+    st.prepare()
+    st.begin()
+    st.steps(W)
+    st.poll(); st.take_rows()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- timed region: K steps, state resident in HBM
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = st.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    st.steps(K)
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = st.launch_count() - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    running, stop, cs, rw = st.poll()
+    assert running == B and int(rw.min()) == K, "a member dropped out of the timed region"
+    st.take_rows()
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- per-kernel durations (CUDA events around every launch, same stream), second pass
+    st.set_timing(True)
+    st.steps(K)
+    tk, nk = st.get_timing()
+    st.set_timing(False)
+    st.poll(); st.take_rows()
+    st.end()
+    col_us, row_us = tk["col"] / nk * 1e3, tk["row"] / nk * 1e3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    step_bytes = ALGO_BYTES_PER_SIM_STEP * B
+    achieved = step_bytes / ((col_us + row_us) * 1e-6) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_step_per_sim")
+        traffic = traffic * B if traffic else None
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_col<512,STEP> + k_row<512,STEP> (the two launches of one step)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "peak_source": peak_src, "traffic": traffic,
+                "algorithmic_bytes_per_launch_pair": step_bytes,
+                "k_col_us": round(col_us, 2), "k_row_us": round(row_us, 2),
+                "k_col_gbs_own_32N2": round(32 * N_GRID ** 2 * B / (col_us * 1e-6) / 1e9, 1),
+                "k_row_gbs_own_16N2": round(16 * N_GRID ** 2 * B / (row_us * 1e-6) / 1e9, 1)}
+
+    # ---- e2e: public API from host buffers, copies inside the timed region
+    hostU = torch.from_numpy(U0).pin_memory()
+    rows_host = torch.empty((B, K, 9), dtype=torch.float64).pin_memory()
+    U_host = torch.empty((B, N_GRID, N_GRID), dtype=torch.float64).pin_memory()
+    barrier()
+    te0 = time.perf_counter()
+    st.U.copy_(hostU.to("cuda", non_blocking=True).expand(B, N_GRID, N_GRID))      # H2D (members share the field)
+    st._meanU = np.full(B, float(U0.mean()))
+    st.prepare()
+    st.begin()
+    st.steps(K, last=True)
+    st.poll()
+    rows_host.copy_(st.rows[:, :K, :], non_blocking=True)                            # D2H TimeData
+    st.end()
+    U_host.copy_(st.U, non_blocking=True)                                            # D2H final fields
+    barrier()
+    te = time.perf_counter() - te0
+    if world > 1:
+        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+    assert np.isfinite(rows_host.numpy()).all()
+    e2e = {"value": round(world * B * K / te, 1), "unit": "sim-steps/s",
+           "h2d_bytes_per_step": int((hostU.numel() * 8 + B * 136) / K),
+           "d2h_bytes_per_step": int((rows_host.numel() + U_host.numel()) * 8 / K),
+           "what": "BatchStepper from pinned host U_init -> prepare -> K steps -> TimeData rows + final U on host"}
+
+    if rank == 0:
+        line = {"metric": "ch_steps_per_sec_n512", "value": round(value, 1), "unit": "sim-steps/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_text(B), "members_per_gpu": B, "N": N_GRID, "l2": "working set 6 MiB/member >> 126 MB L2 "
+                           "(inputs larger than L2, no flush needed)" if B * 6 > 252 else "L2-resident batch"},
+                "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "sims_per_s_at_1674_steps": round(value / 1673.0, 2)}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+            line["single_sim"] = single_sim_probe(ch)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def single_sim_probe(ch):
+    """BASELINE configs[1]: one N=512 simulation run to the energy stop (latency-bound)."""
+    import torch
+    p = ch.Parameters()
+    p.no_gui = True
+    p.kappa_tilde = 2.989112919661156e-4
+    s = ch.Solver(p)
+    s.prepare()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    sol = s.solve_or_resume(p.ntmax)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    return {"workload": "configs[1]: N=512 to the energy stop, device-side stop flag, host poll every 128 steps",
+            "computed_steps": sol.computed_steps, "stop_reason": sol.stop_reason,
+            "steps_per_s": round((sol.computed_steps - 1) / dt, 1), "wall_s": round(dt, 4)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=1024, help="ensemble members per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / single-sim probes")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

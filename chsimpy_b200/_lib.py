@@ -49,6 +49,8 @@ PROTOTYPES = {
     "chs_dctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "chs_idctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "chs_launch_count": (C.c_int64, [C.c_void_p]),
+    "chs_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
+    "chs_get_timing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

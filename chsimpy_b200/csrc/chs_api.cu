@@ -40,8 +40,38 @@ struct chs_solver {
     std::vector<int> hindex;
     int n_running;
     long long launches;
-    bool attrs_set;
+    // optional per-kernel timing (bench.py)
+    bool timing;
+    std::vector<cudaEvent_t> events;       // 4 per iteration: before col, after col, after row, after diag
+    size_t ev_used;
+    bool ev_diag;
+    double t_ms[3];
+    long long t_iters;
 };
+
+static cudaEvent_t next_event(chs_solver* s) {
+    if (s->ev_used == s->events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s->events.push_back(e);
+    }
+    return s->events[s->ev_used++];
+}
+
+static int drain_events(chs_solver* s) {
+    if (s->ev_used == 0) return 0;
+    CHS_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t i = 0; i + 4 <= s->ev_used; i += 4) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, s->events[i], s->events[i + 1]);
+        cudaEventElapsedTime(&b, s->events[i + 1], s->events[i + 2]);
+        cudaEventElapsedTime(&c, s->events[i + 2], s->events[i + 3]);
+        s->t_ms[0] += a; s->t_ms[1] += b; s->t_ms[2] += c;
+        s->t_iters += 1;
+    }
+    s->ev_used = 0;
+    return 0;
+}
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -142,6 +172,8 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     for (int i = 0; i < batch; ++i) s->hindex[i] = i;
     s->n_running = batch;
     s->launches = 0;
+    s->timing = false; s->ev_used = 0; s->ev_diag = false; s->t_iters = 0;
+    s->t_ms[0] = s->t_ms[1] = s->t_ms[2] = 0;
     // twiddle tables in extended precision, rounded once
     const int M = N / 2;
     std::vector<double2> tw(M), om(N);
@@ -176,7 +208,28 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     return s;
 }
 
-extern "C" void chs_destroy(chs_solver* s) { delete s; }
+extern "C" void chs_destroy(chs_solver* s) {
+    if (!s) return;
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    delete s;
+}
+
+extern "C" int chs_set_timing(chs_solver* s, int32_t enable) {
+    if (!s) return fail("chs_set_timing: null handle");
+    if (drain_events(s)) return -1;
+    s->timing = enable != 0;
+    return 0;
+}
+
+extern "C" int chs_get_timing(chs_solver* s, double* ms3, int64_t* n_iters) {
+    if (!s) return fail("chs_get_timing: null handle");
+    if (drain_events(s)) return -1;
+    if (ms3) { ms3[0] = s->t_ms[0]; ms3[1] = s->t_ms[1]; ms3[2] = s->t_ms[2]; }
+    if (n_iters) *n_iters = s->t_iters;
+    s->t_ms[0] = s->t_ms[1] = s->t_ms[2] = 0;
+    s->t_iters = 0;
+    return 0;
+}
 
 extern "C" int chs_set_params(chs_solver* s, int32_t sim, const chs_params* p) {
     if (!s || sim < 0 || sim >= s->batch || !p) return fail("chs_set_params: bad argument");
@@ -290,13 +343,20 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
             a.noise_mean = noise_mean + it;
             a.store_U = 1;
         }
+        if (s->timing) {
+            if (s->ev_used + 4 > 65536 && drain_events(s)) return -1;
+            cudaEventRecord(next_event(s), s->stream);
+        }
         CHS_LAUNCH((k_col<N, COL_STEP>), grid, block, G::SMEM_BYTES, s->stream, a);
+        if (s->timing) cudaEventRecord(next_event(s), s->stream);
         CHS_LAUNCH((k_row<N, ROW_STEP>), grid, block, G::SMEM_BYTES, s->stream, a);
+        if (s->timing) cudaEventRecord(next_event(s), s->stream);
         s->launches += 2;
         if (noise) {
             CHS_LAUNCH((k_diag<N, DIAG_JITTER>), grid, block, G::SMEM_BYTES, s->stream, a);
             s->launches += 1;
         }
+        if (s->timing) cudaEventRecord(next_event(s), s->stream);
     }
     CHS_CUDA(cudaGetLastError());
     return 0;

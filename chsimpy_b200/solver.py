@@ -151,6 +151,16 @@ class BatchStepper:
     def set_state(self, sim, st):
         _lib.check(self.lib, self.lib.chs_set_state(self._h, sim, C.byref(st)), "chs_set_state")
 
+    def set_timing(self, on):
+        _lib.check(self.lib, self.lib.chs_set_timing(self._h, int(bool(on))), "chs_set_timing")
+
+    def get_timing(self):
+        """({'col': ms, 'row': ms, 'diag': ms}, iterations) accumulated since the last call."""
+        ms = (C.c_double * 3)()
+        n = C.c_int64(0)
+        _lib.check(self.lib, self.lib.chs_get_timing(self._h, ms, C.byref(n)), "chs_get_timing")
+        return {"col": ms[0], "row": ms[1], "diag": ms[2]}, int(n.value)
+
     def launch_count(self):
         return int(self.lib.chs_launch_count(self._h))
 

@@ -129,6 +129,13 @@ int chs_idctn(chs_solver*, const double* in, double* out);
 /* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
 int64_t chs_launch_count(const chs_solver*);
 
+/* Optional per-kernel timing for bench.py: when enabled, chs_steps brackets every kernel
+ * with CUDA events on the handle's stream.  chs_get_timing synchronises and returns the
+ * accumulated device milliseconds {column kernel, row kernel, jitter diagnostics kernel}
+ * and the number of iterations they cover, then clears the accumulators. */
+int chs_set_timing(chs_solver*, int32_t enable);
+int chs_get_timing(chs_solver*, double* ms3, int64_t* n_iters);
+
 const char* chs_last_error(void);
 int32_t chs_abi_version(void);
 

@@ -1,0 +1,41 @@
+"""The C-ABI library builds for sm_100a without a GPU and exports every symbol that
+include/chs_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+from chsimpy_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "chs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(chs_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_lib.PROTOTYPES)
+
+
+def test_library_builds_and_exports_everything():
+    path = _lib.build()
+    lib = ctypes.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    _lib.bind(lib)
+    assert lib.chs_abi_version() == 1
+    assert [n for n in (16, 32, 64, 100, 512, 1024, 2048) if lib.chs_supports_n(n)] == [32, 64, 512, 1024]
+    assert lib.chs_workspace_bytes(512, 4) > 0 and lib.chs_workspace_bytes(100, 4) < 0
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.Params) == 15 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.State) == 5 * 8 + 8 + 2 * 4
+
+
+def test_kernels_are_sm100a_sass():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
