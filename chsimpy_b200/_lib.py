@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libchs_b200.so")
-SOURCES = ("chs_api.cu", "chs_kernels.cuh", "dct_core.cuh", "chs_rt.h")
+SOURCES = ("chs_api.cu", "chs_kernels.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -48,6 +48,7 @@ PROTOTYPES = {
     "chs_end": (C.c_int, [C.c_void_p]),
     "chs_dctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "chs_idctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chs_debug_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "chs_launch_count": (C.c_int64, [C.c_void_p]),
     "chs_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "chs_get_timing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

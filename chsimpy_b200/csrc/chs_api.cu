@@ -33,6 +33,7 @@ struct chs_solver {
     double2* tw;
     double2* om;
     double* lam;
+    double2* logtab;
     int* index;
     double* mean;
     // host mirrors
@@ -76,7 +77,7 @@ static int drain_events(chs_solver* s) {
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t sims, part, colpart, tw, om, lam, index, mean, total;
+    size_t sims, part, colpart, tw, om, lam, logtab, index, mean, total;
 };
 static Layout layout(int N, int batch) {
     Layout L;
@@ -88,6 +89,7 @@ static Layout layout(int N, int batch) {
     L.tw = o; o = align_up(o + sizeof(double2) * (size_t)(N / 2));
     L.om = o; o = align_up(o + sizeof(double2) * (size_t)N);
     L.lam = o; o = align_up(o + sizeof(double) * (size_t)N);
+    L.logtab = o; o = align_up(o + sizeof(double2) * (size_t)LOG_TABLE_N);
     L.index = o; o = align_up(o + sizeof(int) * (size_t)batch);
     L.mean = o; o = align_up(o + sizeof(double) * (size_t)batch);
     L.total = o;
@@ -140,7 +142,7 @@ static KArgs base_args(chs_solver* s) {
     a.U = s->U; a.hatU = s->hatU; a.T = s->T;
     a.rows = s->rows; a.rows_cap = s->rows_cap;
     a.part = s->part; a.colpart = s->colpart;
-    a.tw = s->tw; a.om = s->om; a.lam = s->lam;
+    a.tw = s->tw; a.om = s->om; a.lam = s->lam; a.logtab = s->logtab;
     a.mean_host = s->mean;
     return a;
 }
@@ -164,6 +166,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     s->tw = (double2*)(w + L.tw);
     s->om = (double2*)(w + L.om);
     s->lam = (double*)(w + L.lam);
+    s->logtab = (double2*)(w + L.logtab);
     s->index = (int*)(w + L.index);
     s->mean = (double*)(w + L.mean);
     s->hsims.assign(batch, Sim());
@@ -186,10 +189,22 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
         const long double a = -pi * m / (2.0L * N);
         om[m] = make_double2((double)cosl(a), (double)sinl(a));
     }
+    // fast_log table (fastlog.cuh): sub-interval centres of [0.6875, 1.375) in bit-pattern space
+    std::vector<double2> lt(LOG_TABLE_N);
+    for (int i = 0; i < LOG_TABLE_N; ++i) {
+        const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << 45);
+        const unsigned long long b1 = LOG_OFF + ((unsigned long long)(i + 1) << 45);
+        double z0, z1;
+        std::memcpy(&z0, &b0, 8);
+        std::memcpy(&z1, &b1, 8);
+        const double invc = (double)(1.0L / ((long double)z0 * 0.5L + (long double)z1 * 0.5L));
+        lt[i] = make_double2(invc, (double)(-logl((long double)invc)));
+    }
     bool ok = true;
     ok &= cudaMemsetAsync(workspace, 0, L.total, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->tw, tw.data(), sizeof(double2) * M, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->om, om.data(), sizeof(double2) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->index, s->hindex.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaStreamSynchronize(s->stream) == cudaSuccess;
@@ -456,6 +471,15 @@ extern "C" int chs_idctn(chs_solver* s, const double* in, double* out) {
 #define CALL(NN) if (do_dctn<NN>(s, in, out, true)) return -1;
     CHS_FOR_N(s->N, CALL)
 #undef CALL
+    return 0;
+}
+
+extern "C" int chs_debug_log(chs_solver* s, const double* x, double* y, int64_t n) {
+    if (!s || !x || !y || n < 0) return fail("chs_debug_log: bad argument");
+    if (n == 0) return 0;
+    CHS_LAUNCH(k_debug_log, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s->stream, x, y, (long long)n, s->logtab);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
     return 0;
 }
 

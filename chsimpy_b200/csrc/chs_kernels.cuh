@@ -18,6 +18,7 @@
 // jitter is on.  Everything is IEEE float64.
 #pragma once
 #include "dct_core.cuh"
+#include "fastlog.cuh"
 #include "../../include/chs_b200.h"
 
 namespace chs {
@@ -56,6 +57,7 @@ struct KArgs {
     const double2* tw;           // exp(-2 pi i m / M), m < M
     const double2* om;           // exp(-i pi m / (2N)), m < N
     const double* lam;           // 2 cos(pi k/(N-1)) - 2
+    const double2* logtab;       // fast_log table {1/c, log c}
     const double* noise;         // [N][N] uniform draws of this step, or null
     const double* noise_mean;    // mean of that draw
     const double* mean_host;     // prepare: [batch] mean(U)
@@ -116,13 +118,22 @@ CHS_DEV void block_reduce(double (&v)[NV], double* scratch, int tid, int nthread
 // (the host emulation needs NT*NV doubles there; emu::launch() allocates that slack)
 #define CHS_FLAG_PTR(G, sm) (reinterpret_cast<int*>((sm) + G::TILE_DOUBLES))
 #define CHS_RA_SCRATCH(G, sm) ((sm) + G::TILE_DOUBLES + 2)
-#define CHS_RED_SCRATCH(G, sm) ((sm) + G::TILE_DOUBLES + 2 + 2 * G::TPL)
+#define CHS_RED_SCRATCH(G, sm) ((sm) + G::TILE_DOUBLES + 2 + 2 * G::TPL + 2 * LOG_TABLE_N)
+#define CHS_LOGTAB(G, sm) (reinterpret_cast<double2*>((sm) + G::TILE_DOUBLES + 2 + 2 * G::TPL))
+
+// copies the 2 KB fast_log table into shared memory (visible after the next barrier)
+template <class G>
+CHS_DEV double2* stage_logtab(double* sm, const double2* __restrict__ g, int tid) {
+    double2* t = CHS_LOGTAB(G, sm);
+    for (int i = tid; i < LOG_TABLE_N; i += G::NT) t[i] = g[i];
+    return t;
+}
 
 // ---------------------------------------------------------------------------------------
 // thermodynamics of one value (solver.py:166-175 and :218-221)
-CHS_DEV void thermo(double u, const chs_params& p, double& f, double& mu) {
+CHS_DEV void thermo(double u, const chs_params& p, const double2* __restrict__ ltab, double& f, double& mu) {
     const double ui = 1.0 - u;
-    const double lu = log(u), li = log(ui);
+    const double lu = fast_log(u, ltab), li = fast_log(ui, ltab);
     const double d = ui - u;
     const double uui = u * ui;
     f = p.RT * (u * (lu - p.B) + ui * li) + (p.A0 + p.A1 * d) * uui;
@@ -249,11 +260,76 @@ CHS_DEV bool last_cta(Sim* S, int ntiles, int* flag_smem, int tid) {
     return *flag_smem != 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tile I/O.  Loads are issued in independent batches of 8 per thread before the first use
+// (memory-level parallelism), then scattered into the tile.
+//   column tile: all N rows x LINES adjacent columns of a row-major N x N array
+//   row tile   : LINES adjacent rows
+// PHYS = the array index along the line is a physical coordinate (Makhoul position in smem),
+// otherwise it is a spectral index stored at its natural position.
+template <int N, bool PHYS>
+CHS_DEV int line_pos(int n) { return PHYS ? mk_pos<N>(n) : n; }
+
+template <int N, bool PHYS>
+CHS_DEV void col_tile_load(double* sm, const double* __restrict__ g, int l, int t) {
+    using G = Geo<N>;
+    constexpr int CNT = N / G::TPL, UNR = 8;
+#pragma unroll
+    for (int j0 = 0; j0 < CNT; j0 += UNR) {
+        double v[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) v[j] = g[(size_t)(t + (j0 + j) * G::TPL) * N + l];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) sm[line_pos<N, PHYS>(t + (j0 + j) * G::TPL) * G::LP + l] = v[j];
+    }
+}
+
+template <int N, bool PHYS>
+CHS_DEV void col_tile_store(const double* sm, double* __restrict__ g, int l, int t) {
+    using G = Geo<N>;
+    constexpr int CNT = N / G::TPL;
+#pragma unroll 8
+    for (int j = 0; j < CNT; ++j)
+        g[(size_t)(t + j * G::TPL) * N + l] = sm[line_pos<N, PHYS>(t + j * G::TPL) * G::LP + l];
+}
+
+template <int N, bool PHYS>
+CHS_DEV void row_tile_load(double* sm, const double* __restrict__ g, int tid) {
+    using G = Geo<N>;
+    constexpr int CNT = G::LINES * N / G::NT, UNR = 8;
+#pragma unroll
+    for (int j0 = 0; j0 < CNT; j0 += UNR) {
+        double v[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int i = tid + (j0 + j) * G::NT;
+            v[j] = g[(size_t)(i / N) * N + (i % N)];
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int i = tid + (j0 + j) * G::NT;
+            sm[line_pos<N, PHYS>(i % N) * G::LP + (i / N)] = v[j];
+        }
+    }
+}
+
+template <int N, bool PHYS>
+CHS_DEV void row_tile_store(const double* sm, double* __restrict__ g, int tid) {
+    using G = Geo<N>;
+    constexpr int CNT = G::LINES * N / G::NT;
+#pragma unroll 8
+    for (int j = 0; j < CNT; ++j) {
+        const int i = tid + j * G::NT;
+        g[(size_t)(i / N) * N + (i % N)] = sm[line_pos<N, PHYS>(i % N) * G::LP + (i / N)];
+    }
+}
+
 // =======================================================================================
 //  column kernel
 // =======================================================================================
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_col(KArgs a) {
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_col(KArgs a) {
     using G = Geo<N>;
     constexpr int M = G::M, LP = G::LP, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     CHS_SMEM_DECL
@@ -268,11 +344,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_col(KArgs a) {
 
     // -------- load + forward column DCT-II
     if (MODE != COL_INV) {
-        const double* src = a.T + off;
-        for (int i = tid; i < N * LINES; i += NT) {
-            const int y = i / LINES, l2 = i % LINES;
-            sm[mk_pos<N>(y) * LP + l2] = src[(size_t)y * N + kx0 + l2];
-        }
+        col_tile_load<N, true>(sm, a.T + off + kx0, l, t);
         __syncthreads();
         fft_fwd<N>(sl, t, a.tw);
     }
@@ -344,20 +416,14 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_col(KArgs a) {
         if (tid == 0) a.part[((size_t)sim * P_NSLOT + P_GY2) * G::NTILES + tile] = v[0];
     }
     // -------- store T2 tile
-    {
-        double* dstT = a.T + off;
-        for (int i = tid; i < N * LINES; i += NT) {
-            const int y = i / LINES, l2 = i % LINES;
-            dstT[(size_t)y * N + kx0 + l2] = sm[mk_pos<N>(y) * LP + l2];
-        }
-    }
+    col_tile_store<N, true>(sm, a.T + off + kx0, l, t);
 }
 
 // =======================================================================================
 //  row kernel
 // =======================================================================================
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_row(KArgs a) {
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_row(KArgs a) {
     using G = Geo<N>;
     constexpr int M = G::M, LP = G::LP, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int IPT = (M / 2 + TPL - 1) / TPL;
@@ -373,14 +439,12 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_row(KArgs a) {
     const size_t off = (size_t)sim * N * N;
     double* sl = sm + l;
     const bool control = (MODE == ROW_STEP) || (MODE == ROW_FWD_MU);
+    const double2* ltab = control ? stage_logtab<G>(sm, a.logtab, tid) : nullptr;
 
     // ================= inverse half: T2 rows -> U rows (Makhoul order in smem)
     if (MODE == ROW_STEP || MODE == ROW_INV) {
         const double* src = (MODE == ROW_INV && a.src) ? a.src + off : a.T + off;
-        for (int i = tid; i < LINES * N; i += NT) {
-            const int l2 = i / N, k = i % N;
-            sm[k * LP + l2] = src[(size_t)(row0 + l2) * N + k];
-        }
+        row_tile_load<N, false>(sm, src + (size_t)row0 * N, tid);
         __syncthreads();
         double c[IPT][4];
 #pragma unroll
@@ -404,10 +468,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_row(KArgs a) {
     } else {
         // ROW_FWD_U / ROW_FWD_MU: physical U rows -> smem (Makhoul order)
         const double* src = (MODE == ROW_FWD_U && a.src) ? a.src + off : a.U + off;
-        for (int i = tid; i < LINES * N; i += NT) {
-            const int l2 = i / N, x = i % N;
-            sm[mk_pos<N>(x) * LP + l2] = src[(size_t)(row0 + l2) * N + x];
-        }
+        row_tile_load<N, true>(sm, src + (size_t)row0 * N, tid);
         __syncthreads();
     }
 
@@ -425,10 +486,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_row(KArgs a) {
     // ================= physical-space output
     if (MODE == ROW_INV || (MODE == ROW_STEP && a.store_U)) {
         double* dstU = (MODE == ROW_INV && a.dst) ? a.dst + off : a.U + off;
-        for (int i = tid; i < LINES * N; i += NT) {
-            const int l2 = i / N, x = i % N;
-            dstU[(size_t)(row0 + l2) * N + x] = sm[mk_pos<N>(x) * LP + l2];
-        }
+        row_tile_store<N, true>(sm, dstU + (size_t)row0 * N, tid);
         if (MODE == ROW_INV) return;
     }
 
@@ -471,7 +529,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_row(KArgs a) {
         for (int x = x0; x < x0 + XPT; ++x) {
             const double nxt = (x + 1 < x0 + XPT) ? sl[mk_pos<N>(x + 1) * LP] : hi;
             double f, mu;
-            thermo(cur, p, f, mu);
+            thermo(cur, p, ltab, f, mu);
             if (diag) {
                 double g;
                 if (x == 0) g = (nxt - cur) * ih;
@@ -548,10 +606,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_row(KArgs a) {
         }
         __syncthreads();
         double* dstT = (MODE == ROW_FWD_U && a.dst) ? a.dst + off : a.T + off;
-        for (int i = tid; i < LINES * N; i += NT) {
-            const int l2 = i / N, k = i % N;
-            dstT[(size_t)(row0 + l2) * N + k] = sm[k * LP + l2];
-        }
+        row_tile_store<N, false>(sm, dstT + (size_t)row0 * N, tid);
     }
 
     // ================= control (not in jitter mode: k_diag finishes the iteration there)
@@ -590,6 +645,11 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
     const double* U = a.U + (size_t)sim * N * N;
     const double ih = 1.0 / p.delx, ih2 = 0.5 / p.delx;
     const double meanU = (MODE == DIAG_PREPARE) ? a.mean_host[sim] : 0.0;
+    const double2* ltab = nullptr;
+    if (MODE == DIAG_PREPARE) {
+        ltab = stage_logtab<G>(sm, a.logtab, tid);
+        __syncthreads();
+    }
     double v[4] = {0, 0, 0, 0};                    // GY2, GX2, F, ABS
     for (int i = tid; i < LINES * N; i += NT) {
         const int y = row0 + i / N, x = i % N;
@@ -605,7 +665,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
             else if (x == N - 1) gx = (c - U[(size_t)y * N + x - 1]) * ih;
             else gx = (U[(size_t)y * N + x + 1] - U[(size_t)y * N + x - 1]) * ih2;
             double f, mu;
-            thermo(c, p, f, mu);
+            thermo(c, p, ltab, f, mu);
             v[1] += gx * gx;
             v[2] += f;
             v[3] += fabs(c - meanU);
@@ -675,6 +735,12 @@ CHS_KERNEL void k_begin(Sim* sims, int batch) {
     S->halted = 0;
     S->delt_coef = S->p.delt;          // solver.py:151-152: multipliers of the *initial* delt
     S->ticket = 0;
+}
+
+// self-test of fast_log (chs_debug_log)
+CHS_KERNEL void k_debug_log(const double* x, double* y, long long n, const double2* tab) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fast_log(x[i], tab);
 }
 
 CHS_KERNEL void k_rewind(Sim* sims, int batch) {

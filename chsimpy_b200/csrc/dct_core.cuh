@@ -45,8 +45,9 @@ struct Geo {
     static constexpr int TPL = (M / 8 < 32) ? (M / 8) : 32;    // threads per line
     static constexpr int NT = LINES * TPL;                     // threads per CTA
     static constexpr int NTILES = N / LINES;
+    static constexpr int MINB = (N <= 512) ? 2 : 1;             // CTAs per SM the register budget is sized for
     static constexpr int TILE_DOUBLES = N * LP;
-    static constexpr int SCRATCH_DOUBLES = 2 * TPL + (NT / 32 + 1) * 8 + 8;
+    static constexpr int SCRATCH_DOUBLES = 2 * TPL + (NT / 32 + 1) * 8 + 8 + 2 * 128;   // + fast_log table
     static constexpr int SMEM_BYTES = (TILE_DOUBLES + SCRATCH_DOUBLES) * 8;
     static_assert(N >= 32 && (N & (N - 1)) == 0, "FFT path needs a power of two >= 32");
 };

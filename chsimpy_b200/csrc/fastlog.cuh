@@ -1,0 +1,57 @@
+// Table-driven natural logarithm for the chemical potential / free energy (reference
+// chsimpy/solver.py:173,220 call np.log three times per element; it is the largest single
+// consumer of FP64 issue slots in the step).
+//
+//   x = 2^k * z,  z in [0.6875, 1.375);  i = top 7 mantissa bits of (bits(x) - bits(0.6875))
+//   table[i] = { invc, logc }  with invc = double(1/c_i), c_i := 1/invc (c_i ~ centre of
+//   sub-interval i), logc = log(c_i) rounded to double
+//   r = fma(z, invc, -1)              exact to one rounding of a 2^-8-sized number
+//   log x = k ln2 + logc + log1p(r),  log1p(r) = r - r^2/2 + r^3/3 - ... - r^8/8  (|r| < 2^-7)
+// The summation keeps a hi/lo split (k*Ln2hi is exact: Ln2hi has 11 trailing zero bits), so
+// the result is within ~0.6 ulp for |log x| >= 2^-7 and within 3e-19 absolutely below that.
+// This is the evaluation scheme of the ARM optimized-routines / glibc 2.28+ log() (Szabolcs
+// Nagy, 2018), restated; the table is generated on the host at library load (chs_api.cu).
+// Non-finite, zero, negative and subnormal arguments take the libm slow path.
+#pragma once
+#include "chs_rt.h"
+
+namespace chs {
+
+constexpr int LOG_TABLE_N = 128;
+constexpr unsigned long long LOG_OFF = 0x3fe6000000000000ULL;
+
+#ifdef CHS_EMU
+static inline long long chs_d2ll(double x) { long long v; std::memcpy(&v, &x, 8); return v; }
+static inline double chs_ll2d(long long v) { double x; std::memcpy(&x, &v, 8); return x; }
+static inline double chs_fma(double a, double b, double c) { return std::fma(a, b, c); }
+#else
+CHS_DEV long long chs_d2ll(double x) { return __double_as_longlong(x); }
+CHS_DEV double chs_ll2d(long long v) { return __longlong_as_double(v); }
+CHS_DEV double chs_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+#endif
+
+// tab: LOG_TABLE_N entries {invc, logc} (shared or global memory)
+CHS_DEV double fast_log(double x, const double2* __restrict__ tab) {
+    const unsigned long long ix = (unsigned long long)chs_d2ll(x);
+    const unsigned top = (unsigned)(ix >> 52);                       // sign + exponent
+    if (top - 1u >= 0x7feu) return log(x);                           // <=0, subnormal, inf, nan
+    const unsigned long long tmp = ix - LOG_OFF;
+    const int i = (int)((tmp >> 45) & (LOG_TABLE_N - 1));
+    const int k = (int)((long long)tmp >> 52);
+    const double z = chs_ll2d((long long)(ix - (tmp & 0xfff0000000000000ULL)));
+    const double2 e = tab[i];
+    const double r = chs_fma(z, e.x, -1.0);
+    const double kd = (double)k;
+    constexpr double Ln2hi = 0x1.62e42fefa3800p-1, Ln2lo = 0x1.ef35793c76730p-45;
+    const double w = chs_fma(kd, Ln2hi, e.y);
+    const double hi = w + r;
+    const double lo = chs_fma(kd, Ln2lo, (w - hi) + r);
+    const double r2 = r * r;
+    // log1p(r) - r = r2*(-1/2 + r/3) + r2*r2*(-1/4 + r/5 + r2*(-1/6 + r/7 - r2/8))
+    const double p = chs_fma(r2, chs_fma(r2, -1.0 / 8, chs_fma(r, 1.0 / 7, -1.0 / 6)), chs_fma(r, 1.0 / 5, -1.0 / 4));
+    const double q = chs_fma(r, 1.0 / 3, -0.5);
+    const double y = chs_fma(r2, chs_fma(r2, p, q), lo);
+    return y + hi;
+}
+
+}  // namespace chs

@@ -161,6 +161,13 @@ class BatchStepper:
         _lib.check(self.lib, self.lib.chs_get_timing(self._h, ms, C.byref(n)), "chs_get_timing")
         return {"col": ms[0], "row": ms[1], "diag": ms[2]}, int(n.value)
 
+    def debug_log(self, x):
+        """Device fast_log of a host array (self-test of csrc/fastlog.cuh)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        src, dst = self.be.to_device(x), self.be.empty((x.size,))
+        _lib.check(self.lib, self.lib.chs_debug_log(self._h, self.be.ptr(src), self.be.ptr(dst), x.size), "chs_debug_log")
+        return self.be.download(dst)
+
     def launch_count(self):
         return int(self.lib.chs_launch_count(self._h))
 

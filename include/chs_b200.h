@@ -126,6 +126,10 @@ int chs_end(chs_solver*);
 int chs_dctn(chs_solver*, const double* in, double* out);
 int chs_idctn(chs_solver*, const double* in, double* out);
 
+/* Self-test hook: y[i] = the device's table-driven natural log of x[i] (csrc/fastlog.cuh),
+ * the routine that stands in for np.log at solver.py:173,220.  Device pointers. */
+int chs_debug_log(chs_solver*, const double* x, double* y, int64_t n);
+
 /* Number of kernels this handle has launched since creation (bench.py gpu_launches). */
 int64_t chs_launch_count(const chs_solver*);
 
