@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""A0/A1 parameter-sweep ensemble on GPUs -- the `chsimpy-experiment` entry point of the
+reference (chsimpy/experiment.py) with its `multiprocessing.Pool` over runs replaced by
+batched, lock-step simulations on the device(s):
+
+  * the table of A0/A1 factors is generated exactly as the reference does
+    (uniform / sobol / grid / file, `--independent`; experiment.py:148-190);
+  * every member shares seed and initial field and differs in (A0, A1, kappa_tilde)
+    (experiment.py:87-101);  members of one rank step together in one `BatchStepper`;
+  * members stop individually at their energy drop (device-side flags), the grid is
+    compacted at every host poll;
+  * one process per GPU (torchrun): run ids are sharded contiguously over ranks, there
+    is NO collective on the data path; the 12-tuples of experiment.py:114-126 are
+    gathered on rank 0 which writes `<id>-results.csv` / `<id>-results-agg.csv`.
+
+The host-side sympy scalars (kappa_tilde, c_A/c_B, spinodal roots; ~0.9 s per member) are
+computed by a host process pool, overlapped with nothing on the device only in the sense
+that they must precede it (kappa_tilde is an input of the step).
+"""
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import utils
+from .cli_parser import CLIParser
+from .parameters import Parameters
+from .solution import Solution
+from .timedata import TimeData
+
+RESULT_COLUMNS = ['A0', 'A1', 'ca', 'cb', 'sa', 'sb', 'tau0', 't0', 'tsep', 'id', 'fac_A0', 'fac_A1']
+
+
+class ExperimentParams:
+    def __init__(self):
+        self.runs = 2
+        self.jitter_Arellow = 0.995
+        self.jitter_Arelhigh = 1.005
+        self.processes = -1
+        self.independent = False
+        self.A_source = 'uniform'
+        self.A_seed = None
+
+
+class ExperimentCLIParser:
+    """Adds the experiment flags of reference experiment.py:37-59 to the common CLI."""
+
+    def __init__(self):
+        self.cliparser = CLIParser('chsimpy_b200 (experiment.py)')
+        g = self.cliparser.parser.add_argument_group('Experiment')
+        g.add_argument('-R', '--runs', default=3, type=int, help='Number of Monte-Carlo runs')
+        g.add_argument('-P', '--processes', default=-1, type=int,
+                       help='Host processes for the sympy scalars and the exports (-1 = physical cores)')
+        g.add_argument('--independent', action='store_true', help='A0 and A1 do not vary at the same time')
+        g.add_argument('--A-source', default='uniform', help="'uniform' | 'sobol' | 'grid' | <file with A0,A1 rows>")
+        g.add_argument('--A-seed', default=85972, type=int, help='RNG seed for the A0/A1 factors')
+        g.add_argument('--no-export', action='store_true', help='Skip the per-run yaml/csv files (results csv only)')
+
+    def get_parameters(self, argv=None):
+        params = self.cliparser.get_parameters(argv)
+        a = self.cliparser.args
+        ep = ExperimentParams()
+        ep.runs, ep.independent, ep.A_source = a.runs, a.independent, a.A_source
+        ep.processes, ep.A_seed = a.processes, a.A_seed
+        ep.no_export = a.no_export
+        params.no_gui = True
+        params.yaml = True
+        if a.export_csv is None:
+            params.export_csv = 'U, E, E2, SA'
+            params.compress_csv = True
+        if ep.runs < 1:
+            self.cliparser.parser.error('ERROR: --runs must be at least 1.')
+        if params.png_anim:
+            self.cliparser.parser.error('ERROR: --png-anim is not allowed.')
+        return ep, params
+
+
+def factor_table(ep):
+    """(rand_values [items, 2] or None, A_list or None, number of items) -- reference
+    experiment.py:148-190 and :204-209."""
+    A_list = rand_values = None
+    lo, hi = ep.jitter_Arellow, ep.jitter_Arelhigh
+    if ep.A_source in ('uniform', 'sobol'):
+        if ep.A_source == 'sobol':
+            from scipy.stats import qmc
+            q = qmc.Sobol(d=2, seed=ep.A_seed)
+            pts = q.random_base2(int(np.ceil(np.log2(ep.runs))))
+            cols = np.transpose(qmc.scale(pts, lo, hi)[:ep.runs])
+        else:
+            rng = np.random.Generator(np.random.PCG64(ep.A_seed))
+            cols = np.transpose(rng.uniform(lo, hi, size=(ep.runs, 2)))
+        if ep.independent:
+            rand_values = np.ones((2 * ep.runs, 2))
+            rand_values[:ep.runs, 0] = cols[0]
+            rand_values[ep.runs:, 1] = cols[1]
+        else:
+            rand_values = np.ones((ep.runs, 2))
+            rand_values[:, 0] = cols[0]
+            rand_values[:, 1] = cols[1]
+    elif ep.A_source == 'grid':
+        nx = int(np.floor(np.sqrt(ep.runs)))
+        ep.runs = nx * nx
+        xvec = np.linspace(lo, hi, nx)
+        if ep.independent:
+            rand_values = np.ones((2 * nx, 2))
+            rand_values[:nx, 0] = xvec
+            rand_values[nx:, 1] = xvec
+        else:
+            rand_values = np.array([[v, w] for v in xvec for w in xvec])
+    else:
+        A_list = utils.csv_import_matrix(ep.A_source)
+    n_items = rand_values.shape[0] if A_list is None else A_list.shape[0]
+    if ep.independent and ep.A_source in ('sobol', 'uniform'):
+        n_items = min(2 * ep.runs, n_items)
+    else:
+        n_items = min(ep.runs, n_items)
+    return rand_values, A_list, n_items
+
+
+def shard(n_items, rank, world):
+    """Contiguous, balanced range of run ids of `rank` (no communication needed)."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def member_params(init_params, run_id, rand_values, A_list):
+    """Parameters of one member, reference experiment.py:87-101."""
+    p = init_params.deepcopy()
+    p.seed = init_params.seed
+    p.file_id = f"{init_params.file_id}-run{run_id}"
+    if A_list is None:
+        f0, f1 = float(rand_values[run_id, 0]), float(rand_values[run_id, 1])
+        p.func_A0 = lambda temp, f0=f0: utils.A0(temp) * f0
+        p.func_A1 = lambda temp, f1=f1: utils.A1(temp) * f1
+    else:
+        a0, a1 = float(A_list[run_id][0]), float(A_list[run_id][1])
+        p.func_A0 = lambda temp, a0=a0: a0
+        p.func_A1 = lambda temp, a1=a1: a1
+        f0 = f1 = None
+    return p, f0, f1
+
+
+def _host_scalars(job):
+    """Per-member sympy work (reference solution.py:39-46, experiment.py:110-112), in a pool."""
+    R, T, B, a0, a1, at, kappa_given = job
+    if kappa_given is None:
+        kappa = float(utils.get_distance_common_tangent(R=R, T=T, B=B, A0=a0, A1=a1, at=at)) / (0.1602564 * 64) ** 2
+    else:
+        kappa = kappa_given
+    gap = utils.get_miscibility_gap(R, T, B, a0, a1)
+    sa, sb = utils.get_roots_of_EPP(R, T, a0, a1)
+    return kappa, float(gap[0]), float(gap[1]), float(sa), float(sb)
+
+
+def initial_field(params):
+    """The field every member starts from (same seed for all, quirk Q11)."""
+    if params.Uinit_file is not None:
+        return utils.csv_import_matrix(params.Uinit_file)
+    N, c0 = params.N, params.XXX
+    if params.generator == 'lcg':
+        from . import mport
+        return c0 + c0 * 0.01 * mport.matlab_lcg_sample(N, N, params.seed)
+    if params.generator == 'sobol':
+        from scipy.stats import qmc
+        return c0 + c0 * 0.01 * (qmc.Sobol(d=N, seed=params.seed).random(N) - 0.5)
+    if params.generator == 'uniform':
+        return c0 + c0 * 0.01 * (np.random.Generator(np.random.PCG64(params.seed)).random((N, N)) - 0.5)
+    raise ValueError("generator not supported in ensembles: " + str(params.generator))
+
+
+def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_init=None, host_procs=None,
+                   batch_max=2048, poll_every=128, keep_fields=True, backend=None, device=None, timings=None):
+    """Runs the members `run_ids` in lock-step on one GPU.  Returns a list of dicts with the
+    reference's 12-tuple (`tuple`), the TimeData (`timedata`), the final field (`U`, optional)
+    and the per-member Solution scalars."""
+    from .solver import BatchStepper, make_params_struct
+    if run_ids is None:
+        run_ids = range(rand_values.shape[0] if A_list is None else A_list.shape[0])
+    run_ids = list(run_ids)
+    t0 = time.perf_counter()
+    members = [member_params(init_params, rid, rand_values, A_list) for rid in run_ids]
+    jobs = []
+    for p, _, _ in members:
+        jobs.append((p.R, p.temp, p.B, float(p.func_A0(p.temp)), float(p.func_A1(p.temp)), p.XXX, p.kappa_tilde))
+    nproc = host_procs or min(len(jobs), utils.get_number_physical_cores() or 1)
+    if nproc > 1 and len(jobs) > 1:
+        with mp.get_context("fork").Pool(nproc) as pool:
+            scal = pool.map(_host_scalars, jobs, chunksize=max(1, len(jobs) // (4 * nproc)))
+    else:
+        scal = [_host_scalars(j) for j in jobs]
+    t_host = time.perf_counter() - t0
+    if U_init is None:
+        U_init = initial_field(init_params)
+    assert U_init.shape == (init_params.N, init_params.N)
+    out = []
+    t_dev = 0.0
+    for c0 in range(0, len(members), batch_max):
+        chunk = list(range(c0, min(c0 + batch_max, len(members))))
+        sols, structs = [], []
+        for i in chunk:
+            p = members[i][0]
+            p.kappa_tilde = scal[i][0]                 # computed in the pool; Solution() will not redo it
+            s = Solution(p)
+            sols.append(s)
+            structs.append(make_params_struct(p, s))
+        td = time.perf_counter()
+        st = BatchStepper(init_params.N, structs, rows_cap=max(poll_every, 16), backend=backend, device=device)
+        st.set_U(U_init)
+        row0 = st.prepare()
+        iters = max(init_params.ntmax, 0) - 1          # first solve_or_resume call: ntmax-1 iterations (Q3)
+        rows, _ = st.run(iters, poll_every=poll_every)
+        fields = st.get_U() if keep_fields else None
+        states = [st.get_state(j) for j in range(len(chunk))]
+        t_dev += time.perf_counter() - td
+        for j, i in enumerate(chunk):
+            p, f0, f1 = members[i]
+            data = TimeData(capacity=len(rows[j]) + 1)
+            data.extend(row0[j][None, :])
+            sol = sols[j]
+            sol.timedata = data
+            s_ = states[j]
+            sol.computed_steps = int(s_.computed_steps)
+            sol.tau0 = int(s_.tau0) if s_.tau0 != 0 else 0.0
+            sol.t0 = float(s_.t0)
+            sol.stop_reason = {0: 'None', 1: 'energy', 2: 'time-limit'}.get(s_.stop_reason, 'None')
+            if fields is not None:
+                sol.U = fields[j]
+            data.extend(rows[j])                       # AssertionError on NaN, as the reference would
+            kappa, ca, cb, sa, sb = scal[i]
+            tup = (sol.A0, sol.A1, ca, cb, sa, sb, sol.tau0, sol.t0, int(np.argmax(sol.E2)), run_ids[i], f0, f1)
+            out.append({"tuple": tup, "solution": sol, "params": p, "run_id": run_ids[i]})
+        del st
+    if timings is not None:
+        timings.update(host_scalars_s=t_host, device_s=t_dev, host_procs=nproc)
+    return out
+
+
+_EXPORT_JOBS = None      # fork-inherited (Solution objects hold lambdas and cannot be pickled)
+
+
+def _export_member(index):
+    """Per-run files of reference simulator.py:135-156 (yaml scalars + csv matrices)."""
+    fname_sol, yaml_on, export_csv, compress, sol = _EXPORT_JOBS[index]
+    if yaml_on:
+        sol.yaml_export_scalars(fname=fname_sol + '.yaml')
+    if export_csv is not None:
+        fext = 'csv.bz2' if compress else 'csv'
+        for member in export_csv.replace(' ', '').split(','):
+            arr = getattr(sol, member, None)
+            if isinstance(arr, np.ndarray):
+                utils.csv_export_matrix(arr, fname=f"{fname_sol}.{member}.{fext}")
+    return fname_sol
+
+
+def main(argv=None):
+    import pandas as pd
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    parser = ExperimentCLIParser()
+    if rank == 0:
+        parser.cliparser.print_info()
+    ep, init_params = parser.get_parameters(argv)
+    if init_params.file_id is None or init_params.file_id == 'auto':
+        init_params.file_id = utils.get_or_create_file_id(init_params.file_id)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")               # control plane only: gathers result tuples
+        fid = [init_params.file_id]
+        dist.broadcast_object_list(fid, src=0)
+        init_params.file_id = fid[0]
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    rand_values, A_list, n_items = factor_table(ep)
+    if rank == 0:
+        print(str(init_params).replace(", '", "\n '"))
+        utils_meta = [f"runs, {ep.runs}", f"A_source, {ep.A_source}", f"A_seed, {ep.A_seed}",
+                      f"independent, {ep.independent}", f"world_size, {world}",
+                      f"localtime, {utils.get_current_localtime()}", f"argv, '{' '.join(sys.argv)}'"]
+        with open(f"{init_params.file_id}-metadata.csv", 'w') as f:
+            f.write("\n".join(utils_meta))
+    mine = shard(n_items, rank, world)
+    tm = {}
+    t0 = time.perf_counter()
+    res = solve_ensemble(init_params, rand_values, A_list, run_ids=mine,
+                         host_procs=None if ep.processes == -1 else max(1, ep.processes), timings=tm)
+    t_solve = time.perf_counter() - t0
+    if not ep.no_export:
+        jobs = [(f"{r['params'].file_id}.solution", init_params.yaml, init_params.export_csv,
+                 init_params.compress_csv, r["solution"]) for r in res]
+        global _EXPORT_JOBS
+        _EXPORT_JOBS = jobs
+        nproc = max(1, min(len(jobs), utils.get_number_physical_cores() or 1))
+        if nproc > 1:
+            with mp.get_context("fork").Pool(nproc) as pool:
+                pool.map(_export_member, range(len(jobs)))
+        else:
+            for j in range(len(jobs)):
+                _export_member(j)
+        _EXPORT_JOBS = None
+    tuples = [r["tuple"] for r in res]
+    if world > 1:
+        import torch.distributed as dist
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(tuples, gathered, dst=0)
+        if rank == 0:
+            tuples = [t for part in gathered for t in part]
+        dist.barrier()
+    if rank == 0:
+        df = pd.DataFrame(tuples, columns=RESULT_COLUMNS)
+        df[['tau0', 'id']] = df[['tau0', 'id']].astype(int)
+        df.to_csv(f"{init_params.file_id}-results.csv")
+        agg = df.loc[:, df.columns != 'id'].describe()
+        agg.loc['cv'] = agg.loc['std'] / agg.loc['mean']
+        print(agg.T)
+        agg.T.to_csv(f"{init_params.file_id}-results-agg.csv")
+        print(f"members: {len(tuples)} on {world} GPU(s); rank-0 solve {t_solve:.2f} s "
+              f"(host sympy {tm.get('host_scalars_s', 0):.2f} s on {tm.get('host_procs')} procs, "
+              f"device {tm.get('device_s', 0):.2f} s)")
+        print('Output files:')
+        for suffix in ('metadata', 'results-agg', 'results'):
+            print(f"  {init_params.file_id}-{suffix}.csv")
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

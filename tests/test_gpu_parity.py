@@ -197,3 +197,28 @@ def test_properties_full_size():
     assert np.abs(back - U).max() < 1e-14
     # Parseval: orthonormal transform keeps the Frobenius norm
     assert abs(np.linalg.norm(y[0]) - np.linalg.norm(U[0])) < 1e-10
+
+
+def test_ensemble_corners_and_centre():
+    """experiment.py path: 5 members in lock-step (4 corners + centre), each with its own sympy
+    kappa_tilde, stop step, t0, tsep and c_A/c_B -- against the reference's single runs."""
+    import chsimpy_b200 as ch
+    from chsimpy_b200 import experiment as ex
+    rv = np.array([[0.995, 0.995], [0.995, 1.005], [1.005, 0.995], [1.005, 1.005], [1.0, 1.0]])
+    names = ["n512_corner_lo_lo", "n512_corner_lo_hi", "n512_corner_hi_lo", "n512_corner_hi_hi", "n512_stop"]
+    p = ch.Parameters()
+    p.no_gui = True
+    p.file_id = "ens"
+    res = ex.solve_ensemble(p, rv, None)
+    for r, name in zip(res, names):
+        z, m = load(name)
+        sol = r["solution"]
+        assert sol.kappa_tilde == m["kappa_tilde"]
+        assert (sol.tau0, sol.computed_steps, sol.stop_reason) == (m["tau0"], m["computed_steps"], m["stop_reason"])
+        assert abs(sol.t0 - m["t0"]) <= 1e-12 * m["t0"]
+        assert r["tuple"][8] == m["argmax_E2"] and r["tuple"][9] == r["run_id"]
+        check_rows(sol.timedata.data(), z["rows"], 512)
+        st = 8
+        assert np.abs(sol.U[::st, ::st] - z["U_sample"]).max() <= U_TOL
+    ca, cb = res[4]["tuple"][2], res[4]["tuple"][3]
+    assert abs(ca - 0.8121353) < 5e-7 and abs(cb - 0.9723917) < 5e-7
