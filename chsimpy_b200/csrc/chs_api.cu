@@ -33,6 +33,8 @@ struct chs_solver {
     double2* tw;
     double2* om;
     double* lam;
+    double* gsin;
+    int* kof;
     double2* logtab;
     int* index;
     double* mean;
@@ -77,7 +79,7 @@ static int drain_events(chs_solver* s) {
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t sims, part, colpart, tw, om, lam, logtab, index, mean, total;
+    size_t sims, part, colpart, tw, om, lam, gsin, kof, logtab, index, mean, total;
 };
 static Layout layout(int N, int batch) {
     Layout L;
@@ -89,6 +91,8 @@ static Layout layout(int N, int batch) {
     L.tw = o; o = align_up(o + sizeof(double2) * (size_t)(N / 2));
     L.om = o; o = align_up(o + sizeof(double2) * (size_t)N);
     L.lam = o; o = align_up(o + sizeof(double) * (size_t)N);
+    L.gsin = o; o = align_up(o + sizeof(double) * (size_t)N);
+    L.kof = o; o = align_up(o + sizeof(int) * (size_t)N);
     L.logtab = o; o = align_up(o + sizeof(double2) * (size_t)LOG_TABLE_N);
     L.index = o; o = align_up(o + sizeof(int) * (size_t)batch);
     L.mean = o; o = align_up(o + sizeof(double) * (size_t)batch);
@@ -143,6 +147,7 @@ static KArgs base_args(chs_solver* s) {
     a.rows = s->rows; a.rows_cap = s->rows_cap;
     a.part = s->part; a.colpart = s->colpart;
     a.tw = s->tw; a.om = s->om; a.lam = s->lam; a.logtab = s->logtab;
+    a.gsin = s->gsin; a.kof = s->kof;
     a.mean_host = s->mean;
     return a;
 }
@@ -167,6 +172,8 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     s->om = (double2*)(w + L.om);
     s->lam = (double*)(w + L.lam);
     s->logtab = (double2*)(w + L.logtab);
+    s->gsin = (double*)(w + L.gsin);
+    s->kof = (int*)(w + L.kof);
     s->index = (int*)(w + L.index);
     s->mean = (double*)(w + L.mean);
     s->hsims.assign(batch, Sim());
@@ -189,6 +196,26 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
         const long double a = -pi * m / (2.0L * N);
         om[m] = make_double2((double)cosl(a), (double)sinl(a));
     }
+    // gradient-energy weights sin^2(pi k/N) and the slot -> frequency map of the FFT plan
+    std::vector<double> gs(N);
+    for (int k = 0; k < N; ++k) {
+        const long double sn = sinl(pi * k / N);
+        gs[k] = (double)(sn * sn);
+    }
+    std::vector<int> kof(N);
+    {
+        std::vector<int> rad;                       // same plan as Rad<M> (dct_core.cuh)
+        int lg = 0;
+        while ((1 << lg) < M) ++lg;
+        if (lg % 3) rad.push_back(1 << (lg % 3));
+        for (int i = 0; i < lg / 3; ++i) rad.push_back(8);
+        for (int k = 0; k < M; ++k) {
+            int pos = 0, Lb = M, kk = k;
+            for (int r : rad) { pos += (kk % r) * (Lb / r); kk /= r; Lb /= r; }
+            kof[2 * pos] = k;
+            kof[2 * pos + 1] = (k == 0) ? M : N - k;
+        }
+    }
     // fast_log table (fastlog.cuh): sub-interval centres of [0.6875, 1.375) in bit-pattern space
     std::vector<double2> lt(LOG_TABLE_N);
     for (int i = 0; i < LOG_TABLE_N; ++i) {
@@ -204,6 +231,8 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     ok &= cudaMemsetAsync(workspace, 0, L.total, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->tw, tw.data(), sizeof(double2) * M, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->om, om.data(), sizeof(double2) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->gsin, gs.data(), sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->index, s->hindex.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
@@ -352,11 +381,9 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
     const dim3 grid(G::NTILES, s->n_running), block(G::NT);
     for (long long it = 0; it < n_iters; ++it) {
         a.last = (last && it == n_iters - 1) ? 1 : 0;
-        a.iter_in_call = (int)it;
         if (noise) {
             a.noise = noise + (size_t)it * N * N;
             a.noise_mean = noise_mean + it;
-            a.store_U = 1;
         }
         if (s->timing) {
             if (s->ev_used + 4 > 65536 && drain_events(s)) return -1;
@@ -446,10 +473,10 @@ static int do_dctn(chs_solver* s, const double* in, double* out, bool inverse) {
     if (!inverse) {
         a.src = in; a.dst = nullptr;
         CHS_LAUNCH((k_row<N, ROW_FWD_U>), grid, block, G::SMEM_BYTES, s->stream, a);  // in -> T
-        a.src = nullptr; a.dst = out;
+        a.src = nullptr; a.dst = out; a.natural = 1;
         CHS_LAUNCH((k_col<N, COL_FWD>), grid, block, G::SMEM_BYTES, s->stream, a);    // T -> out
     } else {
-        a.src = in; a.dst = nullptr;
+        a.src = in; a.dst = nullptr; a.natural = 1;
         CHS_LAUNCH((k_col<N, COL_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // in -> T
         a.src = nullptr; a.dst = out;
         CHS_LAUNCH((k_row<N, ROW_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // T -> out

@@ -1,18 +1,33 @@
 // Kernels of the B200 Cahn-Hilliard stepper.  One time step of the reference loop
 // (chsimpy/solver.py:165-249) is two launches over the whole batch of simulations:
 //
-//   k_col<STEP> : per tile of 16 columns:  column DCT-II of T1 (= row-DCT of mu)
-//                 -> spectral update  hat_U = (hat_U + Seig*hat_mu)/CHeig  (solver.py:201-206,
+//   k_col<STEP> : per tile of 16 columns.  Column DCT-II of T (= row-DCT of mu), then -- in
+//                 registers, fused with the last forward and first inverse FFT stage -- the
+//                 spectral update  hat_U = (hat_U + Seig*hat_mu)/CHeig  (solver.py:201-206,
 //                 multipliers generated on the fly from the 1-D lambda table, utils.py:34-49)
-//                 -> column DCT-III -> T2, plus the y-part of the gradient energy
-//                 (Parseval over x: sum_x (d_y U)^2 == sum_kx (d_y T2)^2).
-//   k_row<STEP> : per tile of 16 rows:  row DCT-III of T2 -> U_new (solver.py:208)
-//                 [+ jitter, :210-211] -> x-gradient, free energy, PS, SA, Ra (:213-228)
-//                 -> chemical potential mu(U_new) of the NEXT step (:166-175)
-//                 -> row DCT-II -> T1.   The last CTA of a simulation then runs
-//                 step_control(): TimeData row (:231-240), NaN flag (timedata.py:10),
-//                 energy stop test (:242-249, timedata.py:63) and the "pre" part of the
-//                 next iteration: adaptive dt (:177-193), time accounting / limit (:195-199).
+//                 and the gradient energy in spectral form, then the column DCT-III -> T.
+//   k_row<STEP> : per tile of 16 rows.  Row DCT-III of T -> U_new (solver.py:208); the last
+//                 inverse stage, the per-element physics and the first forward stage of the
+//                 NEXT step's transform are one register-resident pass: free energy, PS, SA,
+//                 Ra (:213-228) and the chemical potential mu(U_new) (:166-175); then the row
+//                 DCT-II -> T.  The last CTA of a simulation runs step_control(): TimeData row
+//                 (:231-240), NaN flag (timedata.py:10), energy stop test (:242-249,
+//                 timedata.py:63) and the "pre" part of the next iteration: adaptive dt
+//                 (:177-193), time accounting / limit (:195-199).
+//
+// Gradient energy (np.gradient at solver.py:213-217) without a stencil pass: the DCT-II basis
+// is the half-sample even extension, for which
+//     sum_x (U[x+1]-U[x-1])^2 = sum_k 4 sin^2(pi k/N) C[k]^2     (DST-II orthogonality)
+// so  sum |grad U|^2 h^2 = sum_{ky,kx} (g[ky]+g[kx]) hat_U^2 + 3/4 * (one-sided edge terms),
+// g[k] = sin^2(pi k/N); the edge terms (np.gradient's first-order edges count 4x, the
+// extension 1x) come from U[.,0], U[.,1], U[.,N-2], U[.,N-1] (k_row) and the same rows of T
+// (k_col, Parseval along x).  With jitter the field is no longer the inverse transform of
+// hat_U; k_diag<JITTER> then evaluates every diagnostic from the stored U.
+//
+// Spectral column order: T and hat_U store the x-spectral axis in "slot" order -- slot
+// 2*pos(k) holds frequency k and slot 2*pos(k)+1 holds N-k (pos = digit reversal of the FFT
+// plan) -- which is exactly where the fused last stage leaves its results, so the row
+// kernels never reorder.  `kof[slot]` maps back to the frequency.
 //
 // U itself is not written per step (it is idctn(hat_U), materialised by chs_end) unless
 // jitter is on.  Everything is IEEE float64.
@@ -24,7 +39,9 @@
 namespace chs {
 
 // per-CTA partial sums, reduced in fixed order by the last CTA (deterministic)
-enum { P_GY2 = 0, P_GX2, P_F, P_ABS, P_MU2, P_CNT, P_SUMU, P_NSLOT };
+//   P_GE : raw gradient sum (spectral main part, or the direct stencil sum of k_diag)
+//   P_GYE / P_GXE : 3/4 * edge terms from k_col / k_row
+enum { P_GE = 0, P_GYE, P_GXE, P_F, P_ABS, P_MU2, P_CNT, P_NSLOT };
 
 // device-resident image of one simulation
 struct Sim {
@@ -46,8 +63,8 @@ struct KArgs {
     Sim* sims;
     const int* sim_index;        // blockIdx.y -> simulation (compacted list of running sims), or null
     double* U;                   // [batch][N][N]
-    double* hatU;
-    double* T;
+    double* hatU;                // [batch][N ky][N slots]
+    double* T;                   // [batch][N y][N slots]
     const double* src;           // stand-alone transforms: input  (else null)
     double* dst;                 //                         output
     double* rows;                // [batch][rows_cap][9]
@@ -57,74 +74,65 @@ struct KArgs {
     const double2* tw;           // exp(-2 pi i m / M), m < M
     const double2* om;           // exp(-i pi m / (2N)), m < N
     const double* lam;           // 2 cos(pi k/(N-1)) - 2
+    const double* gsin;          // sin^2(pi k / N)
+    const int* kof;              // slot -> frequency
     const double2* logtab;       // fast_log table {1/c, log c}
     const double* noise;         // [N][N] uniform draws of this step, or null
     const double* noise_mean;    // mean of that draw
     const double* mean_host;     // prepare: [batch] mean(U)
-    int store_U;                 // row step: write U_new to the U buffer
+    int natural;                 // stand-alone transforms: natural column order on the far side
     int last;                    // no "pre" part after this iteration
-    int iter_in_call;            // index of the iteration inside this chs_steps call
 };
 
 #ifdef CHS_EMU
 #define CHS_LDCG(p) (*(p))
+#define CHS_PREFETCH_L2(p) ((void)0)
 #else
 #define CHS_LDCG(p) __ldcg(p)
+#define CHS_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 
 // ---------------------------------------------------------------------------------------
-// Block reduction of NV doubles; result valid in thread 0.  GPU: warp shuffles then one
-// value per warp through shared memory, summed in fixed order.
+// Block sum of NV doubles; result valid in thread 0 AFTER the next __syncthreads() that the
+// caller executes anyway (split in two so that no extra barrier is spent on it):
+//   reduce_stage(): warp shuffles, lane 0 of every warp writes its sums to scratch
+//   reduce_final(): thread 0 adds the per-warp sums in fixed order
 template <int NV>
-CHS_DEV void block_reduce(double (&v)[NV], double* scratch, int tid, int nthreads) {
+CHS_DEV void reduce_stage(const double (&v)[NV], double* scratch, int tid) {
 #ifdef CHS_EMU
     for (int i = 0; i < NV; ++i) scratch[tid * NV + i] = v[i];
-    __syncthreads();
-    if (tid == 0) {
-        for (int i = 0; i < NV; ++i) {
-            double s = 0;
-            for (int j = 0; j < nthreads; ++j) s += scratch[j * NV + i];
-            v[i] = s;
-        }
-    }
-    __syncthreads();
 #else
+    double w[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double x = v[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        v[i] = x;
+        w[i] = x;
     }
-    const int warp = tid >> 5, lane = tid & 31, nw = (nthreads + 31) >> 5;
-    if (lane == 0) {
+    if ((tid & 31) == 0) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) scratch[warp * NV + i] = v[i];
+        for (int i = 0; i < NV; ++i) scratch[(tid >> 5) * NV + i] = w[i];
     }
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            double s = 0;
-            for (int w = 0; w < nw; ++w) s += scratch[w * NV + i];
-            v[i] = s;
-        }
-    }
-    __syncthreads();
 #endif
 }
+template <int NV>
+CHS_DEV void reduce_final(double (&v)[NV], const double* scratch, int nthreads) {
+#ifdef CHS_EMU
+    const int n = nthreads;
+#else
+    const int n = (nthreads + 31) >> 5;
+#endif
+    for (int i = 0; i < NV; ++i) {
+        double s = 0;
+        for (int j = 0; j < n; ++j) s += scratch[j * NV + i];
+        v[i] = s;
+    }
+}
 
-// scratch after the tile: [0,2) last-CTA flag | [2, 2+2*TPL) Ra partials | reduction scratch
-// (the host emulation needs NT*NV doubles there; emu::launch() allocates that slack)
-#define CHS_FLAG_PTR(G, sm) (reinterpret_cast<int*>((sm) + G::TILE_DOUBLES))
-#define CHS_RA_SCRATCH(G, sm) ((sm) + G::TILE_DOUBLES + 2)
-#define CHS_RED_SCRATCH(G, sm) ((sm) + G::TILE_DOUBLES + 2 + 2 * G::TPL + 2 * LOG_TABLE_N)
-#define CHS_LOGTAB(G, sm) (reinterpret_cast<double2*>((sm) + G::TILE_DOUBLES + 2 + 2 * G::TPL))
-
-// copies the 2 KB fast_log table into shared memory (visible after the next barrier)
 template <class G>
 CHS_DEV double2* stage_logtab(double* sm, const double2* __restrict__ g, int tid) {
-    double2* t = CHS_LOGTAB(G, sm);
+    double2* t = reinterpret_cast<double2*>(sm + G::OFF_LOGTAB);
     for (int i = tid; i < LOG_TABLE_N; i += G::NT) t[i] = g[i];
     return t;
 }
@@ -148,7 +156,6 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
                           int last, bool post, double* scratch, int tid, int nthreads) {
     using G = Geo<N>;
     constexpr int NTILES = G::NTILES;
-    // ---- adaptive column minimum (needs all threads) ----------------------------------
     // the test of solver.py:177-181 is made with the value computed_steps will have at the
     // start of the next iteration, i.e. after the increment below when post is true
     const long long cs_next = S->computed_steps + (post ? 1 : 0);
@@ -186,7 +193,8 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
         }
         const double N2 = (double)N * (double)N;
         const double L2sq = p.L * p.L;
-        const double E2 = 0.5 * p.Amr * p.kappa_tilde * L2sq * ((acc[P_GX2] + acc[P_GY2]) / N2);
+        const double grad2 = (acc[P_GE] + acc[P_GYE] + acc[P_GXE]) / (p.delx * p.delx);
+        const double E2 = 0.5 * p.Amr * p.kappa_tilde * L2sq * (grad2 / N2);
         const double E = p.Amr * L2sq * (acc[P_F] / N2) + E2;
         const double PS = acc[P_ABS] / N2;
         const double L2 = sqrt(S->mu2_pending) / N2;
@@ -223,8 +231,7 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
             }
             S->skip_check = 1;
         }
-    }
-    else {                                            // prologue (chs_begin): only ||mu||^2 is new
+    } else {                                          // prologue (chs_begin): only ||mu||^2 is new
         double a2 = 0;
         for (int tl = 0; tl < NTILES; ++tl) a2 += CHS_LDCG(part + P_MU2 * NTILES + tl);
         S->mu2_pending = a2;
@@ -245,11 +252,13 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
     }
 }
 
-// ticket: returns true in every thread of the last CTA of this simulation
-CHS_DEV bool last_cta(Sim* S, int ntiles, int* flag_smem, int tid) {
-    __threadfence();
+// ticket: returns true in every thread of the last CTA of this simulation.  `all_wrote`:
+// threads other than 0 have written global data that the last CTA must see.
+CHS_DEV bool last_cta(Sim* S, int ntiles, int* flag_smem, int tid, bool all_wrote) {
+    if (all_wrote) __threadfence();
     __syncthreads();
     if (tid == 0) {
+        __threadfence();
         const unsigned prev = atomicAdd(&S->ticket, 1u);
         const int lastf = (prev == (unsigned)(ntiles - 1));
         if (lastf) S->ticket = 0;
@@ -260,42 +269,87 @@ CHS_DEV bool last_cta(Sim* S, int ntiles, int* flag_smem, int tid) {
     return *flag_smem != 0;
 }
 
-
 // ---------------------------------------------------------------------------------------
-// Tile I/O.  Loads are issued in independent batches of 8 per thread before the first use
-// (memory-level parallelism), then scattered into the tile.
-//   column tile: all N rows x LINES adjacent columns of a row-major N x N array
-//   row tile   : LINES adjacent rows
-// PHYS = the array index along the line is a physical coordinate (Makhoul position in smem),
-// otherwise it is a spectral index stored at its natural position.
-template <int N, bool PHYS>
-CHS_DEV int line_pos(int n) { return PHYS ? mk_pos<N>(n) : n; }
+// Tile I/O (loads batched before first use).
+// column tile: all N rows x 16 adjacent slots, physical y -> Makhoul position, one complex
+// element (two rows) per thread and step.
+template <int N>
+CHS_DEV void col_pair_rows(int c, int& y0, int& y1) {      // rows holding v[2c], v[2c+1]
+    constexpr int M = N / 2;
+    if (2 * c < M) { y0 = 4 * c; y1 = 4 * c + 2; }
+    else { y0 = 2 * (N - 1 - 2 * c) + 1; y1 = y0 - 2; }
+}
 
-template <int N, bool PHYS>
-CHS_DEV void col_tile_load(double* sm, const double* __restrict__ g, int l, int t) {
+template <int N>
+CHS_DEV void col_tile_load(double2* scl, const double* __restrict__ g, int t) {
     using G = Geo<N>;
-    constexpr int CNT = N / G::TPL, UNR = 8;
+    constexpr int UNR = 4;
 #pragma unroll
-    for (int j0 = 0; j0 < CNT; j0 += UNR) {
-        double v[UNR];
+    for (int j0 = 0; j0 < 16; j0 += UNR) {
+        double a[UNR], b[UNR];
 #pragma unroll
-        for (int j = 0; j < UNR; ++j) v[j] = g[(size_t)(t + (j0 + j) * G::TPL) * N + l];
+        for (int j = 0; j < UNR; ++j) {
+            int y0, y1;
+            col_pair_rows<N>(t + (j0 + j) * G::TPL, y0, y1);
+            a[j] = g[(size_t)y0 * N];
+            b[j] = g[(size_t)y1 * N];
+        }
 #pragma unroll
-        for (int j = 0; j < UNR; ++j) sm[line_pos<N, PHYS>(t + (j0 + j) * G::TPL) * G::LP + l] = v[j];
+        for (int j = 0; j < UNR; ++j) scl[(t + (j0 + j) * G::TPL) * G::LPC] = make_double2(a[j], b[j]);
     }
 }
 
-template <int N, bool PHYS>
-CHS_DEV void col_tile_store(const double* sm, double* __restrict__ g, int l, int t) {
+template <int N>
+CHS_DEV void col_tile_store(const double2* scl, double* __restrict__ g, int t) {
     using G = Geo<N>;
-    constexpr int CNT = N / G::TPL;
-#pragma unroll 8
-    for (int j = 0; j < CNT; ++j)
-        g[(size_t)(t + j * G::TPL) * N + l] = sm[line_pos<N, PHYS>(t + j * G::TPL) * G::LP + l];
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+        const int c = t + j * G::TPL;
+        int y0, y1;
+        col_pair_rows<N>(c, y0, y1);
+        const double2 v = scl[c * G::LPC];
+        g[(size_t)y0 * N] = v.x;
+        g[(size_t)y1 * N] = v.y;
+    }
 }
 
-template <int N, bool PHYS>
-CHS_DEV void row_tile_load(double* sm, const double* __restrict__ g, int tid) {
+// row tile in slot order: one complex element = two adjacent slots = one 16-byte access
+template <int N>
+CHS_DEV void row_tile_load_slots(double2* sc, const double* __restrict__ g, int tid) {
+    using G = Geo<N>;
+    constexpr int M = G::M, CNT = G::LINES * M / G::NT, UNR = 8;       // CNT = 16
+    const double2* g2 = reinterpret_cast<const double2*>(g);
+#pragma unroll
+    for (int j0 = 0; j0 < CNT; j0 += UNR) {
+        double2 v[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int i = tid + (j0 + j) * G::NT;
+            v[j] = g2[(size_t)(i / M) * M + (i % M)];
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int i = tid + (j0 + j) * G::NT;
+            sc[(i % M) * G::LPC + (i / M)] = v[j];
+        }
+    }
+}
+
+template <int N>
+CHS_DEV void row_tile_store_slots(const double2* sc, double* __restrict__ g, int tid) {
+    using G = Geo<N>;
+    constexpr int M = G::M, CNT = G::LINES * M / G::NT;
+    double2* g2 = reinterpret_cast<double2*>(g);
+#pragma unroll 8
+    for (int j = 0; j < CNT; ++j) {
+        const int i = tid + j * G::NT;
+        g2[(size_t)(i / M) * M + (i % M)] = sc[(i % M) * G::LPC + (i / M)];
+    }
+}
+
+// row tile of a physical field (U): x -> Makhoul position (cold paths only)
+template <int N>
+CHS_DEV void row_tile_load_phys(double* sm, const double* __restrict__ g, int tid) {
     using G = Geo<N>;
     constexpr int CNT = G::LINES * N / G::NT, UNR = 8;
 #pragma unroll
@@ -309,21 +363,137 @@ CHS_DEV void row_tile_load(double* sm, const double* __restrict__ g, int tid) {
 #pragma unroll
         for (int j = 0; j < UNR; ++j) {
             const int i = tid + (j0 + j) * G::NT;
-            sm[line_pos<N, PHYS>(i % N) * G::LP + (i / N)] = v[j];
+            sm[real_off<N>(mk_pos<N>(i % N)) + 2 * (i / N)] = v[j];
         }
     }
 }
 
-template <int N, bool PHYS>
-CHS_DEV void row_tile_store(const double* sm, double* __restrict__ g, int tid) {
+template <int N>
+CHS_DEV void row_tile_store_phys(const double* sm, double* __restrict__ g, int tid) {
     using G = Geo<N>;
     constexpr int CNT = G::LINES * N / G::NT;
 #pragma unroll 8
     for (int j = 0; j < CNT; ++j) {
         const int i = tid + j * G::NT;
-        g[(size_t)(i / N) * N + (i % N)] = sm[line_pos<N, PHYS>(i % N) * G::LP + (i / N)];
+        g[(size_t)(i / N) * N + (i % N)] = sm[real_off<N>(mk_pos<N>(i % N)) + 2 * (i / N)];
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// The 8 work items of a thread in the fused last stage.  A/B = the two 8-point blocks
+// (natural order within the block: frequency rho + (M/8)*c).  f.special(...) couples Z[0]
+// with Z[M/2]; f.pair(k, X, Y) couples Z[k] (X) with Z[M-k] (Y), always with k < M/2.
+template <int N, class F>
+CHS_DEV void for_each_item(int t, int rho_a, int rho_b, double (&ar)[8], double (&ai)[8], double (&br)[8],
+                           double (&bi)[8], F& f) {
+    constexpr int Q = N / 16;                       // M/8
+    if (t == 0) {
+        f.special(ar[0], ai[0], ar[4], ai[4]);
+        f.pair(Q * 1, ar[1], ai[1], ar[7], ai[7]);
+        f.pair(Q * 2, ar[2], ai[2], ar[6], ai[6]);
+        f.pair(Q * 3, ar[3], ai[3], ar[5], ai[5]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f.pair(rho_b + Q * i, br[i], bi[i], br[7 - i], bi[7 - i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f.pair(rho_a + Q * i, ar[i], ai[i], br[7 - i], bi[7 - i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f.pair(rho_b + Q * i, br[i], bi[i], ar[7 - i], ai[7 - i]);
+    }
+}
+
+template <int N>
+CHS_DEV void load_block(const double2* scl, int base, double (&xr)[8], double (&xi)[8]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double2 v = scl[(base + c) * Geo<N>::LPC];
+        xr[c] = v.x; xi[c] = v.y;
+    }
+}
+template <int N>
+CHS_DEV void store_block(double2* scl, int base, const double (&xr)[8], const double (&xi)[8]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) scl[(base + c) * Geo<N>::LPC] = make_double2(xr[c], xi[c]);
+}
+
+// in-place slot convention of the row kernels: element pos(k) = (C[k], C[N-k])
+template <int N>
+struct RowPost {
+    const double2* om;
+    CHS_MEM void special(double& ar, double& ai, double& hr, double& hi) {
+        double c[4];
+        post_special<N>(om, ar, ai, hr, hi, c);
+        ar = c[0]; ai = c[1]; hr = c[2]; hi = c[3];
+    }
+    CHS_MEM void pair(int k, double& xr, double& xi, double& yr, double& yi) {
+        double c[4];
+        post_pair<N>(k, om, xr, xi, yr, yi, c);
+        xr = c[0]; xi = c[1]; yr = c[2]; yi = c[3];
+    }
+};
+template <int N>
+struct RowPre {
+    const double2* om;
+    CHS_MEM void special(double& ar, double& ai, double& hr, double& hi) {
+        const double c[4] = {ar, ai, hr, hi};
+        pre_special<N>(om, c, ar, ai, hr, hi);
+    }
+    CHS_MEM void pair(int k, double& xr, double& xi, double& yr, double& yi) {
+        const double c[4] = {xr, xi, yr, yi};
+        pre_pair<N>(k, om, c, xr, xi, yr, yi);
+    }
+};
+
+// column kernels: the C values go to / come from global hat_U rows {k, N-k, M-k, M+k}
+template <int N, int MODE>
+struct ColMid {
+    const double2* om;
+    const double* lam;
+    const double* gsin;
+    double* hat;                 // + column
+    const double* hat_in;        // + column (COL_INV)
+    double lam1, lam2, lamx, gx;
+    double ge;
+    CHS_MEM void apply(const int (&idx)[4], double (&c)[4]) {
+        if (MODE == COL_FWD) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hat[(size_t)idx[j] * N] = c[j];
+        } else if (MODE == COL_STEP) {
+            double h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = hat[(size_t)idx[j] * N];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double leig = __ldg(lam + idx[j]) + lamx;
+                const double Se = __dmul_rn(lam1, leig);
+                const double CH = __dadd_rn(1.0, __dmul_rn(__dmul_rn(lam2, leig), leig));
+                const double hu = __ddiv_rn(__dadd_rn(h[j], __dmul_rn(Se, c[j])), CH);
+                hat[(size_t)idx[j] * N] = hu;
+                ge += (__ldg(gsin + idx[j]) + gx) * (hu * hu);
+                c[j] = hu;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = hat_in[(size_t)idx[j] * N];
+        }
+    }
+    CHS_MEM void special(double& ar, double& ai, double& hr, double& hi) {
+        constexpr int M = N / 2;
+        const int idx[4] = {0, M, M / 2, M + M / 2};
+        double c[4];
+        if (MODE != COL_INV) post_special<N>(om, ar, ai, hr, hi, c);
+        apply(idx, c);
+        if (MODE != COL_FWD) pre_special<N>(om, c, ar, ai, hr, hi);
+    }
+    CHS_MEM void pair(int k, double& xr, double& xi, double& yr, double& yi) {
+        constexpr int M = N / 2;
+        const int idx[4] = {k, N - k, M - k, M + k};
+        double c[4];
+        if (MODE != COL_INV) post_pair<N>(k, om, xr, xi, yr, yi, c);
+        apply(idx, c);
+        if (MODE != COL_FWD) pre_pair<N>(k, om, c, xr, xi, yr, yi);
+    }
+};
 
 // =======================================================================================
 //  column kernel
@@ -331,92 +501,117 @@ CHS_DEV void row_tile_store(const double* sm, double* __restrict__ g, int tid) {
 template <int N, int MODE>
 CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_col(KArgs a) {
     using G = Geo<N>;
-    constexpr int M = G::M, LP = G::LP, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
+    constexpr int M = G::M, LINES = G::LINES, NT = G::NT;
+    constexpr int NST = Rad<M>::nst;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    double2* sc = reinterpret_cast<double2*>(sm);
     const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
     const int sim = a.sim_index ? a.sim_index[blockIdx.y] : (int)blockIdx.y;
     const int tile = blockIdx.x, kx0 = tile * LINES;
     Sim* S = a.sims + sim;
     if (MODE == COL_STEP && S->halted) return;
     const size_t off = (size_t)sim * N * N;
-    double* sl = sm + l;
-
-    // -------- load + forward column DCT-II
-    if (MODE != COL_INV) {
-        col_tile_load<N, true>(sm, a.T + off + kx0, l, t);
-        __syncthreads();
-        fft_fwd<N>(sl, t, a.tw);
+    double2* scl = sc + l;
+    const int col = (MODE != COL_STEP && a.natural) ? a.kof[kx0 + l] : kx0 + l;   // far-side column
+    if (MODE == COL_STEP) {
+        // the hat_U tile is consumed in the middle of the kernel: pull it into L2 now
+        const double* hp = a.hatU + off + kx0;
+        for (int y = tid; y < N; y += NT) CHS_PREFETCH_L2(hp + (size_t)y * N);
     }
-    // -------- spectral middle section (registers <-> global, lanes along kx)
+    // -------- load + forward column DCT-II up to the last stage
+    if (MODE != COL_INV) {
+        col_tile_load<N>(scl, a.T + off + kx0 + l, t);
+        __syncthreads();
+        fft_fwd_range<N, 0, NST - 1>(scl, t, a.tw);
+    }
+    // -------- fused: last forward stage + post + spectral update + pre + first inverse stage
     {
-        double* hat = (MODE == COL_FWD && a.dst) ? a.dst + off : a.hatU + off;
-        const double* hat_in = (MODE == COL_INV && a.src) ? a.src + off : a.hatU + off;
-        double lam1 = 0, lam2 = 0, lamx = 0;
+        int rho_a, rho_b, base_a, base_b;
+        unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+        double ar[8], ai[8], br[8], bi[8];
+        if (MODE != COL_INV) {
+            load_block<N>(scl, base_a, ar, ai);
+            load_block<N>(scl, base_b, br, bi);
+            dft<8, false>(ar, ai);
+            dft<8, false>(br, bi);
+        }
+        ColMid<N, MODE> mid;
+        mid.om = a.om; mid.lam = a.lam; mid.gsin = a.gsin;
+        mid.hat = ((MODE == COL_FWD && a.dst) ? a.dst : a.hatU) + off + col;
+        mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + off + col;
+        mid.ge = 0; mid.lam1 = mid.lam2 = mid.lamx = mid.gx = 0;
         if (MODE == COL_STEP) {
             const double delx2 = S->p.delx * S->p.delx;
-            lam1 = S->delt_coef / delx2;                  // utils.py:41-42
-            lam2 = S->p.kappa_tilde * lam1 / delx2;
-            lamx = a.lam[kx0 + l];
+            mid.lam1 = S->delt_coef / delx2;                  // utils.py:41-42
+            mid.lam2 = S->p.kappa_tilde * mid.lam1 / delx2;
+            const int kx = a.kof[kx0 + l];
+            mid.lamx = a.lam[kx];
+            mid.gx = a.gsin[kx];
         }
-#pragma unroll
-        for (int k0 = 0; k0 < M / 2; k0 += TPL) {
-            const int k = k0 + t;
-            if (M / 2 < TPL && k >= M / 2) break;
-            int idx[4];
-            item_index<N>(k, idx);
-            double c[4];
-            if (MODE != COL_INV) post_item<N>(sl, k, a.om, c);
-            if (MODE == COL_FWD) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) hat[(size_t)idx[j] * N + kx0 + l] = c[j];
-            } else if (MODE == COL_STEP) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const size_t g = (size_t)idx[j] * N + kx0 + l;
-                    const double leig = a.lam[idx[j]] + lamx;
-                    const double Se = __dmul_rn(lam1, leig);
-                    const double CH = __dadd_rn(1.0, __dmul_rn(__dmul_rn(lam2, leig), leig));
-                    const double hu = __ddiv_rn(__dadd_rn(hat[g], __dmul_rn(Se, c[j])), CH);
-                    hat[g] = hu;
-                    c[j] = hu;
-                }
-                pre_item<N>(sl, k, a.om, c);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) c[j] = hat_in[(size_t)idx[j] * N + kx0 + l];
-                pre_item<N>(sl, k, a.om, c);
-            }
+        for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, mid);
+        if (MODE == COL_FWD) return;
+        dft<8, true>(ar, ai);
+        dft<8, true>(br, bi);
+        store_block<N>(scl, base_a, ar, ai);
+        store_block<N>(scl, base_b, br, bi);
+        if (MODE == COL_STEP) {
+            const double v[1] = {mid.ge};
+            reduce_stage<1>(v, sm + G::OFF_RED, tid);
         }
     }
-    if (MODE == COL_FWD) return;
     __syncthreads();
-    // -------- inverse column DCT-III
-    fft_inv<N>(sl, t, a.tw);
-    // -------- y-part of the gradient energy on T2 (np.gradient along axis 0, solver.py:213)
-    if (MODE == COL_STEP) {
-        constexpr int YPT = N / TPL;
-        const int y0 = t * YPT;
-        const double ih = 1.0 / S->p.delx, ih2 = 0.5 / S->p.delx;
-        double prev = (y0 > 0) ? sl[mk_pos<N>(y0 - 1) * LP] : 0.0;
-        double cur = sl[mk_pos<N>(y0) * LP];
-        double acc = 0;
-#pragma unroll 4
-        for (int y = y0; y < y0 + YPT; ++y) {
-            const double nxt = (y + 1 < N) ? sl[mk_pos<N>(y + 1) * LP] : 0.0;
-            double g;
-            if (y == 0) g = (nxt - cur) * ih;
-            else if (y == N - 1) g = (cur - prev) * ih;
-            else g = (nxt - prev) * ih2;
-            acc += g * g;
-            prev = cur; cur = nxt;
+    // -------- remaining inverse stages
+    fft_inv_range<N, 0, NST - 1>(scl, t, a.tw);
+    // -------- partial sums: spectral gradient energy + one-sided y-edge terms (rows 0,1,N-2,N-1 of T)
+    if (MODE == COL_STEP && tid == 0) {
+        double v[1];
+        reduce_final<1>(v, sm + G::OFF_RED, NT);
+        double e = 0;
+        for (int l2 = 0; l2 < LINES; ++l2) {
+            const double u0 = sm[real_off<N>(mk_pos<N>(0)) + 2 * l2], u1 = sm[real_off<N>(mk_pos<N>(1)) + 2 * l2];
+            const double v0 = sm[real_off<N>(mk_pos<N>(N - 1)) + 2 * l2], v1 = sm[real_off<N>(mk_pos<N>(N - 2)) + 2 * l2];
+            e += (u1 - u0) * (u1 - u0) + (v0 - v1) * (v0 - v1);
         }
-        double v[1] = {acc};
-        block_reduce<1>(v, CHS_RED_SCRATCH(G, sm), tid, NT);
-        if (tid == 0) a.part[((size_t)sim * P_NSLOT + P_GY2) * G::NTILES + tile] = v[0];
+        double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
+        pp[P_GE * G::NTILES] = v[0];
+        pp[P_GYE * G::NTILES] = 0.75 * e;
     }
-    // -------- store T2 tile
-    col_tile_store<N, true>(sm, a.T + off + kx0, l, t);
+    // -------- store T tile
+    col_tile_store<N>(scl, a.T + off + kx0 + l, t);
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-element physics on the 2*R real values of one radix-R butterfly of stage 0
+// (positions c_q = j + q*st, re = v[2c], im = v[2c+1]):  U -> mu in place, sums in acc.
+struct RowAcc {
+    double f, ab, mu2, cnt, ra;
+};
+template <int N, int R>
+CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const chs_params& p, const double2* ltab,
+                     bool diag, double meanU, bool ra_line, double ra_mean, RowAcc& acc, double* edge /* line's 4 */) {
+    constexpr int st = (N / 2) / R;
+    if (diag) {
+        if (j == 0) { edge[0] = xr[0]; edge[3] = xr[R / 2]; }                 // U[0], U[N-1]
+        if (j == st - 1) { edge[1] = xi[R - 1]; edge[2] = xi[R / 2 - 1]; }    // U[1], U[N-2]
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double u = h ? xi[q] : xr[q];
+            double f, mu;
+            thermo(u, p, ltab, f, mu);
+            if (diag) {
+                acc.f += f;
+                acc.ab += fabs(u - meanU);
+                acc.cnt += (u < p.threshold) ? 1.0 : 0.0;
+                if (ra_line) acc.ra += fabs(u - ra_mean);
+            }
+            acc.mu2 += mu * mu;
+            if (h) xi[q] = mu; else xr[q] = mu;
+        }
+    }
 }
 
 // =======================================================================================
@@ -425,209 +620,209 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_col(KArgs a) {
 template <int N, int MODE>
 CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_row(KArgs a) {
     using G = Geo<N>;
-    constexpr int M = G::M, LP = G::LP, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
-    constexpr int IPT = (M / 2 + TPL - 1) / TPL;
+    constexpr int M = G::M, LPC = G::LPC, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
+    constexpr int NST = Rad<M>::nst;
+    constexpr int R0 = Rad<M>::radix(0), ST0 = M / R0, NB0 = 16 / R0;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
-    double* ra_scr = CHS_RA_SCRATCH(G, sm);                // 2*TPL doubles
-    int* flag = CHS_FLAG_PTR(G, sm);
+    double2* sc = reinterpret_cast<double2*>(sm);
+    int* flag = reinterpret_cast<int*>(sm + G::OFF_FLAG);
+    double* edge = sm + G::OFF_EDGE;
+    double* ra_scr = sm + G::OFF_RA;
     const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
     const int sim = a.sim_index ? a.sim_index[blockIdx.y] : (int)blockIdx.y;
     const int tile = blockIdx.x, row0 = tile * LINES;
     Sim* S = a.sims + sim;
     if (MODE == ROW_STEP && S->halted) return;
     const size_t off = (size_t)sim * N * N;
-    double* sl = sm + l;
+    double2* scl = sc + l;
     const bool control = (MODE == ROW_STEP) || (MODE == ROW_FWD_MU);
+    const bool jit = (MODE == ROW_STEP) && (a.noise != nullptr);
+    const bool diag = (MODE == ROW_STEP) && !jit;
     const double2* ltab = control ? stage_logtab<G>(sm, a.logtab, tid) : nullptr;
+    const int ra_row = N / 2 + 1;                                           // int(N/2)+1, solver.py:226
+    const bool ra_line = diag && (row0 + l == ra_row);
+    const bool ra_tile = diag && (ra_row >= row0) && (ra_row < row0 + LINES);
+    bool slow = false;                      // adaptive-dt column sums / jitter / prologue: unfused middle
+    bool want_cols = false;
+    if (control) {
+        const long long cs_next = S->computed_steps + (MODE == ROW_STEP ? 1 : 0);
+        want_cols = S->p.adaptive_time && !a.last && cs_next > 500 && (cs_next % 2) == 0;
+        slow = want_cols || jit || (MODE == ROW_FWD_MU);
+    }
 
-    // ================= inverse half: T2 rows -> U rows (Makhoul order in smem)
+    // ================= inverse half: T rows (slot order) -> U rows (Makhoul order in smem)
     if (MODE == ROW_STEP || MODE == ROW_INV) {
-        const double* src = (MODE == ROW_INV && a.src) ? a.src + off : a.T + off;
-        row_tile_load<N, false>(sm, src + (size_t)row0 * N, tid);
+        row_tile_load_slots<N>(sc, a.T + off + (size_t)row0 * N, tid);
         __syncthreads();
-        double c[IPT][4];
-#pragma unroll
-        for (int it = 0; it < IPT; ++it) {
-            const int k = it * TPL + t;
-            if (k < M / 2) {
-                int idx[4];
-                item_index<N>(k, idx);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) c[it][j] = sl[idx[j] * LP];
-            }
+        {   // fused: pre + first inverse stage (two 8-point blocks per thread)
+            int rho_a, rho_b, base_a, base_b;
+            unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+            double ar[8], ai[8], br[8], bi[8];
+            load_block<N>(scl, base_a, ar, ai);
+            load_block<N>(scl, base_b, br, bi);
+            if (ra_line && t == 0) ra_scr[0] = ar[0] * sqrt(1.0 / N);       // row mean = C[0]/sqrt(N)
+            RowPre<N> pre{a.om};
+            for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, pre);
+            dft<8, true>(ar, ai);
+            dft<8, true>(br, bi);
+            store_block<N>(scl, base_a, ar, ai);
+            store_block<N>(scl, base_b, br, bi);
         }
         __syncthreads();
-#pragma unroll
-        for (int it = 0; it < IPT; ++it) {
-            const int k = it * TPL + t;
-            if (k < M / 2) pre_item<N>(sl, k, a.om, c[it]);
+        fft_inv_range<N, 1, NST - 1>(scl, t, a.tw);
+        if (MODE == ROW_INV || slow) {
+            fft_stage<N, 0, true>(scl, t, a.tw);
+            __syncthreads();
         }
-        __syncthreads();
-        fft_inv<N>(sl, t, a.tw);
     } else {
-        // ROW_FWD_U / ROW_FWD_MU: physical U rows -> smem (Makhoul order)
-        const double* src = (MODE == ROW_FWD_U && a.src) ? a.src + off : a.U + off;
-        row_tile_load<N, true>(sm, src + (size_t)row0 * N, tid);
+        const double* src = (MODE == ROW_FWD_U && a.src) ? a.src : a.U;
+        row_tile_load_phys<N>(sm, src + off + (size_t)row0 * N, tid);
         __syncthreads();
     }
 
-    // ================= jitter (solver.py:210-211): U += jitter*(2*noise - 1)
-    if (MODE == ROW_STEP && a.noise != nullptr) {
-        const double jit = S->p.jitter;
+    if (MODE == ROW_INV) {
+        double* dstU = (a.dst ? a.dst : a.U) + off + (size_t)row0 * N;
+        row_tile_store_phys<N>(sm, dstU, tid);
+        return;
+    }
+
+    // ================= jitter (solver.py:210-211): U += jitter*(2*noise - 1), and U is state now
+    if (jit) {
+        const double jv = S->p.jitter;
+        const double* nz = a.noise + (size_t)row0 * N;
+        double* dstU = a.U + off + (size_t)row0 * N;
         for (int i = tid; i < LINES * N; i += NT) {
             const int l2 = i / N, x = i % N;
-            const double r = a.noise[(size_t)(row0 + l2) * N + x];
-            sm[mk_pos<N>(x) * LP + l2] += jit * (2.0 * r - 1.0);
+            double* q = sm + real_off<N>(mk_pos<N>(x)) + 2 * l2;
+            const double u = *q + jv * (2.0 * nz[(size_t)l2 * N + x] - 1.0);
+            *q = u;
+            dstU[(size_t)l2 * N + x] = u;
         }
         __syncthreads();
     }
 
-    // ================= physical-space output
-    if (MODE == ROW_INV || (MODE == ROW_STEP && a.store_U)) {
-        double* dstU = (MODE == ROW_INV && a.dst) ? a.dst + off : a.U + off;
-        row_tile_store<N, true>(sm, dstU + (size_t)row0 * N, tid);
-        if (MODE == ROW_INV) return;
-    }
-
-    // ================= diagnostics of U_new and chemical potential for the next step
+    // ================= physics + first forward stage
     if (control) {
-        constexpr int XPT = N / TPL;
-        const int x0 = t * XPT;
         const chs_params p = S->p;
-        const bool diag = (MODE == ROW_STEP);
-        const int ra_row = N / 2 + 1;                                   // int(N/2)+1, solver.py:226
-        const bool ra_line = diag && (row0 + l == ra_row);
-        const bool ra_tile = diag && (ra_row >= row0) && (ra_row < row0 + LINES);
-        // mean(U_new): hat_U[0,0]/N is conserved by the update (Q4); jitter shifts it
-        double meanU = 0;
-        if (diag) {
-            meanU = a.hatU[off] / (double)N;
-            if (a.noise != nullptr) meanU += p.jitter * (2.0 * a.noise_mean[0] - 1.0);
-        }
-        const double lo = (x0 > 0) ? sl[mk_pos<N>(x0 - 1) * LP] : 0.0;
-        const double hi = (x0 + XPT < N) ? sl[mk_pos<N>(x0 + XPT) * LP] : 0.0;
-        if (ra_tile) {
-            if (ra_line) {
-                double s = 0;
-                for (int x = x0; x < x0 + XPT; ++x) s += sl[mk_pos<N>(x) * LP];
-                ra_scr[t] = s;
-            }
-        }
-        __syncthreads();
-        double ra_mean = 0;
-        if (ra_line) {
-            double s = 0;
-            for (int j = 0; j < TPL; ++j) s += ra_scr[j];
-            ra_mean = s / (double)N;
-        }
-        const double ih = 1.0 / p.delx, ih2 = 0.5 / p.delx;
-        double v[6] = {0, 0, 0, 0, 0, 0};           // GX2, F, ABS, MU2, CNT, SUMU
-        double ra_abs = 0;
-        double prev = lo, cur = sl[mk_pos<N>(x0) * LP];
-#pragma unroll 4
-        for (int x = x0; x < x0 + XPT; ++x) {
-            const double nxt = (x + 1 < x0 + XPT) ? sl[mk_pos<N>(x + 1) * LP] : hi;
-            double f, mu;
-            thermo(cur, p, ltab, f, mu);
-            if (diag) {
-                double g;
-                if (x == 0) g = (nxt - cur) * ih;
-                else if (x == N - 1) g = (cur - prev) * ih;
-                else g = (nxt - prev) * ih2;
-                v[0] += g * g;
-                v[1] += f;
-                v[2] += fabs(cur - meanU);
-                v[4] += (cur < p.threshold) ? 1.0 : 0.0;
-                v[5] += cur;
-                if (ra_line) ra_abs += fabs(cur - ra_mean);
-            }
-            v[3] += mu * mu;
-            sl[mk_pos<N>(x) * LP] = mu;
-            prev = cur; cur = nxt;
-        }
-        if (ra_line) ra_scr[TPL + t] = ra_abs;
-        block_reduce<6>(v, CHS_RED_SCRATCH(G, sm), tid, NT);        // contains barriers
-        if (tid == 0) {
-            double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
-            pp[P_MU2 * G::NTILES] = v[3];
-            if (diag) {
-                pp[P_GX2 * G::NTILES] = v[0];
-                pp[P_F * G::NTILES] = v[1];
-                pp[P_ABS * G::NTILES] = v[2];
-                pp[P_CNT * G::NTILES] = v[4];
-                pp[P_SUMU * G::NTILES] = v[5];
-            } else {
-                pp[P_GX2 * G::NTILES] = 0; pp[P_F * G::NTILES] = 0; pp[P_ABS * G::NTILES] = 0;
-                pp[P_CNT * G::NTILES] = 0; pp[P_SUMU * G::NTILES] = 0;
-            }
-            if (ra_tile) {
-                double s = 0;
-                for (int j = 0; j < TPL; ++j) s += ra_scr[TPL + j];
-                S->ra = s / (double)N;
-            }
-        }
-        // adaptive dt: column sums of delt_max/sqrt(1 + 62.5 mu^2) over this tile's rows (solver.py:182-183)
-        const long long cs_next = S->computed_steps + (diag ? 1 : 0);
-        if (p.adaptive_time && !a.last && cs_next > 500 && (cs_next % 2) == 0) {
-            for (int x = tid; x < N; x += NT) {
-                const double* col = sm + mk_pos<N>(x) * LP;
-                double s = 0;
+        const double meanU = diag ? a.hatU[off] / (double)N : 0.0;          // conserved mean (Q4)
+        const double ra_mean = ra_line ? ra_scr[0] : 0.0;
+        RowAcc acc = {0, 0, 0, 0, 0};
 #pragma unroll
-                for (int l2 = 0; l2 < LINES; ++l2) {
-                    const double m = col[l2];
-                    s += p.delt_max / sqrt(1.0 + 62.5 * (m * m));
+        for (int i = 0; i < NB0; ++i) {
+            const int j = t + i * TPL;
+            double xr[R0], xi[R0];
+#pragma unroll
+            for (int q = 0; q < R0; ++q) {
+                const double2 v = scl[(j + q * ST0) * LPC];
+                xr[q] = v.x; xi[q] = v.y;
+            }
+            double2 w[R0];
+            if (!slow) {
+#pragma unroll
+                for (int q = 1; q < R0; ++q) {
+                    w[q] = __ldg(a.tw + j * q);
+                    const double x = xr[q], y = xi[q];
+                    xr[q] = x * w[q].x + y * w[q].y;                         // conj twiddle, then inverse DFT
+                    xi[q] = y * w[q].x - x * w[q].y;
                 }
-                a.colpart[((size_t)sim * G::NTILES + tile) * N + x] = s;
+                dft<R0, true>(xr, xi);
             }
-            __syncthreads();                                       // mu is transformed in place next
+            physics<N, R0>(xr, xi, j, p, ltab, diag, meanU, ra_line, ra_mean, acc, edge + 4 * l);
+            if (!slow) {
+                dft<R0, false>(xr, xi);
+#pragma unroll
+                for (int q = 1; q < R0; ++q) {
+                    const double x = xr[q], y = xi[q];
+                    xr[q] = x * w[q].x - y * w[q].y;
+                    xi[q] = x * w[q].y + y * w[q].x;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < R0; ++q) scl[(j + q * ST0) * LPC] = make_double2(xr[q], xi[q]);
         }
+        if (ra_line) ra_scr[2 + t] = acc.ra;
+        const double v[4] = {acc.f, acc.ab, acc.mu2, acc.cnt};
+        reduce_stage<4>(v, sm + G::OFF_RED, tid);
+        __syncthreads();
+        if (tid == 0) {
+            double s4[4];
+            reduce_final<4>(s4, sm + G::OFF_RED, NT);
+            double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
+            pp[P_MU2 * G::NTILES] = s4[2];
+            if (diag) {
+                double e = 0;
+                for (int l2 = 0; l2 < LINES; ++l2) {
+                    const double* eg = edge + 4 * l2;
+                    e += (eg[1] - eg[0]) * (eg[1] - eg[0]) + (eg[3] - eg[2]) * (eg[3] - eg[2]);
+                }
+                pp[P_GXE * G::NTILES] = 0.75 * e;
+                pp[P_F * G::NTILES] = s4[0];
+                pp[P_ABS * G::NTILES] = s4[1];
+                pp[P_CNT * G::NTILES] = s4[3];
+                if (ra_tile) {
+                    double s = 0;
+                    for (int jj = 0; jj < TPL; ++jj) s += ra_scr[2 + jj];
+                    S->ra = s / (double)N;
+                }
+            }
+        }
+        if (slow) {
+            // adaptive dt: column sums of delt_max/sqrt(1 + 62.5 mu^2) over this tile's rows (solver.py:182-183)
+            if (want_cols) {
+                for (int x = tid; x < N; x += NT) {
+                    const double* colp = sm + real_off<N>(mk_pos<N>(x));
+                    double s = 0;
+#pragma unroll
+                    for (int l2 = 0; l2 < LINES; ++l2) {
+                        const double m = colp[2 * l2];
+                        s += p.delt_max / sqrt(1.0 + 62.5 * (m * m));
+                    }
+                    a.colpart[((size_t)sim * G::NTILES + tile) * N + x] = s;
+                }
+                __syncthreads();
+            }
+            fft_stage<N, 0, false>(scl, t, a.tw);
+            __syncthreads();
+        }
+    } else {
+        fft_stage<N, 0, false>(scl, t, a.tw);            // ROW_FWD_U
+        __syncthreads();
     }
 
-    // ================= forward half: rows -> row DCT-II -> T
-    fft_fwd<N>(sl, t, a.tw);
+    // ================= forward half: remaining stages, fused last stage + post, store
+    fft_fwd_range<N, 1, NST - 1>(scl, t, a.tw);
     {
-        double c[IPT][4];
-#pragma unroll
-        for (int it = 0; it < IPT; ++it) {
-            const int k = it * TPL + t;
-            if (k < M / 2) post_item<N>(sl, k, a.om, c[it]);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < IPT; ++it) {
-            const int k = it * TPL + t;
-            if (k < M / 2) {
-                int idx[4];
-                item_index<N>(k, idx);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sl[idx[j] * LP] = c[it][j];
-            }
-        }
-        __syncthreads();
-        double* dstT = (MODE == ROW_FWD_U && a.dst) ? a.dst + off : a.T + off;
-        row_tile_store<N, false>(sm, dstT + (size_t)row0 * N, tid);
+        int rho_a, rho_b, base_a, base_b;
+        unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+        double ar[8], ai[8], br[8], bi[8];
+        load_block<N>(scl, base_a, ar, ai);
+        load_block<N>(scl, base_b, br, bi);
+        dft<8, false>(ar, ai);
+        dft<8, false>(br, bi);
+        RowPost<N> post{a.om};
+        for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, post);
+        store_block<N>(scl, base_a, ar, ai);
+        store_block<N>(scl, base_b, br, bi);
     }
+    __syncthreads();
+    row_tile_store_slots<N>(sc, ((MODE == ROW_FWD_U && a.dst) ? a.dst : a.T) + off + (size_t)row0 * N, tid);
 
-    // ================= control (not in jitter mode: k_diag finishes the iteration there)
-    if (control) {
-        const bool defer = (MODE == ROW_STEP) && (a.noise != nullptr);
-        if (!defer) {
-            if (last_cta(S, G::NTILES, flag, tid)) {
-                step_control<N>(S, a.part + (size_t)sim * P_NSLOT * G::NTILES,
-                                a.colpart + (size_t)sim * G::NTILES * N,
-                                a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last,
-                                MODE == ROW_STEP, sm, tid, NT);
-            }
+    // ================= control (with jitter k_diag finishes the iteration instead)
+    if (control && !jit) {
+        if (last_cta(S, G::NTILES, flag, tid, want_cols)) {
+            step_control<N>(S, a.part + (size_t)sim * P_NSLOT * G::NTILES,
+                            a.colpart + (size_t)sim * G::NTILES * N,
+                            a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last,
+                            MODE == ROW_STEP, sm, tid, NT);
         }
     }
 }
 
 // =======================================================================================
-//  k_diag: diagnostics straight from the U buffer.
-//    DIAG_PREPARE : all of row 0 (Solver.prepare, solver.py:100-135)
-//    DIAG_JITTER  : only the y-part of the gradient energy of the jittered U (Parseval
-//                   does not hold once noise is added in physical space), then step_control
+//  k_diag: diagnostics straight from the U buffer (np.gradient stencils, solver.py:100-127)
+//    DIAG_PREPARE : row 0 of TimeData (Solver.prepare)
+//    DIAG_JITTER  : all diagnostics of the jittered field, then step_control
 // =======================================================================================
 template <int N, int MODE>
 CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
@@ -635,7 +830,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
     constexpr int LINES = G::LINES, NT = G::NT;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
-    int* flag = CHS_FLAG_PTR(G, sm);
+    int* flag = reinterpret_cast<int*>(sm + G::OFF_FLAG);
     const int tid = threadIdx.x;
     const int sim = a.sim_index ? a.sim_index[blockIdx.y] : (int)blockIdx.y;
     const int tile = blockIdx.x, row0 = tile * LINES;
@@ -643,76 +838,81 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
     if (MODE == DIAG_JITTER && S->halted) return;
     const chs_params p = S->p;
     const double* U = a.U + (size_t)sim * N * N;
-    const double ih = 1.0 / p.delx, ih2 = 0.5 / p.delx;
-    const double meanU = (MODE == DIAG_PREPARE) ? a.mean_host[sim] : 0.0;
-    const double2* ltab = nullptr;
-    if (MODE == DIAG_PREPARE) {
-        ltab = stage_logtab<G>(sm, a.logtab, tid);
-        __syncthreads();
-    }
-    double v[4] = {0, 0, 0, 0};                    // GY2, GX2, F, ABS
+    double meanU;
+    if (MODE == DIAG_PREPARE) meanU = a.mean_host[sim];
+    else meanU = a.hatU[(size_t)sim * N * N] / (double)N + p.jitter * (2.0 * a.noise_mean[0] - 1.0);
+    const double2* ltab = stage_logtab<G>(sm, a.logtab, tid);
+    __syncthreads();
+    double v[4] = {0, 0, 0, 0};                    // raw grad^2 (x h^2), F, ABS, CNT
     for (int i = tid; i < LINES * N; i += NT) {
         const int y = row0 + i / N, x = i % N;
         const double c = U[(size_t)y * N + x];
-        double gy;
-        if (y == 0) gy = (U[(size_t)(y + 1) * N + x] - c) * ih;
-        else if (y == N - 1) gy = (c - U[(size_t)(y - 1) * N + x]) * ih;
-        else gy = (U[(size_t)(y + 1) * N + x] - U[(size_t)(y - 1) * N + x]) * ih2;
-        v[0] += gy * gy;
-        if (MODE == DIAG_PREPARE) {
-            double gx;
-            if (x == 0) gx = (U[(size_t)y * N + 1] - c) * ih;
-            else if (x == N - 1) gx = (c - U[(size_t)y * N + x - 1]) * ih;
-            else gx = (U[(size_t)y * N + x + 1] - U[(size_t)y * N + x - 1]) * ih2;
-            double f, mu;
-            thermo(c, p, ltab, f, mu);
-            v[1] += gx * gx;
-            v[2] += f;
-            v[3] += fabs(c - meanU);
-        }
+        double gy, gx;
+        if (y == 0) gy = U[(size_t)(y + 1) * N + x] - c;
+        else if (y == N - 1) gy = c - U[(size_t)(y - 1) * N + x];
+        else gy = 0.5 * (U[(size_t)(y + 1) * N + x] - U[(size_t)(y - 1) * N + x]);
+        if (x == 0) gx = U[(size_t)y * N + 1] - c;
+        else if (x == N - 1) gx = c - U[(size_t)y * N + x - 1];
+        else gx = 0.5 * (U[(size_t)y * N + x + 1] - U[(size_t)y * N + x - 1]);
+        double f, mu;
+        thermo(c, p, ltab, f, mu);
+        v[0] += gy * gy + gx * gx;
+        v[1] += f;
+        v[2] += fabs(c - meanU);
+        v[3] += (c < p.threshold) ? 1.0 : 0.0;
     }
-    block_reduce<4>(v, CHS_RED_SCRATCH(G, sm), tid, NT);
+    reduce_stage<4>(v, sm + G::OFF_RED, tid);
+    __syncthreads();
     double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
     if (tid == 0) {
-        pp[P_GY2 * G::NTILES] = v[0];
-        if (MODE == DIAG_PREPARE) {
-            pp[P_GX2 * G::NTILES] = v[1];
-            pp[P_F * G::NTILES] = v[2];
-            pp[P_ABS * G::NTILES] = v[3];
-        }
+        reduce_final<4>(v, sm + G::OFF_RED, NT);
+        pp[P_GE * G::NTILES] = v[0];
+        pp[P_GYE * G::NTILES] = 0;
+        pp[P_GXE * G::NTILES] = 0;
+        pp[P_F * G::NTILES] = v[1];
+        pp[P_ABS * G::NTILES] = v[2];
+        pp[P_CNT * G::NTILES] = v[3];
     }
-    // Ra of row int(N/2)+1 (solver.py:115-116)
+    __syncthreads();
+    // Ra of row int(N/2)+1 (solver.py:115-116 / :226)
     const int ra_row = N / 2 + 1;
-    if (MODE == DIAG_PREPARE && ra_row >= row0 && ra_row < row0 + LINES) {
+    if (ra_row >= row0 && ra_row < row0 + LINES) {
         double s[1] = {0};
         for (int x = tid; x < N; x += NT) s[0] += U[(size_t)ra_row * N + x];
-        block_reduce<1>(s, CHS_RED_SCRATCH(G, sm), tid, NT);
-        if (tid == 0) sm[0] = s[0] / (double)N;
+        reduce_stage<1>(s, sm + G::OFF_RED, tid);
         __syncthreads();
-        const double m = sm[0];
+        if (tid == 0) {
+            reduce_final<1>(s, sm + G::OFF_RED, NT);
+            sm[G::OFF_RA] = s[0] / (double)N;
+        }
+        __syncthreads();
+        const double m = sm[G::OFF_RA];
         double q[1] = {0};
         for (int x = tid; x < N; x += NT) q[0] += fabs(U[(size_t)ra_row * N + x] - m);
-        block_reduce<1>(q, CHS_RED_SCRATCH(G, sm), tid, NT);
-        if (tid == 0) S->ra = q[0] / (double)N;
+        reduce_stage<1>(q, sm + G::OFF_RED, tid);
+        __syncthreads();
+        if (tid == 0) {
+            reduce_final<1>(q, sm + G::OFF_RED, NT);
+            S->ra = q[0] / (double)N;
+        }
     }
-    if (!last_cta(S, G::NTILES, flag, tid)) return;
+    if (!last_cta(S, G::NTILES, flag, tid, false)) return;
     if (MODE == DIAG_JITTER) {
         step_control<N>(S, a.part + (size_t)sim * P_NSLOT * G::NTILES, a.colpart + (size_t)sim * G::NTILES * N,
-                        a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last, true,
-                        sm, tid, NT);
+                        a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last, true, sm, tid, NT);
         return;
     }
     if (tid != 0) return;
     // ---- Solver.prepare(): row 0 and state reset (solver.py:117-135)
-    double acc[4] = {0, 0, 0, 0};
-    const int slots[4] = {P_GY2, P_GX2, P_F, P_ABS};
+    double acc[3] = {0, 0, 0};
+    const int slots[3] = {P_GE, P_F, P_ABS};
     const double* part = a.part + (size_t)sim * P_NSLOT * G::NTILES;
-    for (int s = 0; s < 4; ++s)
+    for (int s = 0; s < 3; ++s)
         for (int tl = 0; tl < G::NTILES; ++tl) acc[s] += CHS_LDCG(part + slots[s] * G::NTILES + tl);
     const double N2 = (double)N * (double)N, L2sq = p.L * p.L;
-    const double E2 = 0.5 * p.Amr * p.kappa_tilde * L2sq * ((acc[0] + acc[1]) / N2);
-    const double E = p.Amr * L2sq * (acc[2] / N2) + E2;
-    const double PS = acc[3] / N2;
+    const double E2 = 0.5 * p.Amr * p.kappa_tilde * L2sq * ((acc[0] / (p.delx * p.delx)) / N2);
+    const double E = p.Amr * L2sq * (acc[1] / N2) + E2;
+    const double PS = acc[2] / N2;
     double* r = a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS;
     r[CHS_COL_IT] = 0; r[CHS_COL_E] = E; r[CHS_COL_E2] = E2; r[CHS_COL_SA] = 0; r[CHS_COL_DOMTIME] = 0;
     r[CHS_COL_RA] = S->ra; r[CHS_COL_L2] = 0; r[CHS_COL_PS] = PS; r[CHS_COL_DELT] = S->delt;

@@ -11,6 +11,7 @@
 #else
 #include <cuda_runtime.h>
 #define CHS_DEV __device__ __forceinline__
+#define CHS_MEM __device__ __forceinline__
 #define CHS_HD __host__ __device__ __forceinline__
 #define CHS_KERNEL __global__
 #define CHS_CX __host__ __device__

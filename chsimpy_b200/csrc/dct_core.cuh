@@ -3,18 +3,20 @@
 //
 // Algorithm (one "line" = one row or one column of N reals, M = N/2):
 //   DCT-II :  Makhoul even/odd reorder v -> pack z[n] = v[2n] + i v[2n+1] -> M-point complex
-//             FFT (in-place decimation-in-frequency, digit-reversed output) -> one combined
-//             "post" pass (real-FFT untangle + quarter-wave twiddle) -> C[k].
-//   DCT-III:  the exact transpose: "pre" pass -> in-place decimation-in-time inverse FFT
+//             FFT (in place, decimation in frequency, digit-reversed output) -> "post" step
+//             (real-FFT untangle + quarter-wave twiddle) -> C[k].
+//   DCT-III:  the exact transpose: "pre" step -> in-place decimation-in-time inverse FFT
 //             (digit-reversed input, natural output) -> un-reorder.
-// Because the forward FFT leaves its output digit-reversed and the inverse FFT consumes
-// digit-reversed input, no reordering pass is ever executed.
+// The forward FFT leaves its output digit-reversed and the inverse consumes digit-reversed
+// input, so no reordering pass is ever executed.  The post/pre step couples frequency k with
+// M-k; both live in the two 8-point blocks of the LAST radix-8 stage that one thread owns
+// (fused_* in chs_kernels.cuh), so post/pre never touch shared memory on their own.
 //
-// Tile layout in shared memory: LINES lines are transformed together and the line index
-// is the fastest-varying (lane) dimension:  element p of line l lives at  sm[p*LP + l].
-// Every FFT access of a warp therefore touches LINES consecutive doubles -> bank-conflict
-// free for any stride, and all lanes of a half-warp share their twiddle factors.
-// tools/dct_model.py is the numpy model this file was derived from.
+// Tile layout in shared memory: 16 lines are transformed together and the line index is
+// the lane dimension: complex element c of line l is the double2 at sc[c*LPC + l].  A
+// half-warp therefore reads 16 consecutive double2 (LDS.128, conflict free for any
+// butterfly stride) and shares its twiddle factors.
+// tools/dct_model.py is the numpy model of the transform algebra.
 #pragma once
 #include "chs_rt.h"
 
@@ -41,20 +43,31 @@ struct Geo {
     static constexpr int N = N_;
     static constexpr int M = N / 2;
     static constexpr int LINES = 16;
-    static constexpr int LP = LINES + 1;                       // line pitch (odd: conflict-free transposing I/O)
-    static constexpr int TPL = (M / 8 < 32) ? (M / 8) : 32;    // threads per line
+    static constexpr int LPC = LINES + 1;                      // line pitch in double2 (odd: conflict-free transposing I/O)
+    static constexpr int TPL = M / 16;                         // threads per line: 16 complex points each per stage
     static constexpr int NT = LINES * TPL;                     // threads per CTA
     static constexpr int NTILES = N / LINES;
-    static constexpr int MINB = (N <= 512) ? 2 : 1;             // CTAs per SM the register budget is sized for
-    static constexpr int TILE_DOUBLES = N * LP;
-    static constexpr int SCRATCH_DOUBLES = 2 * TPL + (NT / 32 + 1) * 8 + 8 + 2 * 128;   // + fast_log table
-    static constexpr int SMEM_BYTES = (TILE_DOUBLES + SCRATCH_DOUBLES) * 8;
+    static constexpr int MINB = (N <= 512) ? 2 : 1;            // CTAs per SM the register budget is sized for
+    static constexpr int TILE_DOUBLES = 2 * M * LPC;
+    // scratch after the tile (doubles): flag | x/y edge values | Ra | fast_log table | reduction
+    static constexpr int OFF_FLAG = TILE_DOUBLES;
+    static constexpr int OFF_EDGE = OFF_FLAG + 2;              // [LINES][4]
+    static constexpr int OFF_RA = OFF_EDGE + 4 * LINES;        // mean, spare, then TPL partials
+    static constexpr int OFF_LOGTAB = OFF_RA + 2 + TPL + (TPL & 1);      // keeps double2 alignment
+    static constexpr int OFF_RED = OFF_LOGTAB + 2 * 128;       // (NT/32+1)*8 doubles on the GPU; NT*8 in the host emulation
+    static constexpr int SMEM_BYTES = (OFF_RED + (NT / 32 + 1) * 8 + 8) * 8;
     static_assert(N >= 32 && (N & (N - 1)) == 0, "FFT path needs a power of two >= 32");
+    static_assert(Rad<M>::radix(Rad<M>::nst - 1) == 8 && Rad<M>::nst >= 2, "plan must end with a radix-8 stage");
+    static_assert((OFF_LOGTAB % 2) == 0, "double2 alignment");
 };
 
 // Makhoul reorder: physical index n -> position in v
 template <int N>
 CHS_DEV int mk_pos(int n) { return (n & 1) ? (N - 1 - (n >> 1)) : (n >> 1); }
+
+// offset (in doubles) of real element p (= v index: complex p>>1, part p&1) of line 0
+template <int N>
+CHS_DEV int real_off(int p) { return 2 * ((p >> 1) * Geo<N>::LPC) + (p & 1); }
 
 // position of frequency k after the in-place DIF (mixed-radix digit reversal)
 template <int M>
@@ -118,167 +131,134 @@ CHS_DEV void dft(double (&xr)[R], double (&xi)[R]) {
     }
 }
 
-// ------------------------------------------------------------------ FFT stages on one line
-// sl = smem + l (line base), t = thread index within the line, tw[m] = exp(-2 pi i m / M)
-template <int N, int S>
-CHS_DEV void fft_fwd_stage(double* sl, int t, const double2* __restrict__ tw) {
+// ------------------------------------------------------------------ regular FFT stages
+// scl = (double2*)tile + l (line base), t = thread index within the line,
+// tw[m] = exp(-2 pi i m / M).  Every thread owns 16/r butterflies of radix r.
+template <int N, int S, bool INV>
+CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
     using G = Geo<N>;
-    constexpr int M = G::M, LP = G::LP, TPL = G::TPL;
+    constexpr int M = G::M, LPC = G::LPC, TPL = G::TPL;
     constexpr int r = Rad<M>::radix(S), Lb = Rad<M>::blocklen(S), st = Lb / r;
+    constexpr int NB = 16 / r;
 #pragma unroll
-    for (int u0 = 0; u0 < M / r; u0 += TPL) {
-        const int u = u0 + t;
-        if (M / r < TPL && u >= M / r) break;
+    for (int i = 0; i < NB; ++i) {
+        const int u = t + i * TPL;
         const int j = u % st, base = (u / st) * Lb + j;
         double xr[r], xi[r];
 #pragma unroll
         for (int q = 0; q < r; ++q) {
-            const int c = base + q * st;
-            xr[q] = sl[(2 * c) * LP];
-            xi[q] = sl[(2 * c + 1) * LP];
+            const double2 v = scl[(base + q * st) * LPC];
+            xr[q] = v.x; xi[q] = v.y;
         }
-        dft<r, false>(xr, xi);
+        if (!INV) dft<r, false>(xr, xi);
         if (st > 1) {
 #pragma unroll
             for (int p = 1; p < r; ++p) {
                 const double2 w = __ldg(tw + j * p * (M / Lb));
                 const double a = xr[p], b = xi[p];
-                xr[p] = a * w.x - b * w.y;
-                xi[p] = a * w.y + b * w.x;
+                if (!INV) { xr[p] = a * w.x - b * w.y; xi[p] = a * w.y + b * w.x; }
+                else      { xr[p] = a * w.x + b * w.y; xi[p] = b * w.x - a * w.y; }     // conj(w)
             }
         }
+        if (INV) dft<r, true>(xr, xi);
 #pragma unroll
-        for (int q = 0; q < r; ++q) {
-            const int c = base + q * st;
-            sl[(2 * c) * LP] = xr[q];
-            sl[(2 * c + 1) * LP] = xi[q];
-        }
+        for (int q = 0; q < r; ++q) scl[(base + q * st) * LPC] = make_double2(xr[q], xi[q]);
     }
 }
 
-template <int N, int S>
-CHS_DEV void fft_inv_stage(double* sl, int t, const double2* __restrict__ tw) {
-    using G = Geo<N>;
-    constexpr int M = G::M, LP = G::LP, TPL = G::TPL;
-    constexpr int r = Rad<M>::radix(S), Lb = Rad<M>::blocklen(S), st = Lb / r;
-#pragma unroll
-    for (int u0 = 0; u0 < M / r; u0 += TPL) {
-        const int u = u0 + t;
-        if (M / r < TPL && u >= M / r) break;
-        const int j = u % st, base = (u / st) * Lb + j;
-        double xr[r], xi[r];
-#pragma unroll
-        for (int q = 0; q < r; ++q) {
-            const int c = base + q * st;
-            xr[q] = sl[(2 * c) * LP];
-            xi[q] = sl[(2 * c + 1) * LP];
-        }
-        if (st > 1) {
-#pragma unroll
-            for (int p = 1; p < r; ++p) {
-                const double2 w = __ldg(tw + j * p * (M / Lb));     // conj(w) applied
-                const double a = xr[p], b = xi[p];
-                xr[p] = a * w.x + b * w.y;
-                xi[p] = b * w.x - a * w.y;
-            }
-        }
-        dft<r, true>(xr, xi);
-#pragma unroll
-        for (int q = 0; q < r; ++q) {
-            const int c = base + q * st;
-            sl[(2 * c) * LP] = xr[q];
-            sl[(2 * c + 1) * LP] = xi[q];
-        }
-    }
-}
-
-// all stages; every stage is followed by a block barrier
-template <int N, int S = 0>
-CHS_DEV void fft_fwd(double* sl, int t, const double2* __restrict__ tw) {
-    if constexpr (S < Rad<N / 2>::nst) {
-        fft_fwd_stage<N, S>(sl, t, tw);
+// forward stages [S0, S1): each followed by a block barrier
+template <int N, int S0, int S1>
+CHS_DEV void fft_fwd_range(double2* scl, int t, const double2* __restrict__ tw) {
+    if constexpr (S0 < S1) {
+        fft_stage<N, S0, false>(scl, t, tw);
         __syncthreads();
-        fft_fwd<N, S + 1>(sl, t, tw);
+        fft_fwd_range<N, S0 + 1, S1>(scl, t, tw);
     }
 }
-template <int N, int S = Rad<N / 2>::nst - 1>
-CHS_DEV void fft_inv(double* sl, int t, const double2* __restrict__ tw) {
-    if constexpr (S >= 0) {
-        fft_inv_stage<N, S>(sl, t, tw);
+// inverse stages S1-1 down to S0: each followed by a block barrier
+template <int N, int S0, int S1>
+CHS_DEV void fft_inv_range(double2* scl, int t, const double2* __restrict__ tw) {
+    if constexpr (S0 < S1) {
+        fft_stage<N, S1 - 1, true>(scl, t, tw);
         __syncthreads();
-        fft_inv<N, S - 1>(sl, t, tw);
+        fft_inv_range<N, S0, S1 - 1>(scl, t, tw);
     }
 }
 
-// ------------------------------------------------------------------ post / pre passes
-// Work item k in [0, M/2): k >= 1 couples Z[k], Z[M-k] <-> C[k], C[N-k], C[M-k], C[M+k];
-// item 0 couples Z[0], Z[M/2] <-> C[0], C[M], C[M/2], C[3M/2].   om[m] = exp(-i pi m / (2N)).
+// ------------------------------------------------------------------ post / pre algebra (registers)
+// om[m] = exp(-i pi m / (2N)).  For 1 <= k < M/2:
+//   post: Z[k]=(ar,ai), Z[M-k]=(br,bi)  ->  c = {C[k], C[N-k], C[M-k], C[M+k]}
+//   pre : the inverse map, including the 1/M of the unnormalised inverse FFT.
+// special: Z[0], Z[M/2] <-> {C[0], C[M], C[M/2], C[3M/2]}.
 template <int N>
-CHS_DEV void item_index(int k, int (&idx)[4]) {
+CHS_DEV void post_pair(int k, const double2* __restrict__ om, double ar, double ai, double br, double bi,
+                       double (&c)[4]) {
     constexpr int M = N / 2;
-    if (k == 0) { idx[0] = 0; idx[1] = M; idx[2] = M / 2; idx[3] = M + M / 2; }
-    else { idx[0] = k; idx[1] = N - k; idx[2] = M - k; idx[3] = M + k; }
+    const double2 t = __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    const double sc = 0.5 * sqrt(2.0 / N);
+    const double er = ar + br, ei = ai - bi;                  // 2E
+    const double o_r = ai + bi, o_i = br - ar;                // 2O = -i (a - conj b)
+    const double tr = t.x * o_r - t.y * o_i, ti = t.x * o_i + t.y * o_r;
+    const double pr = (er + tr) * sc, pi = (ei + ti) * sc;
+    const double qr = (er - tr) * sc, qi = (ei - ti) * sc;
+    c[0] = wk.x * pr - wk.y * pi;
+    c[1] = -(wk.x * pi + wk.y * pr);
+    c[2] = wm.x * qr + wm.y * qi;                             // Re(wm * conj(Q))
+    c[3] = wm.x * qi - wm.y * qr;                             // -Im(wm * conj(Q))
 }
 
 template <int N>
-CHS_DEV void post_item(const double* sl, int k, const double2* __restrict__ om, double (&c)[4]) {
-    constexpr int M = N / 2, LP = Geo<N>::LP;
-    if (k == 0) {
-        const int p0 = freq_pos<M>(0), ph = freq_pos<M>(M / 2);
-        const double ar = sl[(2 * p0) * LP], ai = sl[(2 * p0 + 1) * LP];
-        const double hr = sl[(2 * ph) * LP], hi = sl[(2 * ph + 1) * LP];
-        const double rn = sqrt(1.0 / N), s = sqrt(2.0 / N);
-        const double2 w = __ldg(om + M / 2);
-        c[0] = rn * (ar + ai);
-        c[1] = rn * (ar - ai);
-        c[2] = s * (w.x * hr + w.y * hi);          // Re(w * conj(Zh))
-        c[3] = -s * (w.y * hr - w.x * hi);         // -Im(w * conj(Zh))
-    } else {
-        const int pa = freq_pos<M>(k), pb = freq_pos<M>(M - k);
-        const double ar = sl[(2 * pa) * LP], ai = sl[(2 * pa + 1) * LP];
-        const double br = sl[(2 * pb) * LP], bi = sl[(2 * pb + 1) * LP];
-        const double2 t = __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
-        const double sc = 0.5 * sqrt(2.0 / N);
-        const double er = ar + br, ei = ai - bi;                  // 2E
-        const double o_r = ai + bi, o_i = br - ar;                // 2O = -i (a - conj b)
-        const double tr = t.x * o_r - t.y * o_i, ti = t.x * o_i + t.y * o_r;
-        const double pr = (er + tr) * sc, pi = (ei + ti) * sc;
-        const double qr = (er - tr) * sc, qi = (ei - ti) * sc;
-        c[0] = wk.x * pr - wk.y * pi;
-        c[1] = -(wk.x * pi + wk.y * pr);
-        c[2] = wm.x * qr + wm.y * qi;                             // Re(wm * conj(Q))
-        c[3] = wm.x * qi - wm.y * qr;                             // -Im(wm * conj(Q))
-    }
+CHS_DEV void post_special(const double2* __restrict__ om, double ar, double ai, double hr, double hi,
+                          double (&c)[4]) {
+    constexpr int M = N / 2;
+    const double rn = sqrt(1.0 / N), s = sqrt(2.0 / N);
+    const double2 w = __ldg(om + M / 2);
+    c[0] = rn * (ar + ai);
+    c[1] = rn * (ar - ai);
+    c[2] = s * (w.x * hr + w.y * hi);          // Re(w * conj(Zh))
+    c[3] = -s * (w.y * hr - w.x * hi);         // -Im(w * conj(Zh))
 }
 
 template <int N>
-CHS_DEV void pre_item(double* sl, int k, const double2* __restrict__ om, const double (&c)[4]) {
-    constexpr int M = N / 2, LP = Geo<N>::LP;
-    if (k == 0) {
-        const int p0 = freq_pos<M>(0), ph = freq_pos<M>(M / 2);
-        const double rn = sqrt(1.0 / N), is = 1.0 / (sqrt(2.0 / N) * M);
-        const double2 w = __ldg(om + M / 2);
-        sl[(2 * p0) * LP] = rn * (c[0] + c[1]);
-        sl[(2 * p0 + 1) * LP] = rn * (c[0] - c[1]);
-        const double u = c[2] * is, v = -c[3] * is;               // A/(sM) = u + i v
-        const double vr = w.x * u + w.y * v, vi = w.x * v - w.y * u;   // conj(w)*A, w=(x,y): (x - i y)(u + i v)
-        sl[(2 * ph) * LP] = vr;
-        sl[(2 * ph + 1) * LP] = -vi;
-    } else {
-        const int pa = freq_pos<M>(k), pb = freq_pos<M>(M - k);
-        const double2 t = __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
-        const double sc = 1.0 / (sqrt(2.0 / N) * N);              // 1/(2 s M)
-        // V = conj(wk) * (c0 - i c1),  V2 = conj(wm) * (c2 - i c3)
-        const double vr = wk.x * c[0] - wk.y * c[1], vi = -wk.x * c[1] - wk.y * c[0];
-        const double v2r = wm.x * c[2] - wm.y * c[3], v2i = -wm.x * c[3] - wm.y * c[2];
-        const double er = (vr + v2r) * sc, ei = (vi - v2i) * sc;  // E
-        const double dr = (vr - v2r) * sc, di = (vi + v2i) * sc;  // V - conj(V2)
-        const double o_r = dr * t.x + di * t.y, o_i = di * t.x - dr * t.y;   // O = D * conj(t)
-        sl[(2 * pa) * LP] = er - o_i;
-        sl[(2 * pa + 1) * LP] = ei + o_r;
-        sl[(2 * pb) * LP] = er + o_i;
-        sl[(2 * pb + 1) * LP] = o_r - ei;
-    }
+CHS_DEV void pre_pair(int k, const double2* __restrict__ om, const double (&c)[4], double& ar, double& ai,
+                      double& br, double& bi) {
+    constexpr int M = N / 2;
+    const double2 t = __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    const double sc = 1.0 / (sqrt(2.0 / N) * N);              // 1/(2 s M)
+    const double vr = wk.x * c[0] - wk.y * c[1], vi = -wk.x * c[1] - wk.y * c[0];       // conj(wk)(c0 - i c1)
+    const double v2r = wm.x * c[2] - wm.y * c[3], v2i = -wm.x * c[3] - wm.y * c[2];
+    const double er = (vr + v2r) * sc, ei = (vi - v2i) * sc;  // E
+    const double dr = (vr - v2r) * sc, di = (vi + v2i) * sc;  // V - conj(V2)
+    const double o_r = dr * t.x + di * t.y, o_i = di * t.x - dr * t.y;   // O = D * conj(t)
+    ar = er - o_i; ai = ei + o_r;
+    br = er + o_i; bi = o_r - ei;
 }
+
+template <int N>
+CHS_DEV void pre_special(const double2* __restrict__ om, const double (&c)[4], double& ar, double& ai,
+                         double& hr, double& hi) {
+    constexpr int M = N / 2;
+    const double rn = sqrt(1.0 / N), is = 1.0 / (sqrt(2.0 / N) * M);
+    const double2 w = __ldg(om + M / 2);
+    ar = rn * (c[0] + c[1]);
+    ai = rn * (c[0] - c[1]);
+    const double u = c[2] * is, v = -c[3] * is;               // A/(sM) = u + i v
+    const double vr = w.x * u + w.y * v, vi = w.x * v - w.y * u;   // conj(w) * A
+    hr = vr; hi = -vi;
+}
+
+// The two blocks of the last radix-8 stage owned by thread t, and the frequency residues
+// (k mod M/8) they hold: the block of residue rho starts at complex position freq_pos(rho).
+template <int N>
+CHS_DEV void unit_blocks(int t, int& rho_a, int& rho_b, int& base_a, int& base_b) {
+    constexpr int M = N / 2;
+    rho_a = (t == 0) ? 0 : t;
+    rho_b = (t == 0) ? (M / 16) : (M / 8 - t);
+    base_a = freq_pos<M>(rho_a);
+    base_b = freq_pos<M>(rho_b);
+}
+
+// Column slot s (PERM order used by T and hat_U along the x-spectral axis) holds frequency:
+//   s = 2*pos(k) + 0 -> k ;  s = 2*pos(k) + 1 -> N-k  (k = 0: M).   Host table `kof`.
 
 }  // namespace chs

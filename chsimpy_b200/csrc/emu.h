@@ -61,6 +61,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
 #define __restrict__
 #define __launch_bounds__(...)
 #define CHS_DEV static inline
+#define CHS_MEM inline
 #define CHS_HD static inline
 #define CHS_KERNEL static
 #define CHS_CX
