@@ -381,24 +381,45 @@ CHS_DEV void row_tile_store_phys(const double* sm, double* __restrict__ g, int t
 
 // ---------------------------------------------------------------------------------------
 // The 8 work items of a thread in the fused last stage.  A/B = the two 8-point blocks
-// (natural order within the block: frequency rho + (M/8)*c).  f.special(...) couples Z[0]
-// with Z[M/2]; f.pair(k, X, Y) couples Z[k] (X) with Z[M-k] (Y), always with k < M/2.
+// (natural order within the block: frequency rho + (M/8)*c).  Item c of group 1 couples
+// Z[k] = A[c] with Z[M-k] = B[7-c], k = rho_a + (M/8)c; group 2 the same with A and B
+// swapped and rho_b; always k < M/2.  Thread 0 owns the two self-paired blocks (rho = 0 and
+// M/16): swapping their upper halves first makes the same pairing pattern apply, with
+// k = 0 (Z[0] with Z[M/2]) as the one special item.
+//   f.begin(k0)                      first item's frequency (lets f start its global loads)
+//   f.first(k, knext, X, Y)          item that may be the special one (k == 0)
+//   f.pair(k, knext, X, Y)           knext < 0: no further item
 template <int N, class F>
 CHS_DEV void for_each_item(int t, int rho_a, int rho_b, double (&ar)[8], double (&ai)[8], double (&br)[8],
                            double (&bi)[8], F& f) {
     constexpr int Q = N / 16;                       // M/8
     if (t == 0) {
-        f.special(ar[0], ai[0], ar[4], ai[4]);
-        f.pair(Q * 1, ar[1], ai[1], ar[7], ai[7]);
-        f.pair(Q * 2, ar[2], ai[2], ar[6], ai[6]);
-        f.pair(Q * 3, ar[3], ai[3], ar[5], ai[5]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) f.pair(rho_b + Q * i, br[i], bi[i], br[7 - i], bi[7 - i]);
-    } else {
+        for (int h = 0; h < 2; ++h) {
+            double (&A)[8] = h ? ai : ar;
+            double (&B)[8] = h ? bi : br;
+            const double a4 = A[4], a5 = A[5], a6 = A[6], a7 = A[7];
+            A[4] = B[4]; A[5] = B[5]; A[6] = B[6]; A[7] = B[7];
+            B[4] = a5; B[5] = a6; B[6] = a7; B[7] = a4;
+        }
+    }
+    f.begin(rho_a);
+    f.first(rho_a, rho_a + Q, ar[0], ai[0], br[7], bi[7]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) f.pair(rho_a + Q * i, ar[i], ai[i], br[7 - i], bi[7 - i]);
+    for (int c = 1; c < 4; ++c)
+        f.pair(rho_a + Q * c, (c < 3) ? rho_a + Q * (c + 1) : rho_b, ar[c], ai[c], br[7 - c], bi[7 - c]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) f.pair(rho_b + Q * i, br[i], bi[i], ar[7 - i], ai[7 - i]);
+    for (int c = 0; c < 4; ++c)
+        f.pair(rho_b + Q * c, (c < 3) ? rho_b + Q * (c + 1) : -1, br[c], bi[c], ar[7 - c], ai[7 - c]);
+    if (t == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double (&A)[8] = h ? ai : ar;
+            double (&B)[8] = h ? bi : br;
+            const double b4 = B[4], b5 = B[5], b6 = B[6], b7 = B[7];
+            B[4] = A[4]; B[5] = A[5]; B[6] = A[6]; B[7] = A[7];
+            A[5] = b4; A[6] = b5; A[7] = b6; A[4] = b7;
+        }
     }
 }
 
@@ -420,12 +441,15 @@ CHS_DEV void store_block(double2* scl, int base, const double (&xr)[8], const do
 template <int N>
 struct RowPost {
     const double2* om;
-    CHS_MEM void special(double& ar, double& ai, double& hr, double& hi) {
-        double c[4];
-        post_special<N>(om, ar, ai, hr, hi, c);
-        ar = c[0]; ai = c[1]; hr = c[2]; hi = c[3];
+    CHS_MEM void begin(int) {}
+    CHS_MEM void first(int k, int kn, double& xr, double& xi, double& yr, double& yi) {
+        if (k == 0) {
+            double c[4];
+            post_special<N>(om, xr, xi, yr, yi, c);
+            xr = c[0]; xi = c[1]; yr = c[2]; yi = c[3];
+        } else pair(k, kn, xr, xi, yr, yi);
     }
-    CHS_MEM void pair(int k, double& xr, double& xi, double& yr, double& yi) {
+    CHS_MEM void pair(int k, int, double& xr, double& xi, double& yr, double& yi) {
         double c[4];
         post_pair<N>(k, om, xr, xi, yr, yi, c);
         xr = c[0]; xi = c[1]; yr = c[2]; yi = c[3];
@@ -434,17 +458,22 @@ struct RowPost {
 template <int N>
 struct RowPre {
     const double2* om;
-    CHS_MEM void special(double& ar, double& ai, double& hr, double& hi) {
-        const double c[4] = {ar, ai, hr, hi};
-        pre_special<N>(om, c, ar, ai, hr, hi);
+    CHS_MEM void begin(int) {}
+    CHS_MEM void first(int k, int kn, double& xr, double& xi, double& yr, double& yi) {
+        if (k == 0) {
+            const double c[4] = {xr, xi, yr, yi};
+            pre_special<N>(om, c, xr, xi, yr, yi);
+        } else pair(k, kn, xr, xi, yr, yi);
     }
-    CHS_MEM void pair(int k, double& xr, double& xi, double& yr, double& yi) {
+    CHS_MEM void pair(int k, int, double& xr, double& xi, double& yr, double& yi) {
         const double c[4] = {xr, xi, yr, yi};
         pre_pair<N>(k, om, c, xr, xi, yr, yi);
     }
 };
 
 // column kernels: the C values go to / come from global hat_U rows {k, N-k, M-k, M+k}
+// (special item: {0, M, M/2, 3M/2}).  The hat_U values of the NEXT item are loaded while the
+// current one is processed (one-item software pipeline; the tile was also prefetched to L2).
 template <int N, int MODE>
 struct ColMid {
     const double2* om;
@@ -454,43 +483,61 @@ struct ColMid {
     const double* hat_in;        // + column (COL_INV)
     double lam1, lam2, lamx, gx;
     double ge;
-    CHS_MEM void apply(const int (&idx)[4], double (&c)[4]) {
+    double hn[4];                // prefetched hat_U of the next item
+    CHS_MEM void rows_of(int k, int (&idx)[4]) {
+        constexpr int M = N / 2;
+        idx[0] = k;
+        idx[1] = (k == 0) ? M : N - k;
+        idx[2] = (k == 0) ? M / 2 : M - k;
+        idx[3] = (k == 0) ? M + M / 2 : M + k;
+    }
+    CHS_MEM void fetch(int k) {
+        if (MODE == COL_FWD) return;
+        int idx[4];
+        rows_of(k, idx);
+        const double* src = (MODE == COL_INV) ? hat_in : hat;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hn[j] = src[(size_t)idx[j] * N];
+    }
+    CHS_MEM void begin(int k) { fetch(k); }
+    CHS_MEM void apply(int k, int kn, double (&c)[4]) {
+        int idx[4];
+        rows_of(k, idx);
+        double h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = hn[j];
+        if (kn >= 0) fetch(kn);
         if (MODE == COL_FWD) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) hat[(size_t)idx[j] * N] = c[j];
         } else if (MODE == COL_STEP) {
-            double h[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = hat[(size_t)idx[j] * N];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const double leig = __ldg(lam + idx[j]) + lamx;
                 const double Se = __dmul_rn(lam1, leig);
                 const double CH = __dadd_rn(1.0, __dmul_rn(__dmul_rn(lam2, leig), leig));
-                const double hu = __ddiv_rn(__dadd_rn(h[j], __dmul_rn(Se, c[j])), CH);
+                const double hu = div_ge1(__dadd_rn(h[j], __dmul_rn(Se, c[j])), CH);
                 hat[(size_t)idx[j] * N] = hu;
                 ge += (__ldg(gsin + idx[j]) + gx) * (hu * hu);
                 c[j] = hu;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) c[j] = hat_in[(size_t)idx[j] * N];
+            for (int j = 0; j < 4; ++j) c[j] = h[j];
         }
     }
-    CHS_MEM void special(double& ar, double& ai, double& hr, double& hi) {
-        constexpr int M = N / 2;
-        const int idx[4] = {0, M, M / 2, M + M / 2};
-        double c[4];
-        if (MODE != COL_INV) post_special<N>(om, ar, ai, hr, hi, c);
-        apply(idx, c);
-        if (MODE != COL_FWD) pre_special<N>(om, c, ar, ai, hr, hi);
+    CHS_MEM void first(int k, int kn, double& xr, double& xi, double& yr, double& yi) {
+        if (k == 0) {
+            double c[4];
+            if (MODE != COL_INV) post_special<N>(om, xr, xi, yr, yi, c);
+            apply(k, kn, c);
+            if (MODE != COL_FWD) pre_special<N>(om, c, xr, xi, yr, yi);
+        } else pair(k, kn, xr, xi, yr, yi);
     }
-    CHS_MEM void pair(int k, double& xr, double& xi, double& yr, double& yi) {
-        constexpr int M = N / 2;
-        const int idx[4] = {k, N - k, M - k, M + k};
+    CHS_MEM void pair(int k, int kn, double& xr, double& xi, double& yr, double& yi) {
         double c[4];
         if (MODE != COL_INV) post_pair<N>(k, om, xr, xi, yr, yi, c);
-        apply(idx, c);
+        apply(k, kn, c);
         if (MODE != COL_FWD) pre_pair<N>(k, om, c, xr, xi, yr, yi);
     }
 };
@@ -708,7 +755,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_row(KArgs a) {
         const double meanU = diag ? a.hatU[off] / (double)N : 0.0;          // conserved mean (Q4)
         const double ra_mean = ra_line ? ra_scr[0] : 0.0;
         RowAcc acc = {0, 0, 0, 0, 0};
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < NB0; ++i) {
             const int j = t + i * TPL;
             double xr[R0], xi[R0];

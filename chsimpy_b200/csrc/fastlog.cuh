@@ -30,11 +30,32 @@ CHS_DEV double chs_ll2d(long long v) { return __longlong_as_double(v); }
 CHS_DEV double chs_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
 #endif
 
+// out-of-line slow path (keeps the 64 inlined copies of fast_log small: the instruction
+// cache matters for the fully unrolled row kernel)
+#ifdef CHS_EMU
+static inline double slow_log(double x) { return std::log(x); }
+static inline double div_ge1(double a, double b) { return a / b; }
+#else
+__device__ __noinline__ double slow_log(double x) { return log(x); }
+// a / b for finite b >= 1: reciprocal seed + 2 Newton steps + one residual correction
+// (no denormal/overflow slow path needed, unlike the generic IEEE division sequence)
+CHS_DEV double div_ge1(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = __fma_rn(-b, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-b, r, 1.0);
+    r = __fma_rn(r, e, r);
+    const double q = a * r;
+    return __fma_rn(__fma_rn(-b, q, a), r, q);
+}
+#endif
+
 // tab: LOG_TABLE_N entries {invc, logc} (shared or global memory)
 CHS_DEV double fast_log(double x, const double2* __restrict__ tab) {
     const unsigned long long ix = (unsigned long long)chs_d2ll(x);
     const unsigned top = (unsigned)(ix >> 52);                       // sign + exponent
-    if (top - 1u >= 0x7feu) return log(x);                           // <=0, subnormal, inf, nan
+    if (top - 1u >= 0x7feu) return slow_log(x);                      // <=0, subnormal, inf, nan
     const unsigned long long tmp = ix - LOG_OFF;
     const int i = (int)((tmp >> 45) & (LOG_TABLE_N - 1));
     const int k = (int)((long long)tmp >> 52);
