@@ -91,7 +91,8 @@ def load():
     """Returns the bound CUDA library, building it on first use.  Never falls back."""
     global _lib
     if _lib is None:
-        path = build()
+        # CHS_B200_LIB: an alternative build of the SAME CUDA library (tuning experiments only)
+        path = os.environ.get("CHS_B200_LIB") or build()
         _lib = bind(C.CDLL(path))
         if _lib.chs_abi_version() != 1:
             raise RuntimeError("libchs_b200.so ABI mismatch")

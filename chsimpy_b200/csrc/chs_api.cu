@@ -3,6 +3,7 @@
 // by g++ with -DCHS_EMU as the host test harness (chs_rt.h).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,6 +44,8 @@ struct chs_solver {
     std::vector<int> hindex;
     int n_running;
     long long launches;
+    int num_sms;
+    int cap_col[3], cap_row[4];     // resident CTAs per kernel mode (persistent grids)
     // optional per-kernel timing (bench.py)
     bool timing;
     std::vector<cudaEvent_t> events;       // 4 per iteration: before col, after col, after row, after diag
@@ -84,7 +87,7 @@ struct Layout {
 static Layout layout(int N, int batch) {
     Layout L;
     size_t o = 0;
-    const int ntiles = N / 16;
+    const int ntiles = N / CHS_LINES;
     L.sims = o; o = align_up(o + sizeof(Sim) * (size_t)batch);
     L.part = o; o = align_up(o + sizeof(double) * (size_t)batch * P_NSLOT * ntiles);
     L.colpart = o; o = align_up(o + sizeof(double) * (size_t)batch * ntiles * N);
@@ -124,8 +127,15 @@ extern "C" int64_t chs_workspace_bytes(int32_t N, int32_t batch) {
         default: return fail("unsupported N"); \
     }
 
+template <class K>
+static int resident_ctas(K kern, int threads, int smem, int num_sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, (size_t)smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * num_sms;
+}
+
 template <int N>
-static int set_attrs() {
+static int set_attrs(chs_solver* s) {
     const int b = Geo<N>::SMEM_BYTES;
     CHS_CUDA(cudaFuncSetAttribute(k_col<N, COL_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_col<N, COL_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
@@ -136,7 +146,27 @@ static int set_attrs() {
     CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_PREPARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_JITTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    const int nt = Geo<N>::NT, ns = s->num_sms;
+    s->cap_col[COL_FWD] = resident_ctas(k_col<N, COL_FWD>, nt, b, ns);
+    s->cap_col[COL_STEP] = resident_ctas(k_col<N, COL_STEP>, nt, b, ns);
+    s->cap_col[COL_INV] = resident_ctas(k_col<N, COL_INV>, nt, b, ns);
+    s->cap_row[ROW_FWD_U] = resident_ctas(k_row<N, ROW_FWD_U>, nt, b, ns);
+    s->cap_row[ROW_FWD_MU] = resident_ctas(k_row<N, ROW_FWD_MU>, nt, b, ns);
+    s->cap_row[ROW_STEP] = resident_ctas(k_row<N, ROW_STEP>, nt, b, ns);
+    s->cap_row[ROW_INV] = resident_ctas(k_row<N, ROW_INV>, nt, b, ns);
     return 0;
+}
+
+// Grid of a tile kernel: one CTA per tile (the host emulation loops over tiles with a few
+// blocks instead, see CHS_TILE_LOOP).
+static dim3 pgrid(int cap, int ntiles, int nsims) {
+    const long long total = (long long)ntiles * nsims;
+#ifdef CHS_EMU
+    return dim3((unsigned)(total < cap ? total : cap));
+#else
+    (void)cap;
+    return dim3((unsigned)total);
+#endif
 }
 
 static KArgs base_args(chs_solver* s) {
@@ -238,7 +268,9 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     ok &= cudaMemcpyAsync(s->index, s->hindex.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaStreamSynchronize(s->stream) == cudaSuccess;
     int rc = 0;
-#define CALL(NN) rc = set_attrs<NN>();
+    s->num_sms = 1;
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
+#define CALL(NN) rc = set_attrs<NN>(s);
     switch (N) {
         case 32: CALL(32) break; case 64: CALL(64) break; case 128: CALL(128) break;
         case 256: CALL(256) break; case 512: CALL(512) break; case 1024: CALL(1024) break;
@@ -348,11 +380,12 @@ template <int N>
 static int do_begin(chs_solver* s) {
     using G = Geo<N>;
     KArgs a = base_args(s);
-    const dim3 grid(G::NTILES, s->batch), block(G::NT);
+    a.nsims = s->batch;
+    const dim3 block(G::NT);
     CHS_LAUNCH(k_begin, dim3((s->batch + 127) / 128), dim3(128), 0, s->stream, s->sims, s->batch);
-    CHS_LAUNCH((k_row<N, ROW_FWD_U>), grid, block, G::SMEM_BYTES, s->stream, a);      // U -> T
-    CHS_LAUNCH((k_col<N, COL_FWD>), grid, block, G::SMEM_BYTES, s->stream, a);        // T -> hat_U
-    CHS_LAUNCH((k_row<N, ROW_FWD_MU>), grid, block, G::SMEM_BYTES, s->stream, a);     // mu(U) -> T, pre-part
+    CHS_LAUNCH((k_row<N, ROW_FWD_U>), pgrid(s->cap_row[ROW_FWD_U], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // U -> T
+    CHS_LAUNCH((k_col<N, COL_FWD>), pgrid(s->cap_col[COL_FWD], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);      // T -> hat_U
+    CHS_LAUNCH((k_row<N, ROW_FWD_MU>), pgrid(s->cap_row[ROW_FWD_MU], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);  // mu(U) -> T, pre-part
     s->launches += 4;
     CHS_CUDA(cudaGetLastError());
     return 0;
@@ -378,7 +411,9 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
     if (s->n_running <= 0) return 0;
     KArgs a = base_args(s);
     a.sim_index = (s->n_running == s->batch) ? nullptr : s->index;
+    a.nsims = s->n_running;
     const dim3 grid(G::NTILES, s->n_running), block(G::NT);
+    const dim3 gcol = pgrid(s->cap_col[COL_STEP], G::NTILES, a.nsims), grow = pgrid(s->cap_row[ROW_STEP], G::NTILES, a.nsims);
     for (long long it = 0; it < n_iters; ++it) {
         a.last = (last && it == n_iters - 1) ? 1 : 0;
         if (noise) {
@@ -389,9 +424,9 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
             if (s->ev_used + 4 > 65536 && drain_events(s)) return -1;
             cudaEventRecord(next_event(s), s->stream);
         }
-        CHS_LAUNCH((k_col<N, COL_STEP>), grid, block, G::SMEM_BYTES, s->stream, a);
+        CHS_LAUNCH((k_col<N, COL_STEP>), gcol, block, G::SMEM_BYTES, s->stream, a);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
-        CHS_LAUNCH((k_row<N, ROW_STEP>), grid, block, G::SMEM_BYTES, s->stream, a);
+        CHS_LAUNCH((k_row<N, ROW_STEP>), grow, block, G::SMEM_BYTES, s->stream, a);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
         s->launches += 2;
         if (noise) {
@@ -445,9 +480,10 @@ static int do_end(chs_solver* s) {
         CHS_CUDA(cudaMemcpyAsync(s->index, stale.data(), sizeof(int) * stale.size(), cudaMemcpyHostToDevice, s->stream));
         KArgs a = base_args(s);
         a.sim_index = s->index;
-        const dim3 grid(G::NTILES, (unsigned)stale.size()), block(G::NT);
-        CHS_LAUNCH((k_col<N, COL_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // hat_U -> T
-        CHS_LAUNCH((k_row<N, ROW_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // T -> U
+        a.nsims = (int)stale.size();
+        const dim3 block(G::NT);
+        CHS_LAUNCH((k_col<N, COL_INV>), pgrid(s->cap_col[COL_INV], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // hat_U -> T
+        CHS_LAUNCH((k_row<N, ROW_INV>), pgrid(s->cap_row[ROW_INV], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> U
         s->launches += 2;
         CHS_CUDA(cudaGetLastError());
     }
@@ -469,17 +505,18 @@ template <int N>
 static int do_dctn(chs_solver* s, const double* in, double* out, bool inverse) {
     using G = Geo<N>;
     KArgs a = base_args(s);
-    const dim3 grid(G::NTILES, s->batch), block(G::NT);
+    a.nsims = s->batch;
+    const dim3 block(G::NT);
     if (!inverse) {
         a.src = in; a.dst = nullptr;
-        CHS_LAUNCH((k_row<N, ROW_FWD_U>), grid, block, G::SMEM_BYTES, s->stream, a);  // in -> T
+        CHS_LAUNCH((k_row<N, ROW_FWD_U>), pgrid(s->cap_row[ROW_FWD_U], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);  // in -> T
         a.src = nullptr; a.dst = out; a.natural = 1;
-        CHS_LAUNCH((k_col<N, COL_FWD>), grid, block, G::SMEM_BYTES, s->stream, a);    // T -> out
+        CHS_LAUNCH((k_col<N, COL_FWD>), pgrid(s->cap_col[COL_FWD], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> out
     } else {
         a.src = in; a.dst = nullptr; a.natural = 1;
-        CHS_LAUNCH((k_col<N, COL_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // in -> T
+        CHS_LAUNCH((k_col<N, COL_INV>), pgrid(s->cap_col[COL_INV], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // in -> T
         a.src = nullptr; a.dst = out;
-        CHS_LAUNCH((k_row<N, ROW_INV>), grid, block, G::SMEM_BYTES, s->stream, a);    // T -> out
+        CHS_LAUNCH((k_row<N, ROW_INV>), pgrid(s->cap_row[ROW_INV], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> out
     }
     s->launches += 2;
     CHS_CUDA(cudaGetLastError());

@@ -82,7 +82,16 @@ struct KArgs {
     const double* mean_host;     // prepare: [batch] mean(U)
     int natural;                 // stand-alone transforms: natural column order on the far side
     int last;                    // no "pre" part after this iteration
+    int nsims;                   // simulations in this launch (entries of sim_index)
 };
+
+// one CTA per tile on the GPU (a resident-CTA loop measured slower and costs registers);
+// the host emulation keeps the loop so that few OS-thread blocks cover all tiles
+#ifdef CHS_EMU
+#define CHS_TILE_LOOP(w, total) for (int w = blockIdx.x; w < (total); w += gridDim.x)
+#else
+#define CHS_TILE_LOOP(w, total) const int w = blockIdx.x; if (w < (total))
+#endif
 
 #ifdef CHS_EMU
 #define CHS_LDCG(p) (*(p))
@@ -130,10 +139,11 @@ CHS_DEV void reduce_final(double (&v)[NV], const double* scratch, int nthreads) 
     }
 }
 
+// asynchronous copy of the 2 KB fast_log table (complete after chs_cp_async_wait_all() + barrier)
 template <class G>
 CHS_DEV double2* stage_logtab(double* sm, const double2* __restrict__ g, int tid) {
     double2* t = reinterpret_cast<double2*>(sm + G::OFF_LOGTAB);
-    for (int i = tid; i < LOG_TABLE_N; i += G::NT) t[i] = g[i];
+    for (int i = tid; i < LOG_TABLE_N; i += G::NT) chs_cp_async16(t + i, g + i);
     return t;
 }
 
@@ -280,22 +290,18 @@ CHS_DEV void col_pair_rows(int c, int& y0, int& y1) {      // rows holding v[2c]
     else { y0 = 2 * (N - 1 - 2 * c) + 1; y1 = y0 - 2; }
 }
 
+// issues the asynchronous copies of a column tile; complete after chs_cp_async_wait_all() + barrier
 template <int N>
-CHS_DEV void col_tile_load(double2* scl, const double* __restrict__ g, int t) {
+CHS_DEV void col_tile_load_async(double2* scl, const double* __restrict__ g, int t) {
     using G = Geo<N>;
-    constexpr int UNR = 4;
 #pragma unroll
-    for (int j0 = 0; j0 < 16; j0 += UNR) {
-        double a[UNR], b[UNR];
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            int y0, y1;
-            col_pair_rows<N>(t + (j0 + j) * G::TPL, y0, y1);
-            a[j] = g[(size_t)y0 * N];
-            b[j] = g[(size_t)y1 * N];
-        }
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) scl[(t + (j0 + j) * G::TPL) * G::LPC] = make_double2(a[j], b[j]);
+    for (int j = 0; j < 16; ++j) {
+        const int c = t + j * G::TPL;
+        int y0, y1;
+        col_pair_rows<N>(c, y0, y1);
+        double* d = reinterpret_cast<double*>(scl + c * G::LPC);
+        chs_cp_async8(d, g + (size_t)y0 * N);
+        chs_cp_async8(d + 1, g + (size_t)y1 * N);
     }
 }
 
@@ -315,23 +321,14 @@ CHS_DEV void col_tile_store(const double2* scl, double* __restrict__ g, int t) {
 
 // row tile in slot order: one complex element = two adjacent slots = one 16-byte access
 template <int N>
-CHS_DEV void row_tile_load_slots(double2* sc, const double* __restrict__ g, int tid) {
+CHS_DEV void row_tile_load_slots_async(double2* sc, const double* __restrict__ g, int tid) {
     using G = Geo<N>;
-    constexpr int M = G::M, CNT = G::LINES * M / G::NT, UNR = 8;       // CNT = 16
+    constexpr int M = G::M, CNT = G::LINES * M / G::NT;                // CNT = 16
     const double2* g2 = reinterpret_cast<const double2*>(g);
 #pragma unroll
-    for (int j0 = 0; j0 < CNT; j0 += UNR) {
-        double2 v[UNR];
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int i = tid + (j0 + j) * G::NT;
-            v[j] = g2[(size_t)(i / M) * M + (i % M)];
-        }
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int i = tid + (j0 + j) * G::NT;
-            sc[(i % M) * G::LPC + (i / M)] = v[j];
-        }
+    for (int j = 0; j < CNT; ++j) {
+        const int i = tid + j * G::NT;
+        chs_cp_async16(sc + (i % M) * G::LPC + (i / M), g2 + (size_t)(i / M) * M + (i % M));
     }
 }
 
@@ -483,7 +480,7 @@ struct ColMid {
     const double* hat_in;        // + column (COL_INV)
     double lam1, lam2, lamx, gx;
     double ge;
-    double hn[4];                // prefetched hat_U of the next item
+    double hn[4];                // hat_U of the next item (prefetched one item ahead)
     CHS_MEM void rows_of(int k, int (&idx)[4]) {
         constexpr int M = N / 2;
         idx[0] = k;
@@ -500,6 +497,8 @@ struct ColMid {
         for (int j = 0; j < 4; ++j) hn[j] = src[(size_t)idx[j] * N];
     }
     CHS_MEM void begin(int k) { fetch(k); }
+    // takes the prefetched hat_U of item k and immediately starts the loads of item kn, which
+    // then have this item's update + pre math and the next item's post math to arrive
     CHS_MEM void apply(int k, int kn, double (&c)[4]) {
         int idx[4];
         rows_of(k, idx);
@@ -511,6 +510,9 @@ struct ColMid {
 #pragma unroll
             for (int j = 0; j < 4; ++j) hat[(size_t)idx[j] * N] = c[j];
         } else if (MODE == COL_STEP) {
+            // g[k] = sin^2(pi k/N): g[N-k] = g[k], g[M-k] = g[M+k] = 1 - g[k]  (one lookup per item)
+            const double g0 = __ldg(gsin + idx[0]);
+            const double gs[4] = {g0, (k == 0) ? 1.0 : g0, (k == 0) ? 0.5 : 1.0 - g0, (k == 0) ? 0.5 : 1.0 - g0};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const double leig = __ldg(lam + idx[j]) + lamx;
@@ -518,7 +520,7 @@ struct ColMid {
                 const double CH = __dadd_rn(1.0, __dmul_rn(__dmul_rn(lam2, leig), leig));
                 const double hu = div_ge1(__dadd_rn(h[j], __dmul_rn(Se, c[j])), CH);
                 hat[(size_t)idx[j] * N] = hu;
-                ge += (__ldg(gsin + idx[j]) + gx) * (hu * hu);
+                ge += (gs[j] + gx) * (hu * hu);
                 c[j] = hu;
             }
         } else {
@@ -546,86 +548,100 @@ struct ColMid {
 //  column kernel
 // =======================================================================================
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_col(KArgs a) {
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
     using G = Geo<N>;
     constexpr int M = G::M, LINES = G::LINES, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
     double2* sc = reinterpret_cast<double2*>(sm);
+    // tables stay in global memory (L1-resident): shared-memory copies cost more LSU/MIO
+    // pressure than they save in latency (measured, profiles/)
+    const double2* __restrict__ s_tw = a.tw;
+    const double2* __restrict__ s_om = a.om;
+    const double* __restrict__ s_lam = a.lam;
     const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
-    const int sim = a.sim_index ? a.sim_index[blockIdx.y] : (int)blockIdx.y;
-    const int tile = blockIdx.x, kx0 = tile * LINES;
-    Sim* S = a.sims + sim;
-    if (MODE == COL_STEP && S->halted) return;
-    const size_t off = (size_t)sim * N * N;
     double2* scl = sc + l;
-    const int col = (MODE != COL_STEP && a.natural) ? a.kof[kx0 + l] : kx0 + l;   // far-side column
-    if (MODE == COL_STEP) {
-        // the hat_U tile is consumed in the middle of the kernel: pull it into L2 now
-        const double* hp = a.hatU + off + kx0;
-        for (int y = tid; y < N; y += NT) CHS_PREFETCH_L2(hp + (size_t)y * N);
-    }
-    // -------- load + forward column DCT-II up to the last stage
-    if (MODE != COL_INV) {
-        col_tile_load<N>(scl, a.T + off + kx0 + l, t);
-        __syncthreads();
-        fft_fwd_range<N, 0, NST - 1>(scl, t, a.tw);
-    }
-    // -------- fused: last forward stage + post + spectral update + pre + first inverse stage
-    {
-        int rho_a, rho_b, base_a, base_b;
-        unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-        double ar[8], ai[8], br[8], bi[8];
-        if (MODE != COL_INV) {
-            load_block<N>(scl, base_a, ar, ai);
-            load_block<N>(scl, base_b, br, bi);
-            dft<8, false>(ar, ai);
-            dft<8, false>(br, bi);
-        }
-        ColMid<N, MODE> mid;
-        mid.om = a.om; mid.lam = a.lam; mid.gsin = a.gsin;
-        mid.hat = ((MODE == COL_FWD && a.dst) ? a.dst : a.hatU) + off + col;
-        mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + off + col;
-        mid.ge = 0; mid.lam1 = mid.lam2 = mid.lamx = mid.gx = 0;
+    const int total = G::NTILES * a.nsims;
+    // persistent CTA: tiles w, w + gridDim.x, ... (consecutive w = neighbouring tiles of one sim)
+    CHS_TILE_LOOP(w, total) {
+        const int si = w / G::NTILES, tile = w % G::NTILES, kx0 = tile * LINES;
+        const int sim = a.sim_index ? a.sim_index[si] : si;
+        Sim* S = a.sims + sim;
+        const size_t off = (size_t)sim * N * N;
+        // all global traffic of the tile prologue is issued before the first dependent use
+        if (MODE != COL_INV) col_tile_load_async<N>(scl, a.T + off + kx0 + l, t);
         if (MODE == COL_STEP) {
+            // the hat_U tile is consumed in the middle of the tile's work: pull it into L2 now
+            const double* hp = a.hatU + off + kx0;
+            for (int y = tid; y < N; y += NT) CHS_PREFETCH_L2(hp + (size_t)y * N);
+        }
+        const int col = (MODE != COL_STEP && a.natural) ? a.kof[kx0 + l] : kx0 + l;   // far-side column
+        double lam1 = 0, lam2 = 0, lamx = 0, gxs = 0;
+        int halted = 0;
+        if (MODE == COL_STEP) {
+            halted = S->halted;
             const double delx2 = S->p.delx * S->p.delx;
-            mid.lam1 = S->delt_coef / delx2;                  // utils.py:41-42
-            mid.lam2 = S->p.kappa_tilde * mid.lam1 / delx2;
+            lam1 = S->delt_coef / delx2;                          // utils.py:41-42
+            lam2 = S->p.kappa_tilde * lam1 / delx2;
             const int kx = a.kof[kx0 + l];
-            mid.lamx = a.lam[kx];
-            mid.gx = a.gsin[kx];
+            lamx = a.lam[kx];
+            gxs = a.gsin[kx];
         }
-        for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, mid);
-        if (MODE == COL_FWD) return;
-        dft<8, true>(ar, ai);
-        dft<8, true>(br, bi);
-        store_block<N>(scl, base_a, ar, ai);
-        store_block<N>(scl, base_b, br, bi);
-        if (MODE == COL_STEP) {
-            const double v[1] = {mid.ge};
-            reduce_stage<1>(v, sm + G::OFF_RED, tid);
+        chs_cp_async_wait_all();
+        __syncthreads();
+        if (!halted) {
+            // -------- forward column DCT-II up to the last stage
+            if (MODE != COL_INV) fft_fwd_range<N, 0, NST - 1>(scl, t, s_tw);
+            // -------- fused: last forward stage + post + spectral update + pre + first inverse stage
+            int rho_a, rho_b, base_a, base_b;
+            unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+            double ar[8], ai[8], br[8], bi[8];
+            if (MODE != COL_INV) {
+                load_block<N>(scl, base_a, ar, ai);
+                load_block<N>(scl, base_b, br, bi);
+                dft<8, false>(ar, ai);
+                dft<8, false>(br, bi);
+            }
+            ColMid<N, MODE> mid;
+            mid.om = s_om; mid.lam = s_lam; mid.gsin = a.gsin;
+            mid.hat = ((MODE == COL_FWD && a.dst) ? a.dst : a.hatU) + off + col;
+            mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + off + col;
+            mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
+            for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, mid);
+            if (MODE != COL_FWD) {
+                dft<8, true>(ar, ai);
+                dft<8, true>(br, bi);
+                store_block<N>(scl, base_a, ar, ai);
+                store_block<N>(scl, base_b, br, bi);
+                if (MODE == COL_STEP) {
+                    const double v[1] = {mid.ge};
+                    reduce_stage<1>(v, sm + G::OFF_RED, tid);
+                }
+                __syncthreads();
+                // -------- remaining inverse stages
+                fft_inv_range<N, 0, NST - 1>(scl, t, s_tw);
+                // -------- partial sums: spectral gradient energy + one-sided y-edge terms
+                if (MODE == COL_STEP && tid == 0) {
+                    double v[1];
+                    reduce_final<1>(v, sm + G::OFF_RED, NT);
+                    double e = 0;
+                    for (int l2 = 0; l2 < LINES; ++l2) {
+                        const double u0 = sm[real_off<N>(mk_pos<N>(0)) + 2 * l2], u1 = sm[real_off<N>(mk_pos<N>(1)) + 2 * l2];
+                        const double v0 = sm[real_off<N>(mk_pos<N>(N - 1)) + 2 * l2], v1 = sm[real_off<N>(mk_pos<N>(N - 2)) + 2 * l2];
+                        e += (u1 - u0) * (u1 - u0) + (v0 - v1) * (v0 - v1);
+                    }
+                    double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
+                    pp[P_GE * G::NTILES] = v[0];
+                    pp[P_GYE * G::NTILES] = 0.75 * e;
+                }
+                // -------- store T tile
+                col_tile_store<N>(scl, a.T + off + kx0 + l, t);
+            }
         }
+        __syncthreads();                 // the tile buffer is reused by the next iteration
     }
-    __syncthreads();
-    // -------- remaining inverse stages
-    fft_inv_range<N, 0, NST - 1>(scl, t, a.tw);
-    // -------- partial sums: spectral gradient energy + one-sided y-edge terms (rows 0,1,N-2,N-1 of T)
-    if (MODE == COL_STEP && tid == 0) {
-        double v[1];
-        reduce_final<1>(v, sm + G::OFF_RED, NT);
-        double e = 0;
-        for (int l2 = 0; l2 < LINES; ++l2) {
-            const double u0 = sm[real_off<N>(mk_pos<N>(0)) + 2 * l2], u1 = sm[real_off<N>(mk_pos<N>(1)) + 2 * l2];
-            const double v0 = sm[real_off<N>(mk_pos<N>(N - 1)) + 2 * l2], v1 = sm[real_off<N>(mk_pos<N>(N - 2)) + 2 * l2];
-            e += (u1 - u0) * (u1 - u0) + (v0 - v1) * (v0 - v1);
-        }
-        double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
-        pp[P_GE * G::NTILES] = v[0];
-        pp[P_GYE * G::NTILES] = 0.75 * e;
-    }
-    // -------- store T tile
-    col_tile_store<N>(scl, a.T + off + kx0 + l, t);
+    chs_cp_async_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -665,7 +681,7 @@ CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const chs_params& 
 //  row kernel
 // =======================================================================================
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_row(KArgs a) {
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_row(KArgs a) {
     using G = Geo<N>;
     constexpr int M = G::M, LPC = G::LPC, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
@@ -673,197 +689,220 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_row(KArgs a) {
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
     double2* sc = reinterpret_cast<double2*>(sm);
+    const double2* __restrict__ s_tw = a.tw;
+    const double2* __restrict__ s_om = a.om;
     int* flag = reinterpret_cast<int*>(sm + G::OFF_FLAG);
     double* edge = sm + G::OFF_EDGE;
     double* ra_scr = sm + G::OFF_RA;
     const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
-    const int sim = a.sim_index ? a.sim_index[blockIdx.y] : (int)blockIdx.y;
-    const int tile = blockIdx.x, row0 = tile * LINES;
-    Sim* S = a.sims + sim;
-    if (MODE == ROW_STEP && S->halted) return;
-    const size_t off = (size_t)sim * N * N;
     double2* scl = sc + l;
     const bool control = (MODE == ROW_STEP) || (MODE == ROW_FWD_MU);
     const bool jit = (MODE == ROW_STEP) && (a.noise != nullptr);
     const bool diag = (MODE == ROW_STEP) && !jit;
     const double2* ltab = control ? stage_logtab<G>(sm, a.logtab, tid) : nullptr;
     const int ra_row = N / 2 + 1;                                           // int(N/2)+1, solver.py:226
-    const bool ra_line = diag && (row0 + l == ra_row);
-    const bool ra_tile = diag && (ra_row >= row0) && (ra_row < row0 + LINES);
-    bool slow = false;                      // adaptive-dt column sums / jitter / prologue: unfused middle
-    bool want_cols = false;
-    if (control) {
-        const long long cs_next = S->computed_steps + (MODE == ROW_STEP ? 1 : 0);
-        want_cols = S->p.adaptive_time && !a.last && cs_next > 500 && (cs_next % 2) == 0;
-        slow = want_cols || jit || (MODE == ROW_FWD_MU);
-    }
-
-    // ================= inverse half: T rows (slot order) -> U rows (Makhoul order in smem)
-    if (MODE == ROW_STEP || MODE == ROW_INV) {
-        row_tile_load_slots<N>(sc, a.T + off + (size_t)row0 * N, tid);
-        __syncthreads();
-        {   // fused: pre + first inverse stage (two 8-point blocks per thread)
-            int rho_a, rho_b, base_a, base_b;
-            unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-            double ar[8], ai[8], br[8], bi[8];
-            load_block<N>(scl, base_a, ar, ai);
-            load_block<N>(scl, base_b, br, bi);
-            if (ra_line && t == 0) ra_scr[0] = ar[0] * sqrt(1.0 / N);       // row mean = C[0]/sqrt(N)
-            RowPre<N> pre{a.om};
-            for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, pre);
-            dft<8, true>(ar, ai);
-            dft<8, true>(br, bi);
-            store_block<N>(scl, base_a, ar, ai);
-            store_block<N>(scl, base_b, br, bi);
+    const int total = G::NTILES * a.nsims;
+    // persistent CTA: tiles w, w + gridDim.x, ...
+    CHS_TILE_LOOP(w, total) {
+        const int si = w / G::NTILES, tile = w % G::NTILES, row0 = tile * LINES;
+        const int sim = a.sim_index ? a.sim_index[si] : si;
+        Sim* S = a.sims + sim;
+        const size_t off = (size_t)sim * N * N;
+        // tile prologue: every global access is issued before the first dependent use
+        if (MODE == ROW_STEP || MODE == ROW_INV) row_tile_load_slots_async<N>(sc, a.T + off + (size_t)row0 * N, tid);
+        const double hat00 = diag ? a.hatU[off] : 0.0;
+        const bool ra_line = diag && (row0 + l == ra_row);
+        const bool ra_tile = diag && (ra_row >= row0) && (ra_row < row0 + LINES);
+        bool slow = false;                  // adaptive-dt column sums / jitter / prologue: unfused middle
+        bool want_cols = false;
+        int halted = 0;
+        if (control) {
+            halted = (MODE == ROW_STEP) ? S->halted : 0;
+            const long long cs_next = S->computed_steps + (MODE == ROW_STEP ? 1 : 0);
+            want_cols = S->p.adaptive_time && !a.last && cs_next > 500 && (cs_next % 2) == 0;
+            slow = want_cols || jit || (MODE == ROW_FWD_MU);
         }
-        __syncthreads();
-        fft_inv_range<N, 1, NST - 1>(scl, t, a.tw);
-        if (MODE == ROW_INV || slow) {
-            fft_stage<N, 0, true>(scl, t, a.tw);
-            __syncthreads();
+        if (MODE == ROW_FWD_U || MODE == ROW_FWD_MU) {
+            const double* src = (MODE == ROW_FWD_U && a.src) ? a.src : a.U;
+            row_tile_load_phys<N>(sm, src + off + (size_t)row0 * N, tid);
         }
-    } else {
-        const double* src = (MODE == ROW_FWD_U && a.src) ? a.src : a.U;
-        row_tile_load_phys<N>(sm, src + off + (size_t)row0 * N, tid);
+        chs_cp_async_wait_all();
         __syncthreads();
-    }
-
-    if (MODE == ROW_INV) {
-        double* dstU = (a.dst ? a.dst : a.U) + off + (size_t)row0 * N;
-        row_tile_store_phys<N>(sm, dstU, tid);
-        return;
-    }
-
-    // ================= jitter (solver.py:210-211): U += jitter*(2*noise - 1), and U is state now
-    if (jit) {
-        const double jv = S->p.jitter;
-        const double* nz = a.noise + (size_t)row0 * N;
-        double* dstU = a.U + off + (size_t)row0 * N;
-        for (int i = tid; i < LINES * N; i += NT) {
-            const int l2 = i / N, x = i % N;
-            double* q = sm + real_off<N>(mk_pos<N>(x)) + 2 * l2;
-            const double u = *q + jv * (2.0 * nz[(size_t)l2 * N + x] - 1.0);
-            *q = u;
-            dstU[(size_t)l2 * N + x] = u;
-        }
-        __syncthreads();
-    }
-
-    // ================= physics + first forward stage
-    if (control) {
-        const chs_params p = S->p;
-        const double meanU = diag ? a.hatU[off] / (double)N : 0.0;          // conserved mean (Q4)
-        const double ra_mean = ra_line ? ra_scr[0] : 0.0;
-        RowAcc acc = {0, 0, 0, 0, 0};
-#pragma unroll 1
-        for (int i = 0; i < NB0; ++i) {
-            const int j = t + i * TPL;
-            double xr[R0], xi[R0];
-#pragma unroll
-            for (int q = 0; q < R0; ++q) {
-                const double2 v = scl[(j + q * ST0) * LPC];
-                xr[q] = v.x; xi[q] = v.y;
-            }
-            double2 w[R0];
-            if (!slow) {
-#pragma unroll
-                for (int q = 1; q < R0; ++q) {
-                    w[q] = __ldg(a.tw + j * q);
-                    const double x = xr[q], y = xi[q];
-                    xr[q] = x * w[q].x + y * w[q].y;                         // conj twiddle, then inverse DFT
-                    xi[q] = y * w[q].x - x * w[q].y;
-                }
-                dft<R0, true>(xr, xi);
-            }
-            physics<N, R0>(xr, xi, j, p, ltab, diag, meanU, ra_line, ra_mean, acc, edge + 4 * l);
-            if (!slow) {
-                dft<R0, false>(xr, xi);
-#pragma unroll
-                for (int q = 1; q < R0; ++q) {
-                    const double x = xr[q], y = xi[q];
-                    xr[q] = x * w[q].x - y * w[q].y;
-                    xi[q] = x * w[q].y + y * w[q].x;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < R0; ++q) scl[(j + q * ST0) * LPC] = make_double2(xr[q], xi[q]);
-        }
-        if (ra_line) ra_scr[2 + t] = acc.ra;
-        const double v[4] = {acc.f, acc.ab, acc.mu2, acc.cnt};
-        reduce_stage<4>(v, sm + G::OFF_RED, tid);
-        __syncthreads();
-        if (tid == 0) {
-            double s4[4];
-            reduce_final<4>(s4, sm + G::OFF_RED, NT);
-            double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
-            pp[P_MU2 * G::NTILES] = s4[2];
-            if (diag) {
-                double e = 0;
-                for (int l2 = 0; l2 < LINES; ++l2) {
-                    const double* eg = edge + 4 * l2;
-                    e += (eg[1] - eg[0]) * (eg[1] - eg[0]) + (eg[3] - eg[2]) * (eg[3] - eg[2]);
-                }
-                pp[P_GXE * G::NTILES] = 0.75 * e;
-                pp[P_F * G::NTILES] = s4[0];
-                pp[P_ABS * G::NTILES] = s4[1];
-                pp[P_CNT * G::NTILES] = s4[3];
-                if (ra_tile) {
-                    double s = 0;
-                    for (int jj = 0; jj < TPL; ++jj) s += ra_scr[2 + jj];
-                    S->ra = s / (double)N;
-                }
-            }
-        }
-        if (slow) {
-            // adaptive dt: column sums of delt_max/sqrt(1 + 62.5 mu^2) over this tile's rows (solver.py:182-183)
-            if (want_cols) {
-                for (int x = tid; x < N; x += NT) {
-                    const double* colp = sm + real_off<N>(mk_pos<N>(x));
-                    double s = 0;
-#pragma unroll
-                    for (int l2 = 0; l2 < LINES; ++l2) {
-                        const double m = colp[2 * l2];
-                        s += p.delt_max / sqrt(1.0 + 62.5 * (m * m));
-                    }
-                    a.colpart[((size_t)sim * G::NTILES + tile) * N + x] = s;
+        if (!halted) {
+            // ============= inverse half: T rows (slot order) -> U rows (Makhoul order in smem)
+            if (MODE == ROW_STEP || MODE == ROW_INV) {
+                {   // fused: pre + first inverse stage (two 8-point blocks per thread)
+                    int rho_a, rho_b, base_a, base_b;
+                    unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+                    double ar[8], ai[8], br[8], bi[8];
+                    load_block<N>(scl, base_a, ar, ai);
+                    load_block<N>(scl, base_b, br, bi);
+                    if (ra_line && t == 0) ra_scr[0] = ar[0] * sqrt(1.0 / N);       // row mean = C[0]/sqrt(N)
+                    RowPre<N> pre{s_om};
+                    for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, pre);
+                    dft<8, true>(ar, ai);
+                    dft<8, true>(br, bi);
+                    store_block<N>(scl, base_a, ar, ai);
+                    store_block<N>(scl, base_b, br, bi);
                 }
                 __syncthreads();
+                fft_inv_range<N, 1, NST - 1>(scl, t, s_tw);
+                if (MODE == ROW_INV || slow) {
+                    fft_stage<N, 0, true>(scl, t, s_tw);
+                    __syncthreads();
+                }
             }
-            fft_stage<N, 0, false>(scl, t, a.tw);
-            __syncthreads();
+            if (MODE == ROW_INV) {
+                double* dstU = (a.dst ? a.dst : a.U) + off + (size_t)row0 * N;
+                row_tile_store_phys<N>(sm, dstU, tid);
+            } else {
+                // ============= jitter (solver.py:210-211): U += jitter*(2*noise - 1); U is state now
+                if (jit) {
+                    const double jv = S->p.jitter;
+                    const double* nz = a.noise + (size_t)row0 * N;
+                    double* dstU = a.U + off + (size_t)row0 * N;
+                    for (int i = tid; i < LINES * N; i += NT) {
+                        const int l2 = i / N, x = i % N;
+                        double* q = sm + real_off<N>(mk_pos<N>(x)) + 2 * l2;
+                        const double u = *q + jv * (2.0 * nz[(size_t)l2 * N + x] - 1.0);
+                        *q = u;
+                        dstU[(size_t)l2 * N + x] = u;
+                    }
+                    __syncthreads();
+                }
+                // ============= physics + first forward stage
+                if (control) {
+                    const chs_params p = S->p;
+                    const double meanU = hat00 / (double)N;                     // conserved mean (Q4)
+                    const double ra_mean = ra_line ? ra_scr[0] : 0.0;
+                    RowAcc acc = {0, 0, 0, 0, 0};
+#pragma unroll 1
+                    for (int i = 0; i < NB0; ++i) {
+                        const int j = t + i * TPL;
+                        double xr[R0], xi[R0];
+                        double2 wv[R0];
+                        if (!slow) {
+#pragma unroll
+                            for (int q = 1; q < R0; ++q) wv[q] = __ldg(s_tw + j * q);
+                        }
+#pragma unroll
+                        for (int q = 0; q < R0; ++q) {
+                            const double2 v = scl[(j + q * ST0) * LPC];
+                            xr[q] = v.x; xi[q] = v.y;
+                        }
+                        if (!slow) {
+#pragma unroll
+                            for (int q = 1; q < R0; ++q) {
+                                const double x = xr[q], y = xi[q];
+                                xr[q] = x * wv[q].x + y * wv[q].y;               // conj twiddle, then inverse DFT
+                                xi[q] = y * wv[q].x - x * wv[q].y;
+                            }
+                            dft<R0, true>(xr, xi);
+                        }
+                        physics<N, R0>(xr, xi, j, p, ltab, diag, meanU, ra_line, ra_mean, acc, edge + 4 * l);
+                        if (!slow) {
+                            dft<R0, false>(xr, xi);
+#pragma unroll
+                            for (int q = 1; q < R0; ++q) {
+                                const double x = xr[q], y = xi[q];
+                                xr[q] = x * wv[q].x - y * wv[q].y;
+                                xi[q] = x * wv[q].y + y * wv[q].x;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < R0; ++q) scl[(j + q * ST0) * LPC] = make_double2(xr[q], xi[q]);
+                    }
+                    if (ra_line) ra_scr[2 + t] = acc.ra;
+                    const double v[4] = {acc.f, acc.ab, acc.mu2, acc.cnt};
+                    reduce_stage<4>(v, sm + G::OFF_RED, tid);
+                    __syncthreads();
+                    if (tid == 0) {
+                        double s4[4];
+                        reduce_final<4>(s4, sm + G::OFF_RED, NT);
+                        double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
+                        pp[P_MU2 * G::NTILES] = s4[2];
+                        if (diag) {
+                            double e = 0;
+                            for (int l2 = 0; l2 < LINES; ++l2) {
+                                const double* eg = edge + 4 * l2;
+                                e += (eg[1] - eg[0]) * (eg[1] - eg[0]) + (eg[3] - eg[2]) * (eg[3] - eg[2]);
+                            }
+                            pp[P_GXE * G::NTILES] = 0.75 * e;
+                            pp[P_F * G::NTILES] = s4[0];
+                            pp[P_ABS * G::NTILES] = s4[1];
+                            pp[P_CNT * G::NTILES] = s4[3];
+                            if (ra_tile) {
+                                double s = 0;
+                                for (int jj = 0; jj < TPL; ++jj) s += ra_scr[2 + jj];
+                                S->ra = s / (double)N;
+                            }
+                        }
+                        // Ticket now, not at the end of the tile: step_control() only needs every
+                        // CTA's partial sums, so the atomic's round trip hides behind the forward transform.
+                        if (!jit && !want_cols) {
+                            __threadfence();
+                            const unsigned prev = atomicAdd(&S->ticket, 1u);
+                            const int lastf = (prev == (unsigned)(G::NTILES - 1));
+                            if (lastf) S->ticket = 0;
+                            *flag = lastf;
+                        }
+                    }
+                    if (slow) {
+                        // adaptive dt: column sums of delt_max/sqrt(1 + 62.5 mu^2) over this tile's rows (solver.py:182-183)
+                        if (want_cols) {
+                            for (int x = tid; x < N; x += NT) {
+                                const double* colp = sm + real_off<N>(mk_pos<N>(x));
+                                double s = 0;
+#pragma unroll
+                                for (int l2 = 0; l2 < LINES; ++l2) {
+                                    const double m = colp[2 * l2];
+                                    s += p.delt_max / sqrt(1.0 + 62.5 * (m * m));
+                                }
+                                a.colpart[((size_t)sim * G::NTILES + tile) * N + x] = s;
+                            }
+                            __syncthreads();
+                        }
+                        fft_stage<N, 0, false>(scl, t, s_tw);
+                        __syncthreads();
+                    }
+                } else {
+                    fft_stage<N, 0, false>(scl, t, s_tw);            // ROW_FWD_U
+                    __syncthreads();
+                }
+                // ============= forward half: remaining stages, fused last stage + post, store
+                fft_fwd_range<N, 1, NST - 1>(scl, t, s_tw);
+                {
+                    int rho_a, rho_b, base_a, base_b;
+                    unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+                    double ar[8], ai[8], br[8], bi[8];
+                    load_block<N>(scl, base_a, ar, ai);
+                    load_block<N>(scl, base_b, br, bi);
+                    dft<8, false>(ar, ai);
+                    dft<8, false>(br, bi);
+                    RowPost<N> post{s_om};
+                    for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, post);
+                    store_block<N>(scl, base_a, ar, ai);
+                    store_block<N>(scl, base_b, br, bi);
+                }
+                __syncthreads();
+                row_tile_store_slots<N>(sc, ((MODE == ROW_FWD_U && a.dst) ? a.dst : a.T) + off + (size_t)row0 * N, tid);
+                // ============= control (with jitter k_diag finishes the iteration instead)
+                if (control && !jit) {
+                    bool is_last;
+                    if (want_cols) is_last = last_cta(S, G::NTILES, flag, tid, true);   // column sums were written by all threads
+                    else { __syncthreads(); is_last = (*flag != 0); if (is_last) __threadfence(); }
+                    if (is_last) {
+                        step_control<N>(S, a.part + (size_t)sim * P_NSLOT * G::NTILES,
+                                        a.colpart + (size_t)sim * G::NTILES * N,
+                                        a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last,
+                                        MODE == ROW_STEP, sm, tid, NT);
+                    }
+                }
+            }
         }
-    } else {
-        fft_stage<N, 0, false>(scl, t, a.tw);            // ROW_FWD_U
-        __syncthreads();
+        __syncthreads();                 // the tile buffer (and flag / scratch) is reused by the next iteration
     }
-
-    // ================= forward half: remaining stages, fused last stage + post, store
-    fft_fwd_range<N, 1, NST - 1>(scl, t, a.tw);
-    {
-        int rho_a, rho_b, base_a, base_b;
-        unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-        double ar[8], ai[8], br[8], bi[8];
-        load_block<N>(scl, base_a, ar, ai);
-        load_block<N>(scl, base_b, br, bi);
-        dft<8, false>(ar, ai);
-        dft<8, false>(br, bi);
-        RowPost<N> post{a.om};
-        for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, post);
-        store_block<N>(scl, base_a, ar, ai);
-        store_block<N>(scl, base_b, br, bi);
-    }
-    __syncthreads();
-    row_tile_store_slots<N>(sc, ((MODE == ROW_FWD_U && a.dst) ? a.dst : a.T) + off + (size_t)row0 * N, tid);
-
-    // ================= control (with jitter k_diag finishes the iteration instead)
-    if (control && !jit) {
-        if (last_cta(S, G::NTILES, flag, tid, want_cols)) {
-            step_control<N>(S, a.part + (size_t)sim * P_NSLOT * G::NTILES,
-                            a.colpart + (size_t)sim * G::NTILES * N,
-                            a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last,
-                            MODE == ROW_STEP, sm, tid, NT);
-        }
-    }
+    chs_cp_async_wait_all();
 }
 
 // =======================================================================================
@@ -889,6 +928,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
     if (MODE == DIAG_PREPARE) meanU = a.mean_host[sim];
     else meanU = a.hatU[(size_t)sim * N * N] / (double)N + p.jitter * (2.0 * a.noise_mean[0] - 1.0);
     const double2* ltab = stage_logtab<G>(sm, a.logtab, tid);
+    chs_cp_async_wait_all();
     __syncthreads();
     double v[4] = {0, 0, 0, 0};                    // raw grad^2 (x h^2), F, ABS, CNT
     for (int i = tid; i < LINES * N; i += NT) {

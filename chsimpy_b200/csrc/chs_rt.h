@@ -18,4 +18,14 @@
 #define CHS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define CHS_SMEM_DECL extern __shared__ __align__(16) unsigned char chs_smem_raw[];
 #define CHS_SMEM_PTR (chs_smem_raw)
+// asynchronous global->shared copies (LDGSTS): no register staging, all of a tile in flight
+__device__ __forceinline__ void chs_cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src));
+}
+__device__ __forceinline__ void chs_cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src));
+}
+__device__ __forceinline__ void chs_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 #endif

@@ -38,22 +38,34 @@ struct Rad {
     }
 };
 
+#ifndef CHS_LINES
+#define CHS_LINES 8
+#endif
+
 template <int N_>
 struct Geo {
     static constexpr int N = N_;
     static constexpr int M = N / 2;
-    static constexpr int LINES = 16;
+    static constexpr int LINES = CHS_LINES;
     static constexpr int LPC = LINES + 1;                      // line pitch in double2 (odd: conflict-free transposing I/O)
     static constexpr int TPL = M / 16;                         // threads per line: 16 complex points each per stage
     static constexpr int NT = LINES * TPL;                     // threads per CTA
     static constexpr int NTILES = N / LINES;
-    static constexpr int MINB = (N <= 512) ? 2 : 1;            // CTAs per SM the register budget is sized for
+    static constexpr int MINB = (65536 / 128) / NT > 16 ? 16 : ((65536 / 128) / NT > 0 ? (65536 / 128) / NT : 1);   // CTAs per SM at 128 registers/thread
+#ifndef CHS_MINB_ROW
+#define CHS_MINB_ROW 4
+#endif
+#ifndef CHS_MINB_COL
+#define CHS_MINB_COL 4
+#endif
+    static constexpr int MINB_ROW = (NT == 128) ? CHS_MINB_ROW : MINB;   // N = 512: tuned on B200 (profiles/)
+    static constexpr int MINB_COL = (NT == 128) ? CHS_MINB_COL : MINB;
     static constexpr int TILE_DOUBLES = 2 * M * LPC;
     // scratch after the tile (doubles): flag | x/y edge values | Ra | fast_log table | reduction
     static constexpr int OFF_FLAG = TILE_DOUBLES;
     static constexpr int OFF_EDGE = OFF_FLAG + 2;              // [LINES][4]
     static constexpr int OFF_RA = OFF_EDGE + 4 * LINES;        // mean, spare, then TPL partials
-    static constexpr int OFF_LOGTAB = OFF_RA + 2 + TPL + (TPL & 1);      // keeps double2 alignment
+    static constexpr int OFF_LOGTAB = OFF_RA + 2 + TPL + (TPL & 1);      // fast_log table, 128 double2 (keeps double2 alignment)
     static constexpr int OFF_RED = OFF_LOGTAB + 2 * 128;       // (NT/32+1)*8 doubles on the GPU; NT*8 in the host emulation
     static constexpr int SMEM_BYTES = (OFF_RED + (NT / 32 + 1) * 8 + 8) * 8;
     static_assert(N >= 32 && (N & (N - 1)) == 0, "FFT path needs a power of two >= 32");

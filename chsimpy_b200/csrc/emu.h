@@ -98,3 +98,9 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = 0; return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
+static inline void chs_cp_async16(void* d, const void* s) { std::memcpy(d, s, 16); }
+static inline void chs_cp_async8(void* d, const void* s) { std::memcpy(d, s, 8); }
+static inline void chs_cp_async_wait_all() {}
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 3; return 0; }   // 3 "SMs": exercises the persistent loops
+template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 1; return 0; }
