@@ -157,14 +157,18 @@ static int set_attrs(chs_solver* s) {
     return 0;
 }
 
-// Grid of a tile kernel: one CTA per tile (the host emulation loops over tiles with a few
-// blocks instead, see CHS_TILE_LOOP).
-static dim3 pgrid(int cap, int ntiles, int nsims) {
+// Grid of a tile kernel.  Default build: one CTA per tile.  -DCHS_PERSISTENT (experimental)
+// and the host emulation: resident CTAs that loop over tiles (CHS_TILE_LOOP); the environment
+// variable CHS_CTAS_PER_SM then caps the CTAs per SM so that two kernels of two handles on
+// two streams can be co-resident (tools/cosched_bench.py).
+static dim3 pgrid(int cap, int num_sms, int ntiles, int nsims) {
     const long long total = (long long)ntiles * nsims;
-#ifdef CHS_EMU
+#if defined(CHS_EMU) || defined(CHS_PERSISTENT)
+    static const int per_sm = [] { const char* e = getenv("CHS_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (per_sm > 0 && per_sm * num_sms < cap) cap = per_sm * num_sms;
     return dim3((unsigned)(total < cap ? total : cap));
 #else
-    (void)cap;
+    (void)cap; (void)num_sms;
     return dim3((unsigned)total);
 #endif
 }
@@ -383,9 +387,9 @@ static int do_begin(chs_solver* s) {
     a.nsims = s->batch;
     const dim3 block(G::NT);
     CHS_LAUNCH(k_begin, dim3((s->batch + 127) / 128), dim3(128), 0, s->stream, s->sims, s->batch);
-    CHS_LAUNCH((k_row<N, ROW_FWD_U>), pgrid(s->cap_row[ROW_FWD_U], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // U -> T
-    CHS_LAUNCH((k_col<N, COL_FWD>), pgrid(s->cap_col[COL_FWD], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);      // T -> hat_U
-    CHS_LAUNCH((k_row<N, ROW_FWD_MU>), pgrid(s->cap_row[ROW_FWD_MU], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);  // mu(U) -> T, pre-part
+    CHS_LAUNCH((k_row<N, ROW_FWD_U>), pgrid(s->cap_row[ROW_FWD_U], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // U -> T
+    CHS_LAUNCH((k_col<N, COL_FWD>), pgrid(s->cap_col[COL_FWD], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);      // T -> hat_U
+    CHS_LAUNCH((k_row<N, ROW_FWD_MU>), pgrid(s->cap_row[ROW_FWD_MU], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);  // mu(U) -> T, pre-part
     s->launches += 4;
     CHS_CUDA(cudaGetLastError());
     return 0;
@@ -413,7 +417,7 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
     a.sim_index = (s->n_running == s->batch) ? nullptr : s->index;
     a.nsims = s->n_running;
     const dim3 grid(G::NTILES, s->n_running), block(G::NT);
-    const dim3 gcol = pgrid(s->cap_col[COL_STEP], G::NTILES, a.nsims), grow = pgrid(s->cap_row[ROW_STEP], G::NTILES, a.nsims);
+    const dim3 gcol = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, a.nsims), grow = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, a.nsims);
     for (long long it = 0; it < n_iters; ++it) {
         a.last = (last && it == n_iters - 1) ? 1 : 0;
         if (noise) {
@@ -482,8 +486,8 @@ static int do_end(chs_solver* s) {
         a.sim_index = s->index;
         a.nsims = (int)stale.size();
         const dim3 block(G::NT);
-        CHS_LAUNCH((k_col<N, COL_INV>), pgrid(s->cap_col[COL_INV], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // hat_U -> T
-        CHS_LAUNCH((k_row<N, ROW_INV>), pgrid(s->cap_row[ROW_INV], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> U
+        CHS_LAUNCH((k_col<N, COL_INV>), pgrid(s->cap_col[COL_INV], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // hat_U -> T
+        CHS_LAUNCH((k_row<N, ROW_INV>), pgrid(s->cap_row[ROW_INV], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> U
         s->launches += 2;
         CHS_CUDA(cudaGetLastError());
     }
@@ -509,14 +513,14 @@ static int do_dctn(chs_solver* s, const double* in, double* out, bool inverse) {
     const dim3 block(G::NT);
     if (!inverse) {
         a.src = in; a.dst = nullptr;
-        CHS_LAUNCH((k_row<N, ROW_FWD_U>), pgrid(s->cap_row[ROW_FWD_U], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);  // in -> T
+        CHS_LAUNCH((k_row<N, ROW_FWD_U>), pgrid(s->cap_row[ROW_FWD_U], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);  // in -> T
         a.src = nullptr; a.dst = out; a.natural = 1;
-        CHS_LAUNCH((k_col<N, COL_FWD>), pgrid(s->cap_col[COL_FWD], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> out
+        CHS_LAUNCH((k_col<N, COL_FWD>), pgrid(s->cap_col[COL_FWD], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> out
     } else {
         a.src = in; a.dst = nullptr; a.natural = 1;
-        CHS_LAUNCH((k_col<N, COL_INV>), pgrid(s->cap_col[COL_INV], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // in -> T
+        CHS_LAUNCH((k_col<N, COL_INV>), pgrid(s->cap_col[COL_INV], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // in -> T
         a.src = nullptr; a.dst = out;
-        CHS_LAUNCH((k_row<N, ROW_INV>), pgrid(s->cap_row[ROW_INV], G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> out
+        CHS_LAUNCH((k_row<N, ROW_INV>), pgrid(s->cap_row[ROW_INV], s->num_sms, G::NTILES, a.nsims), block, G::SMEM_BYTES, s->stream, a);    // T -> out
     }
     s->launches += 2;
     CHS_CUDA(cudaGetLastError());

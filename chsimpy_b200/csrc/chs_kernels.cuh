@@ -87,8 +87,15 @@ struct KArgs {
 
 // one CTA per tile on the GPU (a resident-CTA loop measured slower and costs registers);
 // the host emulation keeps the loop so that few OS-thread blocks cover all tiles
-#ifdef CHS_EMU
-#define CHS_TILE_LOOP(w, total) for (int w = blockIdx.x; w < (total); w += gridDim.x)
+#if defined(CHS_EMU)
+#define CHS_TILE_FN static inline
+#elif defined(CHS_PERSISTENT)
+#define CHS_TILE_FN __device__ __noinline__
+#else
+#define CHS_TILE_FN __device__ __forceinline__
+#endif
+#if defined(CHS_EMU) || defined(CHS_PERSISTENT)
+#define CHS_TILE_LOOP(w, total) _Pragma("unroll 1") for (int w = blockIdx.x; w < (total); w += gridDim.x)
 #else
 #define CHS_TILE_LOOP(w, total) const int w = blockIdx.x; if (w < (total))
 #endif
@@ -547,24 +554,19 @@ struct ColMid {
 // =======================================================================================
 //  column kernel
 // =======================================================================================
+// one tile of the column kernel (out of line in the persistent build: the compiler then
+// allocates registers for the tile body alone)
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
+CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
     using G = Geo<N>;
     constexpr int M = G::M, LINES = G::LINES, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
-    CHS_SMEM_DECL
-    double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
     double2* sc = reinterpret_cast<double2*>(sm);
-    // tables stay in global memory (L1-resident): shared-memory copies cost more LSU/MIO
-    // pressure than they save in latency (measured, profiles/)
     const double2* __restrict__ s_tw = a.tw;
     const double2* __restrict__ s_om = a.om;
     const double* __restrict__ s_lam = a.lam;
     const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
     double2* scl = sc + l;
-    const int total = G::NTILES * a.nsims;
-    // persistent CTA: tiles w, w + gridDim.x, ... (consecutive w = neighbouring tiles of one sim)
-    CHS_TILE_LOOP(w, total) {
         const int si = w / G::NTILES, tile = w % G::NTILES, kx0 = tile * LINES;
         const int sim = a.sim_index ? a.sim_index[si] : si;
         Sim* S = a.sims + sim;
@@ -639,6 +641,16 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
                 col_tile_store<N>(scl, a.T + off + kx0 + l, t);
             }
         }
+}
+
+template <int N, int MODE>
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
+    using G = Geo<N>;
+    CHS_SMEM_DECL
+    double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    const int total = G::NTILES * a.nsims;
+    CHS_TILE_LOOP(w, total) {
+        k_col_tile<N, MODE>(a, w, sm);
         __syncthreads();                 // the tile buffer is reused by the next iteration
     }
     chs_cp_async_wait_all();
