@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libchs_b200.so")
-SOURCES = ("chs_api.cu", "chs_kernels.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
+SOURCES = ("chs_api.cu", "chs_kernels.cuh", "chs_slab.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -50,6 +50,26 @@ PROTOTYPES = {
     "chs_idctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "chs_debug_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "chs_launch_count": (C.c_int64, [C.c_void_p]),
+    "chs_slab_supports_n": (C.c_int32, [C.c_int32]),
+    "chs_slab_row_granularity": (C.c_int32, [C.c_int32]),
+    "chs_slab_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "chs_slab_create": (C.c_void_p, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Params),
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "chs_slab_destroy": (None, [C.c_void_p]),
+    "chs_slab_row": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double]),
+    "chs_slab_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "chs_slab_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "chs_slab_yedge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "chs_slab_clear_yedge": (C.c_int, [C.c_void_p]),
+    "chs_slab_reduce": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "chs_slab_vec": (C.c_void_p, [C.c_void_p]),
+    "chs_slab_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
+    "chs_slab_control": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "chs_slab_begin": (C.c_int, [C.c_void_p]),
+    "chs_slab_rewind_rows": (C.c_int, [C.c_void_p]),
+    "chs_slab_get_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
+    "chs_slab_set_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),
+    "chs_slab_launch_count": (C.c_int64, [C.c_void_p]),
     "chs_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "chs_get_timing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
 }

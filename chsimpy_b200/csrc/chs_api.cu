@@ -552,3 +552,297 @@ extern "C" int chs_debug_log(chs_solver* s, const double* x, double* y, int64_t 
 }
 
 extern "C" int64_t chs_launch_count(const chs_solver* s) { return s ? s->launches : 0; }
+
+// =======================================================================================
+//  Slab path (large single domain; see chs_slab.cuh and chsimpy_b200/slab.py)
+// =======================================================================================
+#include "chs_slab.cuh"
+
+struct chs_slab {
+    int device, N, rows, row_base, world, rank;
+    double *U, *rowsbuf;
+    long long rows_cap;
+    cudaStream_t stream;
+    Sim* sim;
+    double* part;        // [R_NVAL][ntiles] (also reused by prepare: [4][PREP_BLOCKS])
+    double* part_ge;     // [UPD_BLOCKS]
+    double* yedge;       // [1]
+    double* vec;         // [R_NVAL]
+    double2 *tw, *om, *logtab;
+    double *lam, *gsin;
+    int* kof;
+    Sim hsim;
+    long long launches;
+    int upd_used;
+};
+static const int SLAB_UPD_BLOCKS = 1184, SLAB_PREP_BLOCKS = 1184;
+
+static int slab_lines(int N) { return N <= 2048 ? CHS_LINES : 16384 / N; }
+
+struct SlabLayout { size_t sim, part, part_ge, yedge, vec, tw, om, lam, gsin, kof, logtab, total; };
+static SlabLayout slab_layout(int N, int rows) {
+    SlabLayout L; size_t o = 0;
+    const int ntiles = rows / slab_lines(N);
+    const size_t npart = (size_t)R_NVAL * ntiles > (size_t)4 * SLAB_PREP_BLOCKS ? (size_t)R_NVAL * ntiles : (size_t)4 * SLAB_PREP_BLOCKS;
+    L.sim = o; o = align_up(o + sizeof(Sim));
+    L.part = o; o = align_up(o + sizeof(double) * npart);
+    L.part_ge = o; o = align_up(o + sizeof(double) * SLAB_UPD_BLOCKS);
+    L.yedge = o; o = align_up(o + sizeof(double) * 2);
+    L.vec = o; o = align_up(o + sizeof(double) * R_NVAL);
+    L.tw = o; o = align_up(o + sizeof(double2) * (size_t)(N / 2));
+    L.om = o; o = align_up(o + sizeof(double2) * (size_t)N);
+    L.lam = o; o = align_up(o + sizeof(double) * (size_t)N);
+    L.gsin = o; o = align_up(o + sizeof(double) * (size_t)N);
+    L.kof = o; o = align_up(o + sizeof(int) * (size_t)N);
+    L.logtab = o; o = align_up(o + sizeof(double2) * (size_t)LOG_TABLE_N);
+    L.total = o;
+    return L;
+}
+
+extern "C" int32_t chs_slab_supports_n(int32_t N) {
+    return (N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || N == 8192 || N == 16384) ? 1 : 0;
+}
+extern "C" int32_t chs_slab_row_granularity(int32_t N) { return chs_slab_supports_n(N) ? slab_lines(N) : -1; }
+extern "C" int64_t chs_slab_workspace_bytes(int32_t N, int32_t rows) {
+    if (!chs_slab_supports_n(N) || rows < 1 || rows % slab_lines(N)) return -1;
+    return (int64_t)slab_layout(N, rows).total;
+}
+
+#define CHS_FOR_SLAB_N(N_, CALL)                \
+    switch (N_) {                               \
+        case 64: { CALL(64); } break;           \
+        case 128: { CALL(128); } break;         \
+        case 256: { CALL(256); } break;         \
+        case 512: { CALL(512); } break;         \
+        case 1024: { CALL(1024); } break;       \
+        case 2048: { CALL(2048); } break;       \
+        case 4096: { CALL(4096); } break;       \
+        case 8192: { CALL(8192); } break;       \
+        case 16384: { CALL(16384); } break;     \
+        default: return fail("unsupported N for the slab path"); \
+    }
+
+template <int N>
+static int slab_set_attrs() {
+    const int b = Geo<N>::SMEM_BYTES;
+    CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    return 0;
+}
+
+extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, int32_t row_base, int32_t world, int32_t rank,
+                                     const chs_params* p, double* U, double* rowsbuf, int64_t rows_cap,
+                                     void* workspace, int64_t workspace_bytes, const double* lambda_host, void* stream) {
+    if (!chs_slab_supports_n(N) || rows < 1 || rows % slab_lines(N) || !p) { fail("chs_slab_create: bad N/rows"); return nullptr; }
+    const SlabLayout L = slab_layout(N, rows);
+    if (workspace_bytes < (int64_t)L.total) { fail("chs_slab_create: workspace too small"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail("chs_slab_create: cudaSetDevice failed"); return nullptr; }
+    chs_slab* s = new chs_slab();
+    s->device = device; s->N = N; s->rows = rows; s->row_base = row_base; s->world = world; s->rank = rank;
+    s->U = U; s->rowsbuf = rowsbuf; s->rows_cap = rows_cap; s->stream = (cudaStream_t)stream;
+    unsigned char* w = (unsigned char*)workspace;
+    s->sim = (Sim*)(w + L.sim); s->part = (double*)(w + L.part); s->part_ge = (double*)(w + L.part_ge);
+    s->yedge = (double*)(w + L.yedge); s->vec = (double*)(w + L.vec);
+    s->tw = (double2*)(w + L.tw); s->om = (double2*)(w + L.om); s->lam = (double*)(w + L.lam);
+    s->gsin = (double*)(w + L.gsin); s->kof = (int*)(w + L.kof); s->logtab = (double2*)(w + L.logtab);
+    s->launches = 0; s->upd_used = 0;
+    std::memset(&s->hsim, 0, sizeof(Sim));
+    s->hsim.p = *p; s->hsim.delt = p->delt; s->hsim.delt_coef = p->delt;
+    const int M = N / 2;
+    std::vector<double2> tw(M), om(N), lt(LOG_TABLE_N);
+    std::vector<double> gs(N);
+    std::vector<int> kof(N);
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int m = 0; m < M; ++m) { const long double a = -2.0L * pi * m / M; tw[m] = make_double2((double)cosl(a), (double)sinl(a)); }
+    for (int m = 0; m < N; ++m) { const long double a = -pi * m / (2.0L * N); om[m] = make_double2((double)cosl(a), (double)sinl(a)); }
+    for (int k = 0; k < N; ++k) { const long double sn = sinl(pi * k / N); gs[k] = (double)(sn * sn); }
+    {
+        std::vector<int> rad; int lg = 0;
+        while ((1 << lg) < M) ++lg;
+        if (lg % 3) rad.push_back(1 << (lg % 3));
+        for (int i = 0; i < lg / 3; ++i) rad.push_back(8);
+        for (int k = 0; k < M; ++k) {
+            int pos = 0, Lb = M, kk = k;
+            for (int r : rad) { pos += (kk % r) * (Lb / r); kk /= r; Lb /= r; }
+            kof[2 * pos] = k; kof[2 * pos + 1] = (k == 0) ? M : N - k;
+        }
+    }
+    for (int i = 0; i < LOG_TABLE_N; ++i) {
+        const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << 45), b1 = LOG_OFF + ((unsigned long long)(i + 1) << 45);
+        double z0, z1; std::memcpy(&z0, &b0, 8); std::memcpy(&z1, &b1, 8);
+        const double invc = (double)(1.0L / ((long double)z0 * 0.5L + (long double)z1 * 0.5L));
+        lt[i] = make_double2(invc, (double)(-logl((long double)invc)));
+    }
+    bool ok = cudaMemsetAsync(workspace, 0, L.total, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->tw, tw.data(), sizeof(double2) * M, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->om, om.data(), sizeof(double2) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->gsin, gs.data(), sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->sim, &s->hsim, sizeof(Sim), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaStreamSynchronize(s->stream) == cudaSuccess;
+    int rc = 0;
+#define CALL(NN) rc = slab_set_attrs<NN>();
+    switch (N) {
+        case 64: CALL(64) break; case 128: CALL(128) break; case 256: CALL(256) break; case 512: CALL(512) break;
+        case 1024: CALL(1024) break; case 2048: CALL(2048) break; case 4096: CALL(4096) break;
+        case 8192: CALL(8192) break; case 16384: CALL(16384) break;
+    }
+#undef CALL
+    if (!ok || rc) { if (ok) {} else fail("chs_slab_create: table upload failed"); delete s; return nullptr; }
+    return s;
+}
+extern "C" void chs_slab_destroy(chs_slab* s) { delete s; }
+extern "C" double* chs_slab_vec(chs_slab* s) { return s ? s->vec : nullptr; }
+extern "C" int64_t chs_slab_launch_count(const chs_slab* s) { return s ? s->launches : 0; }
+
+template <int N>
+static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int rows, int row_base, int diag, double mean_u) {
+    using G = Geo<N>;
+    SlabArgs a;
+    a.src = src; a.dst = dst; a.Uout = s->U; a.rows = rows; a.row_base = row_base; a.diag = diag; a.mean_u = mean_u;
+    a.part = s->part; a.S = s->sim; a.tw = s->tw; a.om = s->om; a.logtab = s->logtab;
+    const int ntiles = rows / G::LINES;
+#ifdef CHS_EMU
+    const dim3 grid(ntiles < 3 ? ntiles : 3);
+#else
+    const dim3 grid(ntiles);
+#endif
+    const dim3 block(G::NT);
+    switch (mode) {
+        case S_FWD: CHS_LAUNCH((k_slab_row<N, S_FWD>), grid, block, G::SMEM_BYTES, s->stream, a); break;
+        case S_MU: CHS_LAUNCH((k_slab_row<N, S_MU>), grid, block, G::SMEM_BYTES, s->stream, a); break;
+        case S_INV: CHS_LAUNCH((k_slab_row<N, S_INV>), grid, block, G::SMEM_BYTES, s->stream, a); break;
+        case S_STEP: CHS_LAUNCH((k_slab_row<N, S_STEP>), grid, block, G::SMEM_BYTES, s->stream, a); break;
+        default: return fail("chs_slab_row: bad mode");
+    }
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// mode: 0 S_FWD (physical rows -> row DCT-II), 1 S_MU (U rows -> mu -> row DCT-II), 2 S_INV (row
+// DCT-III -> physical rows), 3 S_STEP (row DCT-III -> U stored in the handle's U buffer ->
+// diagnostics + mu -> row DCT-II).  `rows` rows starting at src/dst; row_base = global index.
+extern "C" int chs_slab_row(chs_slab* s, int32_t mode, const double* src, double* dst, int32_t rows, int32_t row_base,
+                            int32_t diag, double mean_u) {
+    if (!s || !src || !dst || rows < 1 || rows % slab_lines(s->N)) return fail("chs_slab_row: bad argument");
+#define CALL(NN) if (slab_row<NN>(s, mode, src, dst, rows, row_base, diag, mean_u)) return -1;
+    CHS_FOR_SLAB_N(s->N, CALL)
+#undef CALL
+    return 0;
+}
+
+extern "C" int chs_slab_transpose(chs_slab* s, const double* in, double* out, int32_t R, int32_t C, int32_t in_ld, int32_t out_ld) {
+    if (!s || !in || !out) return fail("chs_slab_transpose: bad argument");
+    CHS_LAUNCH(k_slab_transpose, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 32 * 33 * sizeof(double), s->stream,
+               in, out, (int)R, (int)C, (int)in_ld, (int)out_ld);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// H = (H + Seig*B)/CHeig on `rows` local slot-rows (global slot index slot_base + r)
+extern "C" int chs_slab_update(chs_slab* s, double* H, const double* B, int32_t rows, int32_t slot_base) {
+    if (!s || !H || !B) return fail("chs_slab_update: bad argument");
+#ifdef CHS_EMU
+    const int nb = 2, nt = 64;
+#else
+    const int nb = SLAB_UPD_BLOCKS, nt = 256;
+#endif
+    CHS_LAUNCH(k_slab_update, dim3(nb), dim3(nt), nt * sizeof(double), s->stream, H, B, (int)rows, s->N, (int)slot_base,
+               (const int*)s->kof, (const double*)s->lam, (const double*)s->gsin, (const Sim*)s->sim, s->part_ge);
+    s->upd_used = nb;
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// y-edge rows of the stored U (device pointers to row 0/1 or N-2/N-1 of the global field)
+extern "C" int chs_slab_yedge(chs_slab* s, const double* r0, const double* r1, int32_t accumulate) {
+    if (!s || !r0 || !r1) return fail("chs_slab_yedge: bad argument");
+    CHS_LAUNCH(k_slab_yedge, dim3(1), dim3(256), 256 * sizeof(double), s->stream, r0, r1, s->N, s->yedge, (int)accumulate);
+    s->launches += 1;
+    return 0;
+}
+extern "C" int chs_slab_clear_yedge(chs_slab* s) {
+    if (!s) return fail("chs_slab_clear_yedge: null handle");
+    CHS_CUDA(cudaMemsetAsync(s->yedge, 0, sizeof(double) * 2, s->stream));
+    return 0;
+}
+
+// local sums -> vec (to be all-reduced over ranks by the caller when world > 1)
+extern "C" int chs_slab_reduce(chs_slab* s, int32_t rows, int32_t with_update) {
+    if (!s) return fail("chs_slab_reduce: null handle");
+    CHS_LAUNCH(k_slab_reduce, dim3(1), dim3(32), 0, s->stream, (const double*)s->part, (int)(rows / slab_lines(s->N)),
+               (const double*)s->part_ge, with_update ? s->upd_used : 0, (const double*)s->yedge, s->vec);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chs_slab_prepare(chs_slab* s, const double* U_halo, double mean_u) {
+    if (!s || !U_halo) return fail("chs_slab_prepare: bad argument");
+#ifdef CHS_EMU
+    const int nb = 2, nt = 64;
+#else
+    const int nb = SLAB_PREP_BLOCKS, nt = 256;
+#endif
+    CHS_LAUNCH(k_slab_prepare, dim3(nb), dim3(nt), 4 * nt * sizeof(double), s->stream, U_halo, s->rows, s->row_base, s->N,
+               mean_u, (const Sim*)s->sim, (const double2*)s->logtab, s->part);
+    CHS_LAUNCH(k_slab_reduce_prepare, dim3(1), dim3(32), 0, s->stream, (const double*)s->part, nb, s->N, s->vec);
+    s->launches += 2;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// post: 0 prologue (only ||mu||^2 + pre part), 1 end of an iteration, 2 prepare (row 0)
+extern "C" int chs_slab_control(chs_slab* s, int32_t last, int32_t post) {
+    if (!s) return fail("chs_slab_control: null handle");
+    CHS_LAUNCH(k_slab_control, dim3(1), dim3(32), 0, s->stream, s->sim, (const double*)s->vec, s->rowsbuf, s->rows_cap, s->N,
+               (int)last, (int)post);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chs_slab_begin(chs_slab* s) {
+    if (!s) return fail("chs_slab_begin: null handle");
+    CHS_LAUNCH(k_begin, dim3(1), dim3(32), 0, s->stream, s->sim, 1);
+    s->launches += 1;
+    return 0;
+}
+extern "C" int chs_slab_rewind_rows(chs_slab* s) {
+    if (!s) return fail("chs_slab_rewind_rows: null handle");
+    CHS_LAUNCH(k_rewind, dim3(1), dim3(32), 0, s->stream, s->sim, 1);
+    s->launches += 1;
+    return 0;
+}
+
+extern "C" int chs_slab_get_state(chs_slab* s, chs_state* st, int64_t* rows_written, int32_t* halted) {
+    if (!s || !st) return fail("chs_slab_get_state: bad argument");
+    CHS_CUDA(cudaMemcpyAsync(&s->hsim, s->sim, sizeof(Sim), cudaMemcpyDeviceToHost, s->stream));
+    CHS_CUDA(cudaStreamSynchronize(s->stream));
+    const Sim& h = s->hsim;
+    st->delt = h.delt; st->time_delta_sum = h.time_delta_sum; st->time_passed = h.time_passed;
+    st->tau0 = h.tau0; st->t0 = h.t0; st->computed_steps = h.computed_steps;
+    st->skip_check = h.skip_check; st->stop_reason = h.stop_reason;
+    if (rows_written) *rows_written = h.rows_written;
+    if (halted) *halted = h.halted;
+    return 0;
+}
+extern "C" int chs_slab_set_state(chs_slab* s, const chs_state* st) {
+    if (!s || !st) return fail("chs_slab_set_state: bad argument");
+    CHS_CUDA(cudaMemcpyAsync(&s->hsim, s->sim, sizeof(Sim), cudaMemcpyDeviceToHost, s->stream));
+    CHS_CUDA(cudaStreamSynchronize(s->stream));
+    Sim& h = s->hsim;
+    h.delt = st->delt; h.time_delta_sum = st->time_delta_sum; h.time_passed = st->time_passed;
+    h.tau0 = st->tau0; h.t0 = st->t0; h.computed_steps = st->computed_steps;
+    h.skip_check = st->skip_check; h.stop_reason = st->stop_reason;
+    CHS_CUDA(cudaMemcpyAsync(s->sim, &h, sizeof(Sim), cudaMemcpyHostToDevice, s->stream));
+    CHS_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}

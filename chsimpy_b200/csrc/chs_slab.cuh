@@ -1,0 +1,360 @@
+// Slab path: one large N x N domain, row-slab decomposed over P ranks (P = 1: one GPU).
+// Every transform pass works on CONTIGUOUS rows, so the same row machinery serves both
+// directions; the direction change is a transpose -- a local tiled transpose for P = 1, an
+// NCCL all-to-all (issued by the host layer, chsimpy_b200/slab.py) plus the local
+// pack/unpack kernels below for P > 1.  One CH step (reference solver.py:165-249):
+//
+//   A  = rowDCT(mu(U))                       k_slab_row<S_STEP> of the previous step / <S_MU>
+//   B  = transpose(A)                        pack -> all-to-all -> unpack   (x-slot rows, y cols)
+//   B  = rowDCT(B)                           k_slab_row<S_FWD>    -> hat_mu'
+//   H  = (H + Seig*B)/CHeig, grad. energy    k_slab_update        (H = hat_U', slot order on both axes)
+//   B  = rowIDCT(H)                          k_slab_row<S_INV>
+//   A  = transpose(B)                        pack -> all-to-all -> unpack
+//   U, A = rowIDCT(A), physics, rowDCT(mu)   k_slab_row<S_STEP>   (per-tile partial sums)
+//   sums -> all-reduce -> k_slab_control     (TimeData row, NaN flag, stop test, time accounting)
+#pragma once
+#include "chs_kernels.cuh"
+
+namespace chs {
+
+enum { S_FWD = 0, S_MU = 1, S_INV = 2, S_STEP = 3 };
+// reduced vector layout (all-reduced over ranks)
+enum { R_GE = 0, R_EDGE, R_F, R_ABS, R_MU2, R_CNT, R_RA, R_NVAL };
+
+struct SlabArgs {
+    const double* src;
+    double* dst;
+    double* Uout;               // S_STEP: U_new rows are stored here
+    int rows;                   // local rows (multiple of LINES)
+    int row_base;               // global index of local row 0
+    int diag;                   // S_MU / S_STEP: accumulate the diagnostics of the field
+    double mean_u;              // conserved mean of U (PS)
+    double* part;               // [R_NVAL][rows/LINES] per-tile partial sums
+    Sim* S;
+    const double2* tw;
+    const double2* om;
+    const double2* logtab;
+};
+
+template <int N, int MODE>
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, 1) k_slab_row(SlabArgs a) {
+    using G = Geo<N>;
+    constexpr int M = G::M, LPC = G::LPC, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
+    constexpr int NST = Rad<M>::nst;
+    constexpr int R0 = Rad<M>::radix(0), ST0 = M / R0, NB0 = 16 / R0;
+    CHS_SMEM_DECL
+    double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    double2* sc = reinterpret_cast<double2*>(sm);
+    double* edge = sm + G::OFF_EDGE;
+    double* ra_scr = sm + G::OFF_RA;
+    const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
+    double2* scl = sc + l;
+    const int ntiles = a.rows / LINES;
+    const bool physics_on = (MODE == S_MU) || (MODE == S_STEP);
+    const bool diag = physics_on && a.diag;
+    const double2* ltab = physics_on ? stage_logtab<G>(sm, a.logtab, tid) : nullptr;
+    const int ra_row = N / 2 + 1;
+    CHS_TILE_LOOP(tile, ntiles) {
+        const int row0 = tile * LINES;
+        const size_t goff = (size_t)row0 * N;
+        if (MODE == S_INV || MODE == S_STEP) row_tile_load_slots_async<N>(sc, a.src + goff, tid);
+        else row_tile_load_phys<N>(sm, a.src + goff, tid);
+        const bool ra_line = diag && (a.row_base + row0 + l == ra_row);
+        const bool ra_tile = diag && (ra_row >= a.row_base + row0) && (ra_row < a.row_base + row0 + LINES);
+        chs_cp_async_wait_all();
+        __syncthreads();
+        if (MODE == S_INV || MODE == S_STEP) {
+            {
+                int rho_a, rho_b, base_a, base_b;
+                unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+                double ar[8], ai[8], br[8], bi[8];
+                load_block<N>(scl, base_a, ar, ai);
+                load_block<N>(scl, base_b, br, bi);
+                if (ra_line && t == 0) ra_scr[0] = ar[0] * sqrt(1.0 / N);
+                RowPre<N> pre{a.om};
+                for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, pre);
+                dft<8, true>(ar, ai);
+                dft<8, true>(br, bi);
+                store_block<N>(scl, base_a, ar, ai);
+                store_block<N>(scl, base_b, br, bi);
+            }
+            __syncthreads();
+            fft_inv_range<N, 0, NST - 1>(scl, t, a.tw);        // includes stage 0: the field is stored below
+        }
+        if (MODE == S_INV) {
+            row_tile_store_phys<N>(sm, a.dst + goff, tid);
+        } else {
+            if (MODE == S_STEP) {
+                row_tile_store_phys<N>(sm, a.Uout + goff, tid);  // reads only; no barrier needed before the in-place physics
+                __syncthreads();
+            }
+            if (physics_on) {
+                const chs_params p = a.S->p;
+                const double ra_mean = ra_line ? ra_scr[0] : 0.0;
+                RowAcc acc = {0, 0, 0, 0, 0};
+#pragma unroll 1
+                for (int i = 0; i < NB0; ++i) {
+                    const int j = t + i * TPL;
+                    double xr[R0], xi[R0];
+#pragma unroll
+                    for (int q = 0; q < R0; ++q) {
+                        const double2 v = scl[(j + q * ST0) * LPC];
+                        xr[q] = v.x; xi[q] = v.y;
+                    }
+                    physics<N, R0>(xr, xi, j, p, ltab, diag, a.mean_u, ra_line, ra_mean, acc, edge + 4 * l);
+                    dft<R0, false>(xr, xi);
+#pragma unroll
+                    for (int q = 1; q < R0; ++q) {
+                        const double2 w = __ldg(a.tw + j * q);
+                        const double x = xr[q], y = xi[q];
+                        xr[q] = x * w.x - y * w.y;
+                        xi[q] = x * w.y + y * w.x;
+                    }
+#pragma unroll
+                    for (int q = 0; q < R0; ++q) scl[(j + q * ST0) * LPC] = make_double2(xr[q], xi[q]);
+                }
+                if (ra_line) ra_scr[2 + t] = acc.ra;
+                const double v[4] = {acc.f, acc.ab, acc.mu2, acc.cnt};
+                reduce_stage<4>(v, sm + G::OFF_RED, tid);
+                __syncthreads();
+                if (tid == 0) {
+                    double s4[4];
+                    reduce_final<4>(s4, sm + G::OFF_RED, NT);
+                    double* pp = a.part + tile;
+                    double e = 0, ra = 0;
+                    if (diag) {
+                        for (int l2 = 0; l2 < LINES; ++l2) {
+                            const double* eg = edge + 4 * l2;
+                            e += (eg[1] - eg[0]) * (eg[1] - eg[0]) + (eg[3] - eg[2]) * (eg[3] - eg[2]);
+                        }
+                        if (ra_tile) {
+                            for (int jj = 0; jj < TPL; ++jj) ra += ra_scr[2 + jj];
+                            ra /= (double)N;
+                        }
+                    }
+                    pp[R_GE * ntiles] = 0;
+                    pp[R_EDGE * ntiles] = 0.75 * e;
+                    pp[R_F * ntiles] = s4[0];
+                    pp[R_ABS * ntiles] = s4[1];
+                    pp[R_MU2 * ntiles] = s4[2];
+                    pp[R_CNT * ntiles] = s4[3];
+                    pp[R_RA * ntiles] = ra;
+                }
+            } else {
+                fft_stage<N, 0, false>(scl, t, a.tw);
+                __syncthreads();
+            }
+            fft_fwd_range<N, 1, NST - 1>(scl, t, a.tw);
+            {
+                int rho_a, rho_b, base_a, base_b;
+                unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+                double ar[8], ai[8], br[8], bi[8];
+                load_block<N>(scl, base_a, ar, ai);
+                load_block<N>(scl, base_b, br, bi);
+                dft<8, false>(ar, ai);
+                dft<8, false>(br, bi);
+                RowPost<N> post{a.om};
+                for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, post);
+                store_block<N>(scl, base_a, ar, ai);
+                store_block<N>(scl, base_b, br, bi);
+            }
+            __syncthreads();
+            row_tile_store_slots<N>(sc, a.dst + goff, tid);
+        }
+        __syncthreads();
+    }
+    chs_cp_async_wait_all();
+}
+
+// H[r][c] = (H + Seig * B)/CHeig for the local x-slot rows r (global slot slot_base + r) and all
+// y-slots c; accumulates the spectral gradient energy sum (g[kx] + g[ky]) H^2 per block.
+CHS_KERNEL void k_slab_update(double* H, const double* B, int rows, int N, int slot_base, const int* kof,
+                              const double* lam, const double* gsin, const Sim* S, double* part_ge) {
+    const double delx2 = S->p.delx * S->p.delx;
+    const double lam1 = S->delt_coef / delx2;
+    const double lam2 = S->p.kappa_tilde * lam1 / delx2;
+    double ge = 0;
+    const size_t total = (size_t)rows * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / N), c = (int)(i % N);
+        const int kx = kof[slot_base + r], ky = kof[c];
+        const double leig = lam[ky] + lam[kx];
+        const double Se = __dmul_rn(lam1, leig);
+        const double CH = __dadd_rn(1.0, __dmul_rn(__dmul_rn(lam2, leig), leig));
+        const double hu = __ddiv_rn(__dadd_rn(H[i], __dmul_rn(Se, B[i])), CH);
+        H[i] = hu;
+        ge += (gsin[kx] + gsin[ky]) * (hu * hu);
+    }
+    // block sum through shared memory (fixed order)
+    CHS_SMEM_DECL
+    double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    red[threadIdx.x] = ge;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (unsigned j = 0; j < blockDim.x; ++j) s += red[j];
+        part_ge[blockIdx.x] = s;
+    }
+}
+
+// out[c][r] = in[r][c] for an R x C row-major block, through a 32x33 shared tile.
+// in_ld / out_ld: leading dimensions; used for the local transpose (P = 1) and for the
+// per-peer blocks around the all-to-all (P > 1).
+CHS_KERNEL void k_slab_transpose(const double* in, double* out, int R, int C, int in_ld, int out_ld) {
+    CHS_SMEM_DECL
+    double* tile = reinterpret_cast<double*>(CHS_SMEM_PTR);       // 32*33 doubles
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;       // 256 threads: 32 x 8
+    for (int k = ty; k < 32; k += 8)
+        if (by + k < R && bx + tx < C) tile[k * 33 + tx] = in[(size_t)(by + k) * in_ld + bx + tx];
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8)
+        if (bx + k < C && by + tx < R) out[(size_t)(bx + k) * out_ld + by + tx] = tile[tx * 33 + k];
+}
+
+// y-edge terms of the gradient energy from two stored rows of U: 3/4 * sum_x (U[r1][x]-U[r0][x])^2
+CHS_KERNEL void k_slab_yedge(const double* r0, const double* r1, int N, double* out, int accumulate) {
+    CHS_SMEM_DECL
+    double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    double s = 0;
+    for (int x = threadIdx.x; x < N; x += blockDim.x) { const double d = r1[x] - r0[x]; s += d * d; }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (unsigned j = 0; j < blockDim.x; ++j) t += red[j];
+        out[0] = (accumulate ? out[0] : 0.0) + 0.75 * t;
+    }
+}
+
+// Solver.prepare() on a slab with one halo row above and below (Uh = [rows+2][N], row 0 and
+// row rows+1 are the neighbours' rows; ignored at the domain edges): np.gradient stencils,
+// free energy, |U - mean|, and Ra of global row N/2+1; per-block partial sums [4][gridDim.x].
+CHS_KERNEL void k_slab_prepare(const double* Uh, int rows, int row_base, int N, double mean_u, const Sim* S,
+                               const double2* logtab, double* part) {
+    CHS_SMEM_DECL
+    double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);      // 4 * blockDim.x
+    const chs_params p = S->p;
+    const double* U = Uh + N;                                    // local row 0
+    const int ra_row = N / 2 + 1 - row_base;                     // local index (may be out of range)
+    double ra_mean = 0;
+    if (ra_row >= 0 && ra_row < rows) {                          // every block recomputes the row mean (cheap, deterministic)
+        double s = 0;
+        for (int x = 0; x < N; ++x) s += U[(size_t)ra_row * N + x];
+        ra_mean = s / (double)N;
+    }
+    double v[4] = {0, 0, 0, 0};
+    const size_t total = (size_t)rows * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / N), x = (int)(i % N);
+        const int gy_ = row_base + y;
+        const double c = U[i];
+        double gy, gx;
+        if (gy_ == 0) gy = U[i + N] - c;
+        else if (gy_ == N - 1) gy = c - U[i - N];
+        else gy = 0.5 * (U[i + N] - U[i - N]);
+        if (x == 0) gx = U[i + 1] - c;
+        else if (x == N - 1) gx = c - U[i - 1];
+        else gx = 0.5 * (U[i + 1] - U[i - 1]);
+        double f, mu;
+        thermo(c, p, logtab, f, mu);
+        v[0] += gy * gy + gx * gx;
+        v[1] += f;
+        v[2] += fabs(c - mean_u);
+        if (y == ra_row) v[3] += fabs(c - ra_mean);
+    }
+    for (int k = 0; k < 4; ++k) red[k * blockDim.x + threadIdx.x] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (unsigned j = 0; j < blockDim.x; ++j) s += red[threadIdx.x * blockDim.x + j];
+        part[threadIdx.x * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// prepare: vec from the k_slab_prepare block sums
+CHS_KERNEL void k_slab_reduce_prepare(const double* part, int nblk, int N, double* vec) {
+    if (threadIdx.x != 0) return;
+    double s[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < nblk; ++i) s[k] += part[k * nblk + i];
+    for (int v = 0; v < R_NVAL; ++v) vec[v] = 0;
+    vec[R_GE] = s[0]; vec[R_F] = s[1]; vec[R_ABS] = s[2]; vec[R_RA] = s[3] / (double)N;
+}
+
+// vec[v] = sum over tiles of part[v][*] (+ the update kernel's GE blocks, + y-edge), fixed order
+CHS_KERNEL void k_slab_reduce(const double* part, int ntiles, const double* part_ge, int nge, const double* yedge,
+                              double* vec) {
+    const int v = threadIdx.x;
+    if (v >= R_NVAL) return;
+    double s = 0;
+    for (int i = 0; i < ntiles; ++i) s += part[v * ntiles + i];
+    if (v == R_GE) for (int i = 0; i < nge; ++i) s += part_ge[i];
+    if (v == R_EDGE) s += yedge[0];
+    vec[v] = s;
+}
+
+// step_control() of the tile path, fed with the rank-reduced sums (one thread; every rank runs
+// it on identical inputs and so keeps an identical Sim image).  post = 0: prologue.
+CHS_KERNEL void k_slab_control(Sim* S, const double* vec, double* rows, long long rows_cap, int N, int last, int post) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const chs_params& p = S->p;
+    if (post == 2) {                     // Solver.prepare(): row 0 (solver.py:117-135)
+        const double N2 = (double)N * (double)N, L2sq = p.L * p.L;
+        const double E2 = 0.5 * p.Amr * p.kappa_tilde * L2sq * ((vec[R_GE] / (p.delx * p.delx)) / N2);
+        const double E = p.Amr * L2sq * (vec[R_F] / N2) + E2;
+        const double PS = vec[R_ABS] / N2;
+        S->ra = vec[R_RA];
+        double* r = rows;
+        r[CHS_COL_IT] = 0; r[CHS_COL_E] = E; r[CHS_COL_E2] = E2; r[CHS_COL_SA] = 0; r[CHS_COL_DOMTIME] = 0;
+        r[CHS_COL_RA] = S->ra; r[CHS_COL_L2] = 0; r[CHS_COL_PS] = PS; r[CHS_COL_DELT] = S->delt;
+        S->rows_written = 1;
+        S->e2_first = E2; S->e2_prev = E2;
+        S->tau0 = 0; S->t0 = 0;
+        S->stop_reason = ((E != E) || (E2 != E2) || (PS != PS)) ? CHS_STOP_NAN : CHS_STOP_NONE;
+        S->computed_steps = 1;
+        S->halted = 0;
+        return;
+    }
+    if (post) {
+        const double N2 = (double)N * (double)N, L2sq = p.L * p.L;
+        const double grad2 = (vec[R_GE] + vec[R_EDGE]) / (p.delx * p.delx);
+        const double E2 = 0.5 * p.Amr * p.kappa_tilde * L2sq * (grad2 / N2);
+        const double E = p.Amr * L2sq * (vec[R_F] / N2) + E2;
+        const double PS = vec[R_ABS] / N2, L2 = sqrt(S->mu2_pending) / N2, SA = vec[R_CNT] / N2;
+        const double domtime = pow(S->time_passed, 1.0 / 3.0);
+        S->mu2_pending = vec[R_MU2];
+        S->ra = vec[R_RA];
+        const long long rw = S->rows_written;
+        if (rw < rows_cap) {
+            double* r = rows + rw * CHS_NCOLS;
+            r[CHS_COL_IT] = (double)S->computed_steps;
+            r[CHS_COL_E] = E; r[CHS_COL_E2] = E2; r[CHS_COL_SA] = SA; r[CHS_COL_DOMTIME] = domtime;
+            r[CHS_COL_RA] = S->ra; r[CHS_COL_L2] = L2; r[CHS_COL_PS] = PS; r[CHS_COL_DELT] = S->delt;
+        }
+        S->rows_written = rw + 1;
+        S->u_stale = 0;
+        if ((E != E) || (E2 != E2) || (SA != SA) || (domtime != domtime) || (S->ra != S->ra) || (L2 != L2) || (PS != PS)) {
+            S->stop_reason = CHS_STOP_NAN;
+            S->halted = 1;
+            return;
+        }
+        S->computed_steps += 1;
+        const bool falls = (S->e2_prev > E2) && (E2 > S->e2_first);
+        S->e2_prev = E2;
+        if (!S->skip_check && falls) {
+            S->tau0 = (double)S->computed_steps;
+            S->t0 = S->time_passed;
+            if (!p.full_sim) { S->stop_reason = CHS_STOP_ENERGY; S->halted = 1; return; }
+            S->skip_check = 1;
+        }
+    } else {
+        S->mu2_pending = vec[R_MU2];
+    }
+    if (last) return;
+    S->time_delta_sum += S->delt;
+    S->time_passed = S->time_delta_sum / p.M_tilde;
+    if (p.time_limit_s > 0.0 && S->time_passed > p.time_limit_s) { S->stop_reason = CHS_STOP_TIME; S->halted = 1; }
+}
+
+}  // namespace chs

@@ -46,8 +46,10 @@ template <int N_>
 struct Geo {
     static constexpr int N = N_;
     static constexpr int M = N / 2;
-    static constexpr int LINES = CHS_LINES;
-    static constexpr int LPC = LINES + 1;                      // line pitch in double2 (odd: conflict-free transposing I/O)
+    // 8 lines per tile up to N = 2048; larger rows shrink the tile so that it still fits in
+    // shared memory (only the row kernels of the slab path are built for N > 1024)
+    static constexpr int LINES = (N <= 2048) ? CHS_LINES : (16384 / N);
+    static constexpr int LPC = (LINES == 1) ? 1 : LINES + 1;   // line pitch in double2 (odd: conflict-free transposing I/O)
     static constexpr int TPL = M / 16;                         // threads per line: 16 complex points each per stage
     static constexpr int NT = LINES * TPL;                     // threads per CTA
     static constexpr int NTILES = N / LINES;

@@ -1,0 +1,206 @@
+"""Large single domain: one N x N simulation row-slab decomposed over the GPUs of a box
+(BASELINE config 5), or run on one GPU when it does not fit the batched tile path (N > 1024).
+
+Every transform pass of the stepper works on contiguous rows; the change of direction is a
+transpose.  With P ranks each rank owns R = N/P rows of U and R x-spectral rows of hat_U and
+one CH step is (chs_slab.cuh):
+
+    B = transpose(A)          local pack kernels + NCCL all-to-all over NVLink (P > 1)
+    B = rowDCT(B); H = (H + Seig*B)/CHeig; B = rowIDCT(H)
+    A = transpose(B)          second all-to-all
+    U, A = rowIDCT(A) -> physics, diagnostics -> rowDCT(mu)
+    7 diagnostic sums: all-reduce (NCCL) -> device-side control kernel (TimeData row, stop test)
+
+No host synchronisation happens inside a chunk of steps; the host polls the stop flag every
+`poll_every` steps exactly like the batched path.  `SlabEngine` has the same interface as
+`BatchStepper` (batch of one), so `Solver` drives either.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, utils
+
+
+class SlabEngine:
+    S_FWD, S_MU, S_INV, S_STEP = 0, 1, 2, 3
+
+    def __init__(self, N, param_struct, rows_cap=1024, backend=None, device=None, world=None):
+        from .solver import _CudaBackend
+        self.be = backend if backend is not None else _CudaBackend(device)
+        lib = self.lib = self.be.lib
+        self.N = int(N)
+        self.rank, self.P = (0, 1) if world is None else (int(world[0]), int(world[1]))
+        if not lib.chs_slab_supports_n(self.N):
+            raise ValueError(f"N={N} is not supported by the slab path (powers of two, 64..16384)")
+        gran = lib.chs_slab_row_granularity(self.N)
+        if self.N % self.P or (self.N // self.P) % gran or self.N // self.P < 2:
+            raise ValueError(f"N={N} cannot be split into {self.P} slabs of a multiple of {gran} rows")
+        if self.P > 1 and self.be.name != "cuda":
+            raise ValueError("multi-rank slabs need CUDA + NCCL")
+        self.R = R = self.N // self.P
+        self.row_base = self.rank * R
+        self.batch, self.rows_cap = 1, int(rows_cap)
+        n = self.N
+        self.U = self.be.empty((R, n))
+        self.A = self.be.empty((R, n))
+        self.B = self.be.empty((R, n))
+        self.H = self.be.empty((R, n))
+        self.Uh = None                                   # [R+2][N] halo copy, prepare() only
+        self.rows = self.be.empty((self.rows_cap, 9))
+        if self.P > 1:
+            self.send = self.be.empty((self.P, R, R))
+            self.recv = self.be.empty((self.P, R, R))
+        wbytes = lib.chs_slab_workspace_bytes(n, R)
+        self.work = self.be.empty((wbytes,), "u1")
+        lam = np.ascontiguousarray(utils.laplace_spectrum_1d(n), dtype=np.float64)
+        self._ps = param_struct
+        self._h = _lib.check(lib, lib.chs_slab_create(self.be.device_index(), n, R, self.row_base, self.P, self.rank,
+                                                       C.byref(param_struct), self.be.ptr(self.U), self.be.ptr(self.rows),
+                                                       self.rows_cap, self.be.ptr(self.work), wbytes, lam.ctypes.data,
+                                                       self.be.stream_handle()), "chs_slab_create")
+        vec_ptr = lib.chs_slab_vec(self._h)
+        off = vec_ptr - self.be.ptr(self.work)
+        self._vec = self.work[off:off + 56].view(self.be.torch.float64) if self.be.name == "cuda" else None
+        self._full = None
+        self._mean = 0.0
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self.lib.chs_slab_destroy(h)
+
+    # -- helpers ----------------------------------------------------------------------------
+    def _ck(self, rc, what):
+        return _lib.check(self.lib, rc, what)
+
+    def _row(self, mode, src, dst, diag=0):
+        self._ck(self.lib.chs_slab_row(self._h, mode, self.be.ptr(src), self.be.ptr(dst), self.R, self.row_base,
+                                       int(diag), float(self._mean)), "chs_slab_row")
+
+    def _allreduce_vec(self):
+        if self.P > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._vec)                  # 7 doubles, NCCL; identical on every rank
+
+    def _transpose(self, src, dst):
+        """dst[c_local][r_global] = src[r_local][c_global] (works in both directions)."""
+        lib, h, be, R, N, P = self.lib, self._h, self.be, self.R, self.N, self.P
+        if P == 1:
+            self._ck(lib.chs_slab_transpose(h, be.ptr(src), be.ptr(dst), N, N, N, N), "chs_slab_transpose")
+            return
+        import torch.distributed as dist
+        esz = 8
+        for p in range(P):                               # block p of my rows, transposed, goes to rank p
+            self._ck(lib.chs_slab_transpose(h, be.ptr(src) + p * R * esz, be.ptr(self.send) + p * R * R * esz,
+                                            R, R, N, R), "chs_slab_transpose")
+        dist.all_to_all_single(self.recv, self.send)     # NCCL over NVLink / NVSwitch
+        # recv[q] = [c_local][r_local of rank q]  ->  dst[c_local][q*R + r_local]
+        dst.view(R, P, R).copy_(self.recv.permute(1, 0, 2))
+
+    # -- BatchStepper interface -------------------------------------------------------------
+    def set_U(self, U):
+        U = np.asarray(U, dtype=np.float64)
+        if U.ndim == 3:
+            U = U[0]
+        assert U.shape == (self.N, self.N)
+        self._full = U
+        self._mean = float(U.mean())
+        r0, R = self.row_base, self.R
+        self.be.upload(self.U, U[r0:r0 + R])
+
+    def prepare(self):
+        U, r0, R, N = self._full, self.row_base, self.R, self.N
+        halo = np.empty((R + 2, N))
+        halo[1:R + 1] = U[r0:r0 + R]
+        halo[0] = U[r0 - 1] if r0 > 0 else U[r0]
+        halo[R + 1] = U[r0 + R] if r0 + R < N else U[r0 + R - 1]
+        Uh = self.be.to_device(halo)
+        self._ck(self.lib.chs_slab_prepare(self._h, self.be.ptr(Uh), self._mean), "chs_slab_prepare")
+        self._allreduce_vec()
+        self._ck(self.lib.chs_slab_control(self._h, 0, 2), "chs_slab_control")
+        self.get_state(0)
+        return self.be.download(self.rows[:1, :])
+
+    def begin(self):
+        lib, h = self.lib, self._h
+        self._ck(lib.chs_slab_begin(h), "chs_slab_begin")
+        self._row(self.S_FWD, self.U, self.A)            # x-transform of U
+        self._transpose(self.A, self.B)
+        self._row(self.S_FWD, self.B, self.H)            # y-transform -> hat_U' (solver.py:159)
+        self._row(self.S_MU, self.U, self.A)             # mu(U) -> x-transform, ||mu||^2
+        self._ck(lib.chs_slab_clear_yedge(h), "chs_slab_clear_yedge")
+        self._ck(lib.chs_slab_reduce(h, self.R, 0), "chs_slab_reduce")
+        self._allreduce_vec()
+        self._ck(lib.chs_slab_control(h, 0, 0), "chs_slab_control")
+
+    def _step(self, last):
+        lib, h, be, R, N = self.lib, self._h, self.be, self.R, self.N
+        self._transpose(self.A, self.B)
+        self._row(self.S_FWD, self.B, self.B)            # hat_mu'
+        self._ck(lib.chs_slab_update(h, be.ptr(self.H), be.ptr(self.B), R, self.row_base), "chs_slab_update")
+        self._row(self.S_INV, self.H, self.B)
+        self._transpose(self.B, self.A)
+        self._row(self.S_STEP, self.A, self.A, diag=1)   # U_new stored, diagnostics, mu, x-transform
+        esz = 8 * N
+        acc = 0
+        if self.rank == 0:
+            self._ck(lib.chs_slab_yedge(h, be.ptr(self.U), be.ptr(self.U) + esz, 0), "chs_slab_yedge")
+            acc = 1
+        if self.rank == self.P - 1:
+            self._ck(lib.chs_slab_yedge(h, be.ptr(self.U) + (R - 2) * esz, be.ptr(self.U) + (R - 1) * esz, acc),
+                     "chs_slab_yedge")
+            acc = 1
+        if not acc:
+            self._ck(lib.chs_slab_clear_yedge(h), "chs_slab_clear_yedge")
+        self._ck(lib.chs_slab_reduce(h, R, 1), "chs_slab_reduce")
+        self._allreduce_vec()
+        self._ck(lib.chs_slab_control(h, int(bool(last)), 1), "chs_slab_control")
+
+    def get_state(self, sim=0):
+        st = _lib.State()
+        rw, halted = C.c_int64(0), C.c_int32(0)
+        self._ck(self.lib.chs_slab_get_state(self._h, C.byref(st), C.byref(rw), C.byref(halted)), "chs_slab_get_state")
+        self._rw, self._halted = int(rw.value), int(halted.value)
+        return st
+
+    def set_state(self, sim, st):
+        self._ck(self.lib.chs_slab_set_state(self._h, C.byref(st)), "chs_slab_set_state")
+
+    def run(self, iters, draw_noise=None, poll_every=None):
+        if draw_noise is not None:
+            raise NotImplementedError("jitter is not available on the slab path yet")
+        if self._ps.adaptive_time:
+            raise NotImplementedError("adaptive time stepping is not available on the slab path yet")
+        done = np.zeros(1, np.int64)
+        if iters <= 0:
+            return [np.empty((0, 9))], done
+        chunk = self.rows_cap if poll_every is None else min(self.rows_cap, int(poll_every))
+        out = []
+        self.begin()
+        n_done = 0
+        self.get_state(0)
+        while n_done < iters and not self._halted:
+            n = min(chunk, iters - n_done)
+            for i in range(n):
+                self._step(last=(n_done + i + 1 == iters))
+            self.get_state(0)
+            if self._rw:
+                out.append(self.be.download(self.rows[:self._rw, :]))
+                done[0] += self._rw
+                self._ck(self.lib.chs_slab_rewind_rows(self._h), "chs_slab_rewind_rows")
+            n_done += n
+        return [np.concatenate(out) if out else np.empty((0, 9))], done
+
+    def get_U(self, sim=None):
+        """Full field on the host (gathered over the ranks)."""
+        if self.P == 1:
+            return self.be.download(self.U)
+        import torch
+        import torch.distributed as dist
+        parts = [torch.empty_like(self.U) for _ in range(self.P)]
+        dist.all_gather(parts, self.U)
+        return torch.cat(parts, dim=0).cpu().numpy()
+
+    def launch_count(self):
+        return int(self.lib.chs_slab_launch_count(self._h))

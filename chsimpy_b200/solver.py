@@ -214,7 +214,7 @@ class Solver:
     """Cahn-Hilliard integrator (DCT, Flory-Huggins energy) -- API of reference
     chsimpy/solver.py:45-252."""
 
-    def __init__(self, params=None, U_init=None, _backend=None):
+    def __init__(self, params=None, U_init=None, _backend=None, _world=None, _force_slab=False):
         self.params = params
         self.solution = Solution(self.params)
         N = params.N
@@ -248,7 +248,15 @@ class Solver:
             self.create_rand = lambda n: self._rng.random((n, n))
         if self.U_init is None:
             self.U_init = params.XXX + (params.XXX * 0.01 * (self.create_rand(N) - 0.5))
-        self._stepper = BatchStepper(N, [make_params_struct(params, self.solution)], backend=_backend)
+        # engine: the batched tile kernels for N <= 1024 on one GPU, the row-slab path for a
+        # larger domain or one that is decomposed over several ranks (_world = (rank, size))
+        ps = make_params_struct(params, self.solution)
+        be = _backend if _backend is not None else _CudaBackend()
+        if _world is None and not _force_slab and be.lib.chs_supports_n(N):
+            self._stepper = BatchStepper(N, [ps], backend=be)
+        else:
+            from .slab import SlabEngine
+            self._stepper = SlabEngine(N, ps, backend=be, world=_world)
 
     def _draw_sobol(self, n):
         self._sobol_drawn += n

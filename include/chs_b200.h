@@ -140,6 +140,38 @@ int64_t chs_launch_count(const chs_solver*);
 int chs_set_timing(chs_solver*, int32_t enable);
 int chs_get_timing(chs_solver*, double* ms3, int64_t* n_iters);
 
+/* ---------------------------------------------------------------------------------------
+ * Slab path: ONE large N x N simulation, row-slab decomposed over `world` ranks (world = 1:
+ * a single GPU), N in {64 .. 16384}.  Stage-level entry points; the host layer
+ * (chsimpy_b200/slab.py) sequences them and performs the transposes (NCCL all-to-all for
+ * world > 1) and the all-reduce of the 7 diagnostic sums.  Reference: the same loop body
+ * chsimpy/solver.py:165-249; the reference has no counterpart for the decomposition. */
+typedef struct chs_slab chs_slab;
+int32_t chs_slab_supports_n(int32_t N);
+int32_t chs_slab_row_granularity(int32_t N);           /* local row counts must be multiples of this */
+int64_t chs_slab_workspace_bytes(int32_t N, int32_t rows);
+chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, int32_t row_base, int32_t world, int32_t rank,
+                          const chs_params*, double* U /*[rows][N]*/, double* rows_buf, int64_t rows_cap,
+                          void* workspace, int64_t workspace_bytes, const double* lambda_host, void* stream);
+void chs_slab_destroy(chs_slab*);
+/* mode 0: physical rows -> row DCT-II (slot order); 1: U rows -> mu -> row DCT-II; 2: row DCT-III ->
+ * physical rows; 3: row DCT-III -> U (stored in the handle's U buffer) -> diagnostics + mu -> row DCT-II */
+int chs_slab_row(chs_slab*, int32_t mode, const double* src, double* dst, int32_t rows, int32_t row_base,
+                 int32_t diag, double mean_u);
+int chs_slab_transpose(chs_slab*, const double* in, double* out, int32_t R, int32_t C, int32_t in_ld, int32_t out_ld);
+int chs_slab_update(chs_slab*, double* H, const double* B, int32_t rows, int32_t slot_base);   /* solver.py:201-206 */
+int chs_slab_yedge(chs_slab*, const double* row_a, const double* row_b, int32_t accumulate);
+int chs_slab_clear_yedge(chs_slab*);
+int chs_slab_reduce(chs_slab*, int32_t rows, int32_t with_update);    /* local sums -> chs_slab_vec() */
+double* chs_slab_vec(chs_slab*);                                      /* device pointer, 7 doubles */
+int chs_slab_prepare(chs_slab*, const double* U_with_halo /*[rows+2][N]*/, double mean_u);   /* solver.py:84-127 */
+int chs_slab_control(chs_slab*, int32_t last, int32_t post);          /* solver.py:195-199, 230-249 */
+int chs_slab_begin(chs_slab*);
+int chs_slab_rewind_rows(chs_slab*);
+int chs_slab_get_state(chs_slab*, chs_state*, int64_t* rows_written, int32_t* halted);
+int chs_slab_set_state(chs_slab*, const chs_state*);
+int64_t chs_slab_launch_count(const chs_slab*);
+
 const char* chs_last_error(void);
 int32_t chs_abi_version(void);
 

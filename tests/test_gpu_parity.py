@@ -222,3 +222,21 @@ def test_ensemble_corners_and_centre():
         assert np.abs(sol.U[::st, ::st] - z["U_sample"]).max() <= U_TOL
     ca, cb = res[4]["tuple"][2], res[4]["tuple"][3]
     assert abs(ca - 0.8121353) < 5e-7 and abs(cb - 0.9723917) < 5e-7
+
+
+@pytest.mark.parametrize("name,force", [("n2048_k10", False), ("n256_k200", True), ("n1024_k50", True)])
+def test_slab_path_single_gpu(name, force):
+    """Row-slab path (chs_slab.cuh) on one GPU: automatically for N > 1024, forced for smaller N."""
+    import chsimpy_b200 as ch
+    from chsimpy_b200.slab import SlabEngine
+    z, m = load(name)
+    p = make_params(m)
+    s = ch.Solver(p, _force_slab=force)
+    assert isinstance(s._stepper, SlabEngine)
+    s.prepare()
+    sol = s.solve_or_resume(p.ntmax)
+    check_rows(sol.timedata.data(), z["rows"], p.N)
+    st = max(1, p.N // 64)
+    assert np.abs(sol.U[::st, ::st] - z["U_sample"]).max() <= U_TOL
+    assert np.abs(sol.U.sum(axis=1) - z["U_rowsum"]).max() <= U_TOL * p.N
+    assert sol.computed_steps == m["computed_steps"]
