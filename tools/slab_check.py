@@ -29,13 +29,17 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 p = ch.Parameters(); p.no_gui = True; p.N = N; p.full_sim = True; p.kappa_tilde = 2.989112919661156e-4
 t = time.perf_counter(); s = ch.Solver(p, _world=W); s.prepare(); torch.cuda.synchronize()
 if rank == 0: print(f"[slab] N={N} setup+prepare {time.perf_counter()-t:.1f}s", flush=True)
-s.solve_or_resume(4)                       # warm-up (3 iterations)
+eng = s._stepper
+eng.run(3)                                 # warm-up
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 t = time.perf_counter()
-sol = s.solve_or_resume(steps)
+rows, done = eng.run(steps)                # begin + steps iterations + polls; the field stays on the device
 torch.cuda.synchronize()
 dt = time.perf_counter() - t
+sol = s.solution
+sol.timedata.extend(rows[0])
+sol.computed_steps = int(eng.get_state(0).computed_steps)
 if world > 1:
     tt = torch.tensor([dt], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); dt = float(tt.item())
 if rank == 0:
