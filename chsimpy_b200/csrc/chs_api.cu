@@ -412,11 +412,13 @@ extern "C" int chs_begin(chs_solver* s) {
 template <int N>
 static int do_steps(chs_solver* s, long long n_iters, const double* noise, const double* noise_mean, int last) {
     using G = Geo<N>;
-    if (s->n_running <= 0) return 0;
+    if (s->n_running <= 0 || n_iters <= 0) return 0;
     KArgs a = base_args(s);
-    a.sim_index = (s->n_running == s->batch) ? nullptr : s->index;
+    a.sim_index = s->index;                       // identity list until the first compaction
     a.nsims = s->n_running;
-    const dim3 grid(G::NTILES, s->n_running), block(G::NT);
+    const dim3 block(G::NT);
+    if (s->n_running == s->batch) a.sim_index = nullptr;
+    const dim3 grid(G::NTILES, s->n_running);
     const dim3 gcol = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, a.nsims), grow = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, a.nsims);
     for (long long it = 0; it < n_iters; ++it) {
         a.last = (last && it == n_iters - 1) ? 1 : 0;

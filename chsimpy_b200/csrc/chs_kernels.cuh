@@ -692,14 +692,13 @@ CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const chs_params& 
 // =======================================================================================
 //  row kernel
 // =======================================================================================
+// one tile of the row kernel
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_row(KArgs a) {
+CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
     using G = Geo<N>;
     constexpr int M = G::M, LPC = G::LPC, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
     constexpr int R0 = Rad<M>::radix(0), ST0 = M / R0, NB0 = 16 / R0;
-    CHS_SMEM_DECL
-    double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
     double2* sc = reinterpret_cast<double2*>(sm);
     const double2* __restrict__ s_tw = a.tw;
     const double2* __restrict__ s_om = a.om;
@@ -713,9 +712,6 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_row(KArgs a) {
     const bool diag = (MODE == ROW_STEP) && !jit;
     const double2* ltab = control ? stage_logtab<G>(sm, a.logtab, tid) : nullptr;
     const int ra_row = N / 2 + 1;                                           // int(N/2)+1, solver.py:226
-    const int total = G::NTILES * a.nsims;
-    // persistent CTA: tiles w, w + gridDim.x, ...
-    CHS_TILE_LOOP(w, total) {
         const int si = w / G::NTILES, tile = w % G::NTILES, row0 = tile * LINES;
         const int sim = a.sim_index ? a.sim_index[si] : si;
         Sim* S = a.sims + sim;
@@ -912,6 +908,16 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_row(KArgs a) {
                 }
             }
         }
+}
+
+template <int N, int MODE>
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_row(KArgs a) {
+    using G = Geo<N>;
+    CHS_SMEM_DECL
+    double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    const int total = G::NTILES * a.nsims;
+    CHS_TILE_LOOP(w, total) {
+        k_row_tile<N, MODE>(a, w, sm);
         __syncthreads();                 // the tile buffer (and flag / scratch) is reused by the next iteration
     }
     chs_cp_async_wait_all();
