@@ -84,3 +84,26 @@ def test_chunked_jitter_n128_prefix(be):
     rel = np.abs(sol.timedata.data()[:10] - z["rows"][:10]) / np.maximum(np.abs(z["rows"][:10]), 1e-300)
     rel[z["rows"][:10] == 0] = 0
     assert rel.max() < 1e-11
+
+
+def test_slab_path_emulated(be):
+    """Row-slab path (chs_slab.cuh: transposes + row kernels + elementwise update + control
+    kernel) on one emulated rank, with a re-entry, against the reference fixture."""
+    from chsimpy_b200.slab import SlabEngine
+    z = np.load(os.path.join(GOLD, "n64_k200.npz"))
+    m = json.loads(str(z["meta"]))
+    p = ch.Parameters()
+    p.no_gui = True
+    for k, v in m["params"].items():
+        setattr(p, k, v)
+    s = ch.Solver(p, _backend=be, _force_slab=True)
+    assert isinstance(s._stepper, SlabEngine)
+    s.prepare()
+    s.solve_or_resume(8)
+    sol = s.solve_or_resume(4)
+    assert sol.computed_steps == 12
+    rows, ref = sol.timedata.data(), z["rows"][:12]
+    rel = np.abs(rows - ref) / np.maximum(np.abs(ref), 1e-300)
+    rel[ref == 0] = np.abs(rows[ref == 0])
+    assert rel.max() < 1e-11, rel.max(axis=0)
+    assert abs(sol.U.mean() - s.U_init.mean()) < 1e-14

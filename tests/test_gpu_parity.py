@@ -240,3 +240,28 @@ def test_slab_path_single_gpu(name, force):
     assert np.abs(sol.U[::st, ::st] - z["U_sample"]).max() <= U_TOL
     assert np.abs(sol.U.sum(axis=1) - z["U_rowsum"]).max() <= U_TOL * p.N
     assert sol.computed_steps == m["computed_steps"]
+
+
+def test_cli_and_simulator_chunked(tmp_path, monkeypatch):
+    """`python -m chsimpy_b200`-style flow (reference __main__.py:8-25) and the chunked
+    `update_every` path of Simulator.solve (simulator.py:56-87) incl. csv/yaml export."""
+    import chsimpy_b200 as ch
+    monkeypatch.chdir(tmp_path)
+    p = ch.CLIParser().get_parameters(["-N", "128", "-n", "61", "--full-sim", "--no-gui", "-f", "t1",
+                                       "--export-csv", "U,E2", "--yaml", "-K", "3e-4"])
+    sim = ch.Simulator(p)
+    sol = sim.solve()
+    assert sol.computed_steps == 61 and sol.stop_reason == "None"
+    sim.export()
+    U = ch.utils.csv_import_matrix("t1.solution.U.csv")
+    assert np.allclose(U, sol.U, rtol=0, atol=1e-15)
+    assert os.path.exists("t1.solution.yaml") and os.path.exists("t1.solution.E2.csv")
+    # chunked: a view is "required" (png) -> headless stand-in, solve in chunks of 20
+    p2 = ch.CLIParser().get_parameters(["-N", "128", "-n", "60", "--full-sim", "--no-gui", "--png", "--update-every", "20",
+                                        "-K", "3e-4"])
+    with pytest.warns(UserWarning):
+        sim2 = ch.Simulator(p2)
+    sol2 = sim2.solve()
+    assert sim2.steps_total == 60 and sol2.computed_steps == 60
+    # without jitter a chunked run equals the unchunked one to rounding (re-entry recomputes hat_U)
+    assert np.abs(sol2.E - sol.E[:60]).max() / abs(sol.E[0]) < 1e-12
