@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libchs_b200.so")
-SOURCES = ("chs_api.cu", "chs_kernels.cuh", "chs_slab.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
+SOURCES = ("chs_api.cu", "chs_kernels.cuh", "chs_slab.cuh", "chs_gemm.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -33,6 +33,7 @@ PROTOTYPES = {
     "chs_abi_version": (C.c_int32, []),
     "chs_last_error": (C.c_char_p, []),
     "chs_supports_n": (C.c_int32, [C.c_int32]),
+    "chs_uses_gemm": (C.c_int32, [C.c_int32, C.c_int32]),
     "chs_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "chs_create": (C.c_void_p, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "chs_kernels.cuh"
+#include "chs_gemm.cuh"
 
 using namespace chs;
 
@@ -45,6 +46,9 @@ struct chs_solver {
     int n_running;
     long long launches;
     int num_sms;
+    bool gemm;           // DCT-as-GEMM path (chs_gemm.cuh): small / non-power-of-two N
+    int N8, LD;
+    double *Cm, *Ct;
     int cap_col[3], cap_row[4];     // resident CTAs per kernel mode (persistent grids)
     // optional per-kernel timing (bench.py)
     bool timing;
@@ -82,12 +86,27 @@ static int drain_events(chs_solver* s) {
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t sims, part, colpart, tw, om, lam, gsin, kof, logtab, index, mean, total;
+    size_t sims, part, colpart, tw, om, lam, gsin, kof, logtab, index, mean, cm, ct, total;
 };
+static bool fft_supports(int N) { return N == 32 || N == 64 || N == 128 || N == 256 || N == 512 || N == 1024; }
+static bool gemm_supports(int N) { return N >= GEMM_MIN_N && N <= GEMM_MAX_N; }
+// Variant selection per N (and batch) by measurement on B200 (profiles/r1b_gemm_vs_fft.md):
+// N = 32 up to two resident waves of simulations is faster as tensor-core GEMMs inside one CTA
+// (15 vs 27 us per step for one simulation), from N = 64 on the FFT path wins everywhere.
+static bool use_gemm_path(int N, int batch) {
+    static const int force = [] { const char* e = getenv("CHS_FORCE_GEMM"); return e ? atoi(e) : -1; }();
+    if (!gemm_supports(N)) return false;
+    if (!fft_supports(N)) return true;
+    if (force >= 0) return force == 1;
+    return N == 32 && batch <= 296;
+}
+static int gemm_n8(int N) { return (N + 7) / 8 * 8; }
+static int gemm_ld(int N) { return gemm_n8(N) + 4; }
+
 static Layout layout(int N, int batch) {
     Layout L;
     size_t o = 0;
-    const int ntiles = N / CHS_LINES;
+    const int ntiles = (N + CHS_LINES - 1) / CHS_LINES;
     L.sims = o; o = align_up(o + sizeof(Sim) * (size_t)batch);
     L.part = o; o = align_up(o + sizeof(double) * (size_t)batch * P_NSLOT * ntiles);
     L.colpart = o; o = align_up(o + sizeof(double) * (size_t)batch * ntiles * N);
@@ -99,6 +118,9 @@ static Layout layout(int N, int batch) {
     L.logtab = o; o = align_up(o + sizeof(double2) * (size_t)LOG_TABLE_N);
     L.index = o; o = align_up(o + sizeof(int) * (size_t)batch);
     L.mean = o; o = align_up(o + sizeof(double) * (size_t)batch);
+    const size_t n8 = (size_t)gemm_n8(N);
+    L.cm = o; o = align_up(o + sizeof(double) * n8 * n8);
+    L.ct = o; o = align_up(o + sizeof(double) * n8 * n8);
     L.total = o;
     return L;
 }
@@ -106,9 +128,8 @@ static Layout layout(int N, int batch) {
 extern "C" int32_t chs_abi_version(void) { return CHS_ABI_VERSION; }
 extern "C" const char* chs_last_error(void) { return g_err.c_str(); }
 
-extern "C" int32_t chs_supports_n(int32_t N) {
-    return (N == 32 || N == 64 || N == 128 || N == 256 || N == 512 || N == 1024) ? 1 : 0;
-}
+extern "C" int32_t chs_supports_n(int32_t N) { return (fft_supports(N) || gemm_supports(N)) ? 1 : 0; }
+extern "C" int32_t chs_uses_gemm(int32_t N, int32_t batch) { return use_gemm_path(N, batch) ? 1 : 0; }
 
 extern "C" int64_t chs_workspace_bytes(int32_t N, int32_t batch) {
     if (!chs_supports_n(N) || batch < 1) return -1;
@@ -189,7 +210,7 @@ static KArgs base_args(chs_solver* s) {
 extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, double* U, double* hat_U, double* T,
                                   double* rows, int64_t rows_cap, void* workspace, int64_t workspace_bytes,
                                   const double* lambda_host, void* stream) {
-    if (!chs_supports_n(N)) { fail("chs_create: N must be a power of two in [32, 1024]"); return nullptr; }
+    if (!chs_supports_n(N)) { fail("chs_create: unsupported N (FFT path: powers of two 32..1024; GEMM path: 8..104)"); return nullptr; }
     if (batch < 1 || rows_cap < 1) { fail("chs_create: bad batch/rows_cap"); return nullptr; }
     const Layout L = layout(N, batch);
     if (workspace_bytes < (int64_t)L.total) { fail("chs_create: workspace too small"); return nullptr; }
@@ -210,6 +231,8 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     s->kof = (int*)(w + L.kof);
     s->index = (int*)(w + L.index);
     s->mean = (double*)(w + L.mean);
+    s->Cm = (double*)(w + L.cm); s->Ct = (double*)(w + L.ct);
+    s->gemm = use_gemm_path(N, batch); s->N8 = gemm_n8(N); s->LD = gemm_ld(N);
     s->hsims.assign(batch, Sim());
     std::memset(s->hsims.data(), 0, sizeof(Sim) * batch);
     s->hindex.resize(batch);
@@ -221,23 +244,25 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     // twiddle tables in extended precision, rounded once
     const int M = N / 2;
     std::vector<double2> tw(M), om(N);
-    const long double pi = 3.14159265358979323846264338327950288L;
-    for (int m = 0; m < M; ++m) {
-        const long double a = -2.0L * pi * m / M;
-        tw[m] = make_double2((double)cosl(a), (double)sinl(a));
-    }
-    for (int m = 0; m < N; ++m) {
-        const long double a = -pi * m / (2.0L * N);
-        om[m] = make_double2((double)cosl(a), (double)sinl(a));
-    }
-    // gradient-energy weights sin^2(pi k/N) and the slot -> frequency map of the FFT plan
     std::vector<double> gs(N);
-    for (int k = 0; k < N; ++k) {
-        const long double sn = sinl(pi * k / N);
-        gs[k] = (double)(sn * sn);
-    }
     std::vector<int> kof(N);
-    {
+    std::vector<double2> lt(LOG_TABLE_N);
+    std::vector<double> cm, ct;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    if (!s->gemm) {
+        for (int m = 0; m < M; ++m) {
+            const long double a = -2.0L * pi * m / M;
+            tw[m] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+        for (int m = 0; m < N; ++m) {
+            const long double a = -pi * m / (2.0L * N);
+            om[m] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+        // gradient-energy weights sin^2(pi k/N) and the slot -> frequency map of the FFT plan
+        for (int k = 0; k < N; ++k) {
+            const long double sn = sinl(pi * k / N);
+            gs[k] = (double)(sn * sn);
+        }
         std::vector<int> rad;                       // same plan as Rad<M> (dct_core.cuh)
         int lg = 0;
         while ((1 << lg) < M) ++lg;
@@ -249,9 +274,20 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
             kof[2 * pos] = k;
             kof[2 * pos + 1] = (k == 0) ? M : N - k;
         }
+    } else {
+        // orthonormal DCT-II matrix C[k][n] = f_k cos(pi k (2n+1) / (2N)), zero padded to N8 x N8
+        const int n8 = s->N8;
+        cm.assign((size_t)n8 * n8, 0.0);
+        ct.assign((size_t)n8 * n8, 0.0);
+        for (int k = 0; k < N; ++k)
+            for (int n = 0; n < N; ++n) {
+                const long double f = (k == 0) ? sqrtl(1.0L / N) : sqrtl(2.0L / N);
+                const double v = (double)(f * cosl(pi * k * (2 * n + 1) / (2.0L * N)));
+                cm[(size_t)k * n8 + n] = v;
+                ct[(size_t)n * n8 + k] = v;
+            }
     }
     // fast_log table (fastlog.cuh): sub-interval centres of [0.6875, 1.375) in bit-pattern space
-    std::vector<double2> lt(LOG_TABLE_N);
     for (int i = 0; i < LOG_TABLE_N; ++i) {
         const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << 45);
         const unsigned long long b1 = LOG_OFF + ((unsigned long long)(i + 1) << 45);
@@ -269,13 +305,24 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    if (s->gemm) {
+        ok &= cudaMemcpyAsync(s->Cm, cm.data(), sizeof(double) * cm.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+        ok &= cudaMemcpyAsync(s->Ct, ct.data(), sizeof(double) * ct.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    }
     ok &= cudaMemcpyAsync(s->index, s->hindex.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaStreamSynchronize(s->stream) == cudaSuccess;
     int rc = 0;
     s->num_sms = 1;
     cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (s->gemm) {
+        const int smem = (2 * s->N8 * s->LD + 8 * GEMM_NT + 2 * LOG_TABLE_N) * (int)sizeof(double);
+        if (cudaFuncSetAttribute(k_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            fail("chs_create: k_gemm shared memory attribute");
+            rc = -1;
+        }
+    }
 #define CALL(NN) rc = set_attrs<NN>(s);
-    switch (N) {
+    if (!s->gemm) switch (N) {
         case 32: CALL(32) break; case 64: CALL(64) break; case 128: CALL(128) break;
         case 256: CALL(256) break; case 512: CALL(512) break; case 1024: CALL(1024) break;
     }
@@ -360,6 +407,27 @@ static int refresh_index(chs_solver* s) {
     return 0;
 }
 
+// ---- DCT-as-GEMM path (chs_gemm.cuh): one CTA per simulation --------------------------------
+static int gemm_launch(chs_solver* s, int mode, long long n_iters, const double* noise, const double* src, double* dst,
+                       bool running_only) {
+    GemmArgs g;
+    std::memset(&g, 0, sizeof(g));
+    g.sims = s->sims; g.U = s->U; g.hatU = s->hatU; g.rows = s->rows; g.rows_cap = s->rows_cap;
+    g.Cm = s->Cm; g.Ct = s->Ct; g.lam = s->lam; g.logtab = s->logtab; g.noise = noise; g.mean_host = s->mean;
+    g.N = s->N; g.N8 = s->N8; g.LD = s->LD; g.mode = mode; g.n_iters = n_iters; g.src = src; g.dst = dst;
+    int nsims = s->batch;
+    if (running_only) {
+        if (s->n_running <= 0) return 0;
+        nsims = s->n_running;
+        g.sim_index = (s->n_running == s->batch) ? nullptr : s->index;
+    }
+    const int smem = (2 * s->N8 * s->LD + 8 * GEMM_NT + 2 * LOG_TABLE_N) * (int)sizeof(double);
+    CHS_LAUNCH(k_gemm, dim3(nsims), dim3(GEMM_NT), smem, s->stream, g);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int N>
 static int do_prepare(chs_solver* s) {
     using G = Geo<N>;
@@ -374,6 +442,7 @@ extern "C" int chs_prepare(chs_solver* s, const double* mean_U_host) {
     if (!s || !mean_U_host) return fail("chs_prepare: bad argument");
     CHS_CUDA(cudaMemcpyAsync(s->mean, mean_U_host, sizeof(double) * s->batch, cudaMemcpyHostToDevice, s->stream));
     CHS_CUDA(cudaStreamSynchronize(s->stream));        // mean_U_host may be pageable and short-lived
+    if (s->gemm) return gemm_launch(s, 0, 0, nullptr, nullptr, nullptr, false);
 #define CALL(NN) if (do_prepare<NN>(s)) return -1;
     CHS_FOR_N(s->N, CALL)
 #undef CALL
@@ -397,9 +466,13 @@ static int do_begin(chs_solver* s) {
 
 extern "C" int chs_begin(chs_solver* s) {
     if (!s) return fail("chs_begin: null handle");
+    if (s->gemm) {
+        if (gemm_launch(s, 1, 0, nullptr, nullptr, nullptr, false)) return -1;
+    } else {
 #define CALL(NN) if (do_begin<NN>(s)) return -1;
-    CHS_FOR_N(s->N, CALL)
+        CHS_FOR_N(s->N, CALL)
 #undef CALL
+    }
     // the prologue's control step may already halt a sim (time limit); the index list is
     // compacted at the first chs_poll
     s->hindex.resize(s->batch);
@@ -448,6 +521,7 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
 extern "C" int chs_steps(chs_solver* s, int64_t n_iters, const double* noise, const double* noise_mean, int32_t last) {
     if (!s || n_iters < 0) return fail("chs_steps: bad argument");
     if (noise && !noise_mean) return fail("chs_steps: noise without noise_mean");
+    if (s->gemm) return n_iters > 0 ? gemm_launch(s, 2, n_iters, noise, nullptr, nullptr, true) : 0;
 #define CALL(NN) if (do_steps<NN>(s, n_iters, noise, noise_mean, last)) return -1;
     CHS_FOR_N(s->N, CALL)
 #undef CALL
@@ -501,6 +575,7 @@ static int do_end(chs_solver* s) {
 
 extern "C" int chs_end(chs_solver* s) {
     if (!s) return fail("chs_end: null handle");
+    if (s->gemm) { CHS_CUDA(cudaStreamSynchronize(s->stream)); return 0; }     // U is written back by every launch
 #define CALL(NN) if (do_end<NN>(s)) return -1;
     CHS_FOR_N(s->N, CALL)
 #undef CALL
@@ -531,6 +606,7 @@ static int do_dctn(chs_solver* s, const double* in, double* out, bool inverse) {
 
 extern "C" int chs_dctn(chs_solver* s, const double* in, double* out) {
     if (!s || !in || !out) return fail("chs_dctn: bad argument");
+    if (s->gemm) return gemm_launch(s, 3, 0, nullptr, in, out, false);
 #define CALL(NN) if (do_dctn<NN>(s, in, out, false)) return -1;
     CHS_FOR_N(s->N, CALL)
 #undef CALL
@@ -538,6 +614,7 @@ extern "C" int chs_dctn(chs_solver* s, const double* in, double* out) {
 }
 extern "C" int chs_idctn(chs_solver* s, const double* in, double* out) {
     if (!s || !in || !out) return fail("chs_idctn: bad argument");
+    if (s->gemm) return gemm_launch(s, 4, 0, nullptr, in, out, false);
 #define CALL(NN) if (do_dctn<NN>(s, in, out, true)) return -1;
     CHS_FOR_N(s->N, CALL)
 #undef CALL

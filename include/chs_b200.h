@@ -60,8 +60,10 @@ typedef struct chs_solver chs_solver;   /* opaque */
 /* Size in bytes of the device workspace the caller must provide for `batch` sims. */
 int64_t chs_workspace_bytes(int32_t N, int32_t batch);
 
-/* Supported N for the FFT path (powers of two, 32..16384).  Returns 1/0. */
+/* Supported N of the batched stepper: FFT path (powers of two 32..1024) or DCT-as-GEMM path on
+ * the FP64 tensor cores (any N in 8..104).  chs_uses_gemm tells which one chs_create picks. */
 int32_t chs_supports_n(int32_t N);
+int32_t chs_uses_gemm(int32_t N, int32_t batch);
 
 /* Creates a solver for `batch` independent N x N simulations on CUDA device `device`.
  * Buffers (device pointers, row-major, contiguous, owned by the caller):

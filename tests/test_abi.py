@@ -27,8 +27,11 @@ def test_library_builds_and_exports_everything():
         assert hasattr(lib, name), name
     _lib.bind(lib)
     assert lib.chs_abi_version() == 1
-    assert [n for n in (16, 32, 64, 100, 512, 1024, 2048) if lib.chs_supports_n(n)] == [32, 64, 512, 1024]
-    assert lib.chs_workspace_bytes(512, 4) > 0 and lib.chs_workspace_bytes(100, 4) < 0
+    assert [n for n in (4, 16, 32, 64, 100, 200, 512, 1024, 2048) if lib.chs_supports_n(n)] == [16, 32, 64, 100, 512, 1024]
+    assert [n for n in (16, 32, 100, 512) if lib.chs_uses_gemm(n, 1)] == [16, 32, 100]
+    assert lib.chs_uses_gemm(32, 1024) == 0
+    assert lib.chs_workspace_bytes(512, 4) > 0 and lib.chs_workspace_bytes(200, 4) < 0
+    assert [n for n in (512, 2048, 16384, 100) if lib.chs_slab_supports_n(n)] == [512, 2048, 16384]
 
 
 def test_struct_layout_matches_header():

@@ -107,3 +107,23 @@ def test_slab_path_emulated(be):
     rel[ref == 0] = np.abs(rows[ref == 0])
     assert rel.max() < 1e-11, rel.max(axis=0)
     assert abs(sol.U.mean() - s.U_init.mean()) < 1e-14
+
+
+def test_gemm_path_emulated_vs_oracle(be):
+    """DCT-as-GEMM path (chs_gemm.cuh) at a non-power-of-two N, in-kernel time loop with a
+    re-entry, against the oracle (the tensor-core MMA is replaced by scalar dot products in
+    the host build; indexing and control flow are the same)."""
+    import ch_oracle as orc
+    assert be.lib.chs_uses_gemm(20, 1) == 1
+    p = ch.Parameters()
+    p.N, p.no_gui, p.full_sim, p.kappa_tilde, p.ntmax = 20, True, True, 3e-4, 15
+    s = ch.Solver(p, _backend=be)
+    s.prepare()
+    s.solve_or_resume(10)
+    sol = s.solve_or_resume(5)
+    o = orc.run_default(N=20, nsteps=10, kappa_tilde=3e-4, full_sim=True)
+    o.run(5)
+    rel = np.abs(sol.timedata.data() - o.rows) / np.maximum(np.abs(o.rows), 1e-300)
+    rel[o.rows == 0] = 0
+    assert sol.timedata.data().shape == o.rows.shape and rel.max() < 1e-11
+    assert np.abs(sol.U - o.U).max() < 1e-13

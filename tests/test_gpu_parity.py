@@ -265,3 +265,44 @@ def test_cli_and_simulator_chunked(tmp_path, monkeypatch):
     assert sim2.steps_total == 60 and sol2.computed_steps == 60
     # without jitter a chunked run equals the unchunked one to rounding (re-entry recomputes hat_U)
     assert np.abs(sol2.E - sol.E[:60]).max() / abs(sol.E[0]) < 1e-12
+
+
+def test_gemm_path_n100_golden():
+    """DCT-as-GEMM path (FP64 tensor cores, chs_gemm.cuh) at the reference's benchmark smoke size."""
+    from chsimpy_b200 import _lib
+    assert _lib.load().chs_uses_gemm(100, 1) == 1 and _lib.load().chs_uses_gemm(512, 1) == 0
+    run_case("n100_k100")
+
+
+@pytest.mark.parametrize("N,kw", [(40, dict()), (72, dict(jitter=0.004)), (56, dict(adaptive_time=True, delt_max=3e-9)),
+                                  (24, dict(time_max=0.5))])
+def test_gemm_path_vs_oracle(N, kw):
+    """Arbitrary N, with jitter / adaptive dt / time limit, in-kernel time loop vs the oracle."""
+    import ch_oracle as orc
+    import chsimpy_b200 as ch
+    steps = 620 if kw.get("adaptive_time") else 80
+    p = ch.Parameters()
+    p.N, p.ntmax, p.full_sim, p.no_gui, p.kappa_tilde, p.seed = N, steps, True, True, 2.7e-4, 5
+    for k, v in kw.items():
+        setattr(p, k, v)
+    s = ch.Solver(p)
+    s.prepare()
+    sol = s.solve_or_resume(steps)
+    o = orc.run_default(N=N, nsteps=steps, seed=5, kappa_tilde=2.7e-4, full_sim=True, **kw)
+    check_rows(sol.timedata.data(), o.rows, N)
+    assert np.abs(sol.U - o.U).max() <= U_TOL
+    assert sol.stop_reason == o.stop_reason and sol.computed_steps == o.computed_steps
+    assert abs(s.delt - o.delt) <= 1e-12 * o.delt
+
+
+def test_gemm_dctn_matches_scipy():
+    from chsimpy_b200 import _lib
+    from chsimpy_b200.solver import BatchStepper
+    for N in (8, 30, 100):
+        ps = _lib.Params(RT=1, BRT=1, B=1, A0=1, A1=1, Amr=1, kappa_tilde=1, L=2, delx=2 / (N - 1), delt=1e-8,
+                         delt_max=1e-8, M_tilde=1, threshold=0.5, time_limit_s=0, jitter=0, full_sim=1, adaptive_time=0)
+        st = BatchStepper(N, [ps] * 2)
+        x = np.random.default_rng(N).random((2, N, N)) - 0.3
+        ref = np.stack([fp.dctn(x[i], norm="ortho") for i in range(2)])
+        assert np.linalg.norm(st.dctn(x) - ref) / np.linalg.norm(ref) <= 1e-13
+        assert np.abs(st.dctn(ref, inverse=True) - x).max() <= 1e-13
