@@ -299,6 +299,8 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
             line["single_sim"] = single_sim_probe(ch)
+            line["ensemble_to_stop"] = ensemble_to_stop_probe(ch)
+            line["jitter_adaptive"] = jitter_adaptive_probe(ch)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -320,6 +322,52 @@ def single_sim_probe(ch):
     return {"workload": "configs[1]: N=512 to the energy stop, device-side stop flag, host poll every 128 steps",
             "computed_steps": sol.computed_steps, "stop_reason": sol.stop_reason,
             "steps_per_s": round((sol.computed_steps - 1) / dt, 1), "wall_s": round(dt, 4)}
+
+
+def ensemble_to_stop_probe(ch, members=256):
+    """BASELINE configs[2] as the reference runs it: every member to ITS energy stop (device-side
+    flags, grid compaction at each poll); solve only (kappa_tilde interpolated, no exports)."""
+    import torch
+    from chsimpy_b200.solver import BatchStepper, make_params_struct
+    fac, kap = member_scalars(members)
+    structs = []
+    for f, k in zip(fac, kap):
+        p = ch.Parameters()
+        p.no_gui, p.kappa_tilde = True, float(k)
+        p.func_A0 = (lambda f0: (lambda T: ch.utils.A0(T) * f0))(float(f[0]))
+        p.func_A1 = (lambda f1: (lambda T: ch.utils.A1(T) * f1))(float(f[1]))
+        structs.append(make_params_struct(p, ch.Solution(p)))
+    U0 = 0.875 + 0.875 * 0.01 * (np.random.Generator(np.random.PCG64(2023)).random((N_GRID, N_GRID)) - 0.5)
+    st = BatchStepper(N_GRID, structs, rows_cap=128)
+    st.set_U(U0)
+    st.prepare()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    rows, done = st.run(10 ** 6, poll_every=128)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    stops = done + 1
+    return {"workload": f"{members} members, A factors PCG64(85972), each to its own energy stop, host poll every 128 steps",
+            "sims_per_s": round(members / dt, 2), "sim_steps_per_s": round(float(done.sum()) / dt, 1), "wall_s": round(dt, 3),
+            "stop_step_min_mean_max": [int(stops.min()), round(float(stops.mean()), 1), int(stops.max())]}
+
+
+def jitter_adaptive_probe(ch):
+    """BASELINE configs[3]: N=512, --jitter 0.01 --adaptive-time (delt_max=2e-10, the stable variant),
+    host-precomputed PCG64 noise uploaded per 64-step chunk (reproducible: same stream as the reference)."""
+    import torch
+    p = ch.Parameters()
+    p.no_gui, p.full_sim, p.jitter, p.adaptive_time, p.delt_max, p.ntmax = True, True, 0.01, True, 2e-10, 700
+    p.kappa_tilde = 2.989112919661156e-4
+    s = ch.Solver(p)
+    s.prepare()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    sol = s.solve_or_resume(p.ntmax)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    return {"workload": "configs[3]: N=512 jitter 0.01 + adaptive dt (delt_max 2e-10), 700 steps", "steps_per_s": round(699 / dt, 1),
+            "wall_s": round(dt, 3), "delt_last": float(sol.delt[-1]), "note": "bounded by host noise generation + H2D (2 MiB per step)"}
 
 
 def main():

@@ -37,10 +37,10 @@ class _CudaBackend:
         return t.data_ptr()
 
     def upload(self, t, arr):
-        t.copy_(self.torch.from_numpy(np.ascontiguousarray(arr)))
+        t.copy_(self.torch.from_numpy(np.require(arr, dtype=np.float64, requirements=['C', 'W'])))
 
     def to_device(self, arr):
-        return self.torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+        return self.torch.from_numpy(np.require(arr, requirements=['C', 'W'])).to(self.device)
 
     def download(self, t):
         return t.detach().cpu().numpy()
