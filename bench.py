@@ -354,7 +354,7 @@ def ensemble_to_stop_probe(ch, members=256):
 
 def jitter_adaptive_probe(ch):
     """BASELINE configs[3]: N=512, --jitter 0.01 --adaptive-time (delt_max=2e-10, the stable variant),
-    host-precomputed PCG64 noise uploaded per 64-step chunk (reproducible: same stream as the reference)."""
+    the reference's PCG64 noise stream regenerated bit-exactly on the device per 64-step chunk."""
     import torch
     p = ch.Parameters()
     p.no_gui, p.full_sim, p.jitter, p.adaptive_time, p.delt_max, p.ntmax = True, True, 0.01, True, 2e-10, 700
@@ -367,7 +367,7 @@ def jitter_adaptive_probe(ch):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t
     return {"workload": "configs[3]: N=512 jitter 0.01 + adaptive dt (delt_max 2e-10), 700 steps", "steps_per_s": round(699 / dt, 1),
-            "wall_s": round(dt, 3), "delt_last": float(sol.delt[-1]), "note": "bounded by host noise generation + H2D (2 MiB per step)"}
+            "wall_s": round(dt, 3), "delt_last": float(sol.delt[-1]), "note": "noise = numpy PCG64 stream reproduced bit-exactly on the device (k_pcg64_fill); diagnostics via k_diag"}
 
 
 def main():

@@ -49,6 +49,8 @@ PROTOTYPES = {
     "chs_end": (C.c_int, [C.c_void_p]),
     "chs_dctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "chs_idctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chs_pcg64_fill": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64]),
+    "chs_row_means": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "chs_debug_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "chs_launch_count": (C.c_int64, [C.c_void_p]),
     "chs_slab_supports_n": (C.c_int32, [C.c_int32]),

@@ -925,3 +925,34 @@ extern "C" int chs_slab_set_state(chs_slab* s, const chs_state* st) {
     CHS_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
+
+// ---- device-side numpy PCG64 stream (jitter noise) -------------------------------------------
+extern "C" int chs_pcg64_fill(chs_solver* s, uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
+                              uint64_t offset, double* out, int64_t count) {
+    if (!s || !out || count < 0) return fail("chs_pcg64_fill: bad argument");
+    if (count == 0) return 0;
+    const long long threads = (count + PCG_RUN - 1) / PCG_RUN;
+#ifdef CHS_EMU
+    const int nt = 32;
+#else
+    const int nt = 128;
+#endif
+    CHS_LAUNCH(k_pcg64_fill, dim3((unsigned)((threads + nt - 1) / nt)), dim3(nt), 0, s->stream, out, (long long)count,
+               (unsigned long long)state_hi, (unsigned long long)state_lo, (unsigned long long)inc_hi,
+               (unsigned long long)inc_lo, (unsigned long long)offset);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int chs_row_means(chs_solver* s, const double* in, int64_t rows, int64_t cols, double* out) {
+    if (!s || !in || !out || rows < 1 || cols < 1) return fail("chs_row_means: bad argument");
+#ifdef CHS_EMU
+    const int nt = 32;
+#else
+    const int nt = 256;
+#endif
+    CHS_LAUNCH(k_row_means, dim3((unsigned)rows), dim3(nt), nt * sizeof(double), s->stream, in, (long long)cols, out);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1054,3 +1054,58 @@ CHS_KERNEL void k_rewind(Sim* sims, int batch) {
 }
 
 }  // namespace chs
+
+// ---------------------------------------------------------------------------------------
+// Bit-exact numpy PCG64 on the device: the per-step jitter of solver.py:210-211 is
+// `rng.random((N, N))` from the SAME generator that produced U_init (solver.py:78-79).
+// state <- state * MULT + inc (128 bit), output XSL-RR, double = (out >> 11) * 2^-53.
+// Every thread jumps to its position with the O(log n) LCG skip-ahead and then produces a
+// run of PCG_RUN consecutive values, so a whole chunk of steps is one launch and nothing
+// crosses PCIe.
+namespace chs {
+typedef unsigned __int128 u128;
+constexpr int PCG_RUN = 32;
+CHS_DEV u128 pcg_mult() { return ((u128)0x2360ED051FC65DA4ULL << 64) | (u128)0x4385DF649FCCF645ULL; }
+CHS_DEV u128 pcg_advance(u128 state, u128 inc, unsigned long long delta) {
+    u128 acc_mult = 1, acc_plus = 0, cur_mult = pcg_mult(), cur_plus = inc;
+    while (delta > 0) {
+        if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+        cur_plus = (cur_mult + 1) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    return acc_mult * state + acc_plus;
+}
+CHS_KERNEL void k_pcg64_fill(double* out, long long count, unsigned long long s_hi, unsigned long long s_lo,
+                             unsigned long long i_hi, unsigned long long i_lo, unsigned long long offset) {
+    const long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PCG_RUN;
+    if (first >= count) return;
+    const u128 inc = ((u128)i_hi << 64) | i_lo;
+    u128 st = pcg_advance(((u128)s_hi << 64) | s_lo, inc, offset + (unsigned long long)first);
+    const u128 mult = pcg_mult();
+    const long long end = first + PCG_RUN < count ? first + PCG_RUN : count;
+    for (long long i = first; i < end; ++i) {
+        st = st * mult + inc;
+        const unsigned long long hi = (unsigned long long)(st >> 64), lo = (unsigned long long)st;
+        const unsigned long long x = hi ^ lo;
+        const unsigned rot = (unsigned)(hi >> 58);
+        const unsigned long long o = (x >> rot) | (x << ((64 - rot) & 63));
+        out[i] = (double)(o >> 11) * (1.0 / 9007199254740992.0);
+    }
+}
+// out[r] = mean of row r of a [rows][cols] array (one block per row, fixed summation order)
+CHS_KERNEL void k_row_means(const double* in, long long cols, double* out) {
+    CHS_SMEM_DECL
+    double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    const double* p = in + (size_t)blockIdx.x * cols;
+    double s = 0;
+    for (long long i = threadIdx.x; i < cols; i += blockDim.x) s += p[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (unsigned j = 0; j < blockDim.x; ++j) t += red[j];
+        out[blockIdx.x] = t / (double)cols;
+    }
+}
+}  // namespace chs

@@ -161,6 +161,21 @@ class BatchStepper:
         _lib.check(self.lib, self.lib.chs_get_timing(self._h, ms, C.byref(n)), "chs_get_timing")
         return {"col": ms[0], "row": ms[1], "diag": ms[2]}, int(n.value)
 
+    def pcg64_noise(self, bit_generator_state, n):
+        """(noise [n][N][N], per-step means [n]) on the device: the next n*N*N doubles of a numpy
+        PCG64 generator whose `bit_generator.state` is given -- bit-identical to rng.random()."""
+        st = bit_generator_state["state"]
+        s128, i128 = int(st["state"]), int(st["inc"])
+        m64 = (1 << 64) - 1
+        count = n * self.N * self.N
+        noise = self.be.empty((n, self.N, self.N))
+        mean = self.be.empty((n,))
+        _lib.check(self.lib, self.lib.chs_pcg64_fill(self._h, s128 >> 64, s128 & m64, i128 >> 64, i128 & m64, 0,
+                                                     self.be.ptr(noise), count), "chs_pcg64_fill")
+        _lib.check(self.lib, self.lib.chs_row_means(self._h, self.be.ptr(noise), n, self.N * self.N, self.be.ptr(mean)),
+                   "chs_row_means")
+        return noise, mean
+
     def debug_log(self, x):
         """Device fast_log of a host array (self-test of csrc/fastlog.cuh)."""
         x = np.ascontiguousarray(x, dtype=np.float64).ravel()
@@ -195,9 +210,12 @@ class BatchStepper:
             n = min(chunk, iters - done)
             noise = nmean = None
             if draw_noise is not None:
-                host = draw_noise(n)
-                noise = self.be.to_device(host)
-                nmean = self.be.to_device(host.reshape(n, -1).mean(axis=1))
+                drawn = draw_noise(n)
+                if isinstance(drawn, tuple):              # already on the device (PCG64 kernel)
+                    noise, nmean = drawn
+                else:
+                    noise = self.be.to_device(drawn)
+                    nmean = self.be.to_device(drawn.reshape(n, -1).mean(axis=1))
             self.steps(n, noise, nmean, last=(done + n == iters))
             running, _, _, _ = self.poll()
             got = self.take_rows()
@@ -324,6 +342,11 @@ class Solver:
             N = p.N
 
             def draw(n):
+                if self._rng is not None and hasattr(st, "pcg64_noise"):
+                    # numpy's PCG64 stream reproduced on the device; the host generator is only advanced
+                    dev = st.pcg64_noise(self._rng.bit_generator.state, n)
+                    self._rng.bit_generator.advance(n * N * N)
+                    return dev
                 out = np.empty((n, N, N))
                 for i in range(n):
                     out[i] = self.create_rand(N)

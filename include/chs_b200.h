@@ -128,6 +128,14 @@ int chs_end(chs_solver*);
 int chs_dctn(chs_solver*, const double* in, double* out);
 int chs_idctn(chs_solver*, const double* in, double* out);
 
+/* Device-side numpy PCG64: out[i] = the (offset+i)-th `Generator(PCG64).random()` draw after the
+ * generator state {state, inc} (128-bit values as hi/lo words, from `bit_generator.state`), bit
+ * for bit.  Replaces the host-side `rng.random((N, N))` of the per-step jitter (solver.py:78-79,
+ * 210-211) so that no noise crosses PCIe.  chs_row_means: out[r] = mean(in[r, :]). */
+int chs_pcg64_fill(chs_solver*, uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
+                   uint64_t offset, double* out, int64_t count);
+int chs_row_means(chs_solver*, const double* in, int64_t rows, int64_t cols, double* out);
+
 /* Self-test hook: y[i] = the device's table-driven natural log of x[i] (csrc/fastlog.cuh),
  * the routine that stands in for np.log at solver.py:173,220.  Device pointers. */
 int chs_debug_log(chs_solver*, const double* x, double* y, int64_t n);

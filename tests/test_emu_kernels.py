@@ -127,3 +127,13 @@ def test_gemm_path_emulated_vs_oracle(be):
     rel[o.rows == 0] = 0
     assert sol.timedata.data().shape == o.rows.shape and rel.max() < 1e-11
     assert np.abs(sol.U - o.U).max() < 1e-13
+
+
+def test_pcg64_device_stream_emulated(be):
+    from chsimpy_b200 import _lib as L
+    st = BatchStepper(32, [unit_params(32)], backend=be)
+    g = np.random.Generator(np.random.PCG64(7))
+    g.random((32, 32))
+    noise, mean = st.pcg64_noise(g.bit_generator.state, 2)
+    ref = np.stack([g.random((32, 32)) for _ in range(2)])
+    assert np.array_equal(noise, ref)

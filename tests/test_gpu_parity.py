@@ -306,3 +306,19 @@ def test_gemm_dctn_matches_scipy():
         ref = np.stack([fp.dctn(x[i], norm="ortho") for i in range(2)])
         assert np.linalg.norm(st.dctn(x) - ref) / np.linalg.norm(ref) <= 1e-13
         assert np.abs(st.dctn(ref, inverse=True) - x).max() <= 1e-13
+
+
+def test_device_pcg64_is_numpy_bit_exact():
+    """The jitter noise is numpy's PCG64 stream reproduced on the device (no PCIe traffic)."""
+    from chsimpy_b200 import _lib
+    from chsimpy_b200.solver import BatchStepper
+    N = 64
+    ps = _lib.Params(RT=1, BRT=1, B=1, A0=1, A1=1, Amr=1, kappa_tilde=1, L=2, delx=2 / (N - 1), delt=1e-8,
+                     delt_max=1e-8, M_tilde=1, threshold=0.5, time_limit_s=0, jitter=0, full_sim=1, adaptive_time=0)
+    st = BatchStepper(N, [ps])
+    g = np.random.Generator(np.random.PCG64(2023))
+    g.random((N, N))                                   # the U_init draw comes first (solver.py:78-82)
+    noise, mean = st.pcg64_noise(g.bit_generator.state, 5)
+    ref = np.stack([g.random((N, N)) for _ in range(5)])
+    assert np.array_equal(noise.cpu().numpy(), ref)
+    assert np.abs(mean.cpu().numpy() - ref.reshape(5, -1).mean(axis=1)).max() < 1e-15
