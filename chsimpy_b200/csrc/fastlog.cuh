@@ -21,10 +21,18 @@ constexpr int LOG_TABLE_N = 128;
 constexpr unsigned long long LOG_OFF = 0x3fe6000000000000ULL;
 
 #ifdef CHS_EMU
+static inline int chs_hiword(double x) { long long v; std::memcpy(&v, &x, 8); return (int)(v >> 32); }
+static inline double chs_sethiword(double x, int hi) {
+    unsigned long long v; std::memcpy(&v, &x, 8);
+    v = (v & 0xffffffffULL) | ((unsigned long long)(unsigned)hi << 32);
+    double r; std::memcpy(&r, &v, 8); return r;
+}
 static inline long long chs_d2ll(double x) { long long v; std::memcpy(&v, &x, 8); return v; }
 static inline double chs_ll2d(long long v) { double x; std::memcpy(&x, &v, 8); return x; }
 static inline double chs_fma(double a, double b, double c) { return std::fma(a, b, c); }
 #else
+CHS_DEV int chs_hiword(double x) { return __double2hiint(x); }
+CHS_DEV double chs_sethiword(double x, int hi) { return __hiloint2double(hi, __double2loint(x)); }
 CHS_DEV long long chs_d2ll(double x) { return __double_as_longlong(x); }
 CHS_DEV double chs_ll2d(long long v) { return __longlong_as_double(v); }
 CHS_DEV double chs_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
@@ -53,13 +61,13 @@ CHS_DEV double div_ge1(double a, double b) {
 
 // tab: LOG_TABLE_N entries {invc, logc} (shared or global memory)
 CHS_DEV double fast_log(double x, const double2* __restrict__ tab) {
-    const unsigned long long ix = (unsigned long long)chs_d2ll(x);
-    const unsigned top = (unsigned)(ix >> 52);                       // sign + exponent
-    if (top - 1u >= 0x7feu) return slow_log(x);                      // <=0, subnormal, inf, nan
-    const unsigned long long tmp = ix - LOG_OFF;
-    const int i = (int)((tmp >> 45) & (LOG_TABLE_N - 1));
-    const int k = (int)((long long)tmp >> 52);
-    const double z = chs_ll2d((long long)(ix - (tmp & 0xfff0000000000000ULL)));
+    // all bit manipulation on the high 32-bit word (sign, exponent, 20 mantissa bits)
+    const int hx = chs_hiword(x);
+    if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u) return slow_log(x);   // <=0, subnormal, inf, nan
+    const int tmp = hx - 0x3fe60000;                                  // LOG_OFF >> 32
+    const int i = (tmp >> 13) & (LOG_TABLE_N - 1);
+    const int k = tmp >> 20;                                          // arithmetic shift: floor
+    const double z = chs_sethiword(x, hx - (int)((unsigned)tmp & 0xfff00000u));
     const double2 e = tab[i];
     const double r = chs_fma(z, e.x, -1.0);
     const double kd = (double)k;
