@@ -154,29 +154,41 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
     constexpr int M = G::M, LPC = G::LPC, TPL = G::TPL;
     constexpr int r = Rad<M>::radix(S), Lb = Rad<M>::blocklen(S), st = Lb / r;
     constexpr int NB = 16 / r;
+    // all 16 points of the thread are loaded before the first butterfly and stored after the
+    // last one: the compiler cannot prove that the in-place stores of one butterfly do not
+    // alias the loads of the next, so this is what exposes the memory-level parallelism
+    double xr[NB][r], xi[NB][r];
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const int u = t + i * TPL;
-        const int j = u % st, base = (u / st) * Lb + j;
-        double xr[r], xi[r];
+        const int base = (u / st) * Lb + (u % st);
 #pragma unroll
         for (int q = 0; q < r; ++q) {
             const double2 v = scl[(base + q * st) * LPC];
-            xr[q] = v.x; xi[q] = v.y;
+            xr[i][q] = v.x; xi[i][q] = v.y;
         }
-        if (!INV) dft<r, false>(xr, xi);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const int j = (t + i * TPL) % st;
+        if (!INV) dft<r, false>(xr[i], xi[i]);
         if (st > 1) {
 #pragma unroll
             for (int p = 1; p < r; ++p) {
                 const double2 w = __ldg(tw + j * p * (M / Lb));
-                const double a = xr[p], b = xi[p];
-                if (!INV) { xr[p] = a * w.x - b * w.y; xi[p] = a * w.y + b * w.x; }
-                else      { xr[p] = a * w.x + b * w.y; xi[p] = b * w.x - a * w.y; }     // conj(w)
+                const double a = xr[i][p], b = xi[i][p];
+                if (!INV) { xr[i][p] = a * w.x - b * w.y; xi[i][p] = a * w.y + b * w.x; }
+                else      { xr[i][p] = a * w.x + b * w.y; xi[i][p] = b * w.x - a * w.y; }     // conj(w)
             }
         }
-        if (INV) dft<r, true>(xr, xi);
+        if (INV) dft<r, true>(xr[i], xi[i]);
+    }
 #pragma unroll
-        for (int q = 0; q < r; ++q) scl[(base + q * st) * LPC] = make_double2(xr[q], xi[q]);
+    for (int i = 0; i < NB; ++i) {
+        const int u = t + i * TPL;
+        const int base = (u / st) * Lb + (u % st);
+#pragma unroll
+        for (int q = 0; q < r; ++q) scl[(base + q * st) * LPC] = make_double2(xr[i][q], xi[i][q]);
     }
 }
 
