@@ -856,7 +856,7 @@ extern "C" int chs_slab_clear_yedge(chs_slab* s) {
 // local sums -> vec (to be all-reduced over ranks by the caller when world > 1)
 extern "C" int chs_slab_reduce(chs_slab* s, int32_t rows, int32_t with_update) {
     if (!s) return fail("chs_slab_reduce: null handle");
-    CHS_LAUNCH(k_slab_reduce, dim3(1), dim3(32), 0, s->stream, (const double*)s->part, (int)(rows / slab_lines(s->N)),
+    CHS_LAUNCH(k_slab_reduce, dim3(1), dim3(32 * R_NVAL), 32 * R_NVAL * sizeof(double), s->stream, (const double*)s->part, (int)(rows / slab_lines(s->N)),
                (const double*)s->part_ge, with_update ? s->upd_used : 0, (const double*)s->yedge, s->vec);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());

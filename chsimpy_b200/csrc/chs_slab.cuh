@@ -282,16 +282,26 @@ CHS_KERNEL void k_slab_reduce_prepare(const double* part, int nblk, int N, doubl
     vec[R_GE] = s[0]; vec[R_F] = s[1]; vec[R_ABS] = s[2]; vec[R_RA] = s[3] / (double)N;
 }
 
-// vec[v] = sum over tiles of part[v][*] (+ the update kernel's GE blocks, + y-edge), fixed order
+// vec[v] = sum over tiles of part[v][*] (+ the update kernel's GE blocks, + y-edge); one group
+// of 32 threads per value, lane-strided partial sums added in fixed order (deterministic)
 CHS_KERNEL void k_slab_reduce(const double* part, int ntiles, const double* part_ge, int nge, const double* yedge,
                               double* vec) {
-    const int v = threadIdx.x;
-    if (v >= R_NVAL) return;
+    CHS_SMEM_DECL
+    double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);      // R_NVAL * 32
+    const int v = threadIdx.x / 32, lane = threadIdx.x % 32;
     double s = 0;
-    for (int i = 0; i < ntiles; ++i) s += part[v * ntiles + i];
-    if (v == R_GE) for (int i = 0; i < nge; ++i) s += part_ge[i];
-    if (v == R_EDGE) s += yedge[0];
-    vec[v] = s;
+    if (v < R_NVAL) {
+        for (int i = lane; i < ntiles; i += 32) s += part[v * ntiles + i];
+        if (v == R_GE) for (int i = lane; i < nge; i += 32) s += part_ge[i];
+        red[v * 32 + lane] = s;
+    }
+    __syncthreads();
+    if (v < R_NVAL && lane == 0) {
+        double t = 0;
+        for (int j = 0; j < 32; ++j) t += red[v * 32 + j];
+        if (v == R_EDGE) t += yedge[0];
+        vec[v] = t;
+    }
 }
 
 // step_control() of the tile path, fed with the rank-reduced sums (one thread; every rank runs
