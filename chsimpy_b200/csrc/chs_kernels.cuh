@@ -485,6 +485,7 @@ struct ColMid {
     const double* gsin;
     double* hat;                 // + column
     const double* hat_in;        // + column (COL_INV)
+    int hstride;                 // LINES (tile-major hat_U) or N (natural row-major, stand-alone transforms)
     double lam1, lam2, lamx, gx;
     double ge;
     double hn[4];                // hat_U of the next item (prefetched one item ahead)
@@ -501,7 +502,7 @@ struct ColMid {
         rows_of(k, idx);
         const double* src = (MODE == COL_INV) ? hat_in : hat;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hn[j] = src[(size_t)idx[j] * N];
+        for (int j = 0; j < 4; ++j) hn[j] = src[(size_t)idx[j] * hstride];
     }
     CHS_MEM void begin(int k) { fetch(k); }
     // takes the prefetched hat_U of item k and immediately starts the loads of item kn, which
@@ -515,7 +516,7 @@ struct ColMid {
         if (kn >= 0) fetch(kn);
         if (MODE == COL_FWD) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) hat[(size_t)idx[j] * N] = c[j];
+            for (int j = 0; j < 4; ++j) hat[(size_t)idx[j] * hstride] = c[j];
         } else if (MODE == COL_STEP) {
             // g[k] = sin^2(pi k/N): g[N-k] = g[k], g[M-k] = g[M+k] = 1 - g[k]  (one lookup per item)
             const double g0 = __ldg(gsin + idx[0]);
@@ -526,7 +527,7 @@ struct ColMid {
                 const double Se = __dmul_rn(lam1, leig);
                 const double CH = __dadd_rn(1.0, __dmul_rn(__dmul_rn(lam2, leig), leig));
                 const double hu = div_ge1(__dadd_rn(h[j], __dmul_rn(Se, c[j])), CH);
-                hat[(size_t)idx[j] * N] = hu;
+                hat[(size_t)idx[j] * hstride] = hu;
                 ge += (gs[j] + gx) * (hu * hu);
                 c[j] = hu;
             }
@@ -575,8 +576,8 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
         if (MODE != COL_INV) col_tile_load_async<N>(scl, a.T + off + kx0 + l, t);
         if (MODE == COL_STEP) {
             // the hat_U tile is consumed in the middle of the tile's work: pull it into L2 now
-            const double* hp = a.hatU + off + kx0;
-            for (int y = tid; y < N; y += NT) CHS_PREFETCH_L2(hp + (size_t)y * N);
+            const double* hp = a.hatU + off + (size_t)tile * N * LINES;          // contiguous 8*N*LINES bytes
+            for (int i = tid * 16; i < N * LINES; i += NT * 16) CHS_PREFETCH_L2(hp + i);
         }
         const int col = (MODE != COL_STEP && a.natural) ? a.kof[kx0 + l] : kx0 + l;   // far-side column
         double lam1 = 0, lam2 = 0, lamx = 0, gxs = 0;
@@ -607,8 +608,13 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
             }
             ColMid<N, MODE> mid;
             mid.om = s_om; mid.lam = s_lam; mid.gsin = a.gsin;
-            mid.hat = ((MODE == COL_FWD && a.dst) ? a.dst : a.hatU) + off + col;
-            mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + off + col;
+            // hat_U is stored tile-major ([tile][ky][LINES]): the tile of a CTA is one contiguous block;
+            // the stand-alone transforms use natural row-major arrays on the far side
+            const bool nat = (MODE != COL_STEP) && a.natural;
+            mid.hstride = nat ? N : LINES;
+            const size_t toff = nat ? off + col : off + (size_t)tile * N * LINES + l;
+            mid.hat = ((MODE == COL_FWD && a.dst) ? a.dst : a.hatU) + toff;
+            mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + toff;
             mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
             for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, mid);
             if (MODE != COL_FWD) {
