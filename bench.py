@@ -98,7 +98,7 @@ def run_reference(args):
     fac, kap = member_scalars(cores)
     jobs = [(fac[i, 0], fac[i, 1], kap[i], args.warmup * sample, args.steps * sample) for i in range(cores)]
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
+    with mp.get_context("forkserver").Pool(cores) as pool:
         secs = pool.map(_oracle_member, jobs)
     wall = max(secs)
     value = cores * args.steps * sample / wall

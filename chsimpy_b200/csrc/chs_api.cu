@@ -178,18 +178,16 @@ static int set_attrs(chs_solver* s) {
     return 0;
 }
 
-// Grid of a tile kernel.  Default build: one CTA per tile.  -DCHS_PERSISTENT (experimental)
-// and the host emulation: resident CTAs that loop over tiles (CHS_TILE_LOOP); the environment
-// variable CHS_CTAS_PER_SM then caps the CTAs per SM so that two kernels of two handles on
-// two streams can be co-resident (tools/cosched_bench.py).
+// Grid of a tile kernel: one CTA per tile.  (-DCHS_PERSISTENT builds resident CTAs that loop
+// over tiles instead -- measured slower on B200, kept as a compile-time experiment; the host
+// emulation always loops so that a few OS-thread blocks cover all tiles.)
 static dim3 pgrid(int cap, int num_sms, int ntiles, int nsims) {
     const long long total = (long long)ntiles * nsims;
+    (void)num_sms;
 #if defined(CHS_EMU) || defined(CHS_PERSISTENT)
-    static const int per_sm = [] { const char* e = getenv("CHS_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-    if (per_sm > 0 && per_sm * num_sms < cap) cap = per_sm * num_sms;
     return dim3((unsigned)(total < cap ? total : cap));
 #else
-    (void)cap; (void)num_sms;
+    (void)cap;
     return dim3((unsigned)total);
 #endif
 }

@@ -187,7 +187,8 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
         jobs.append((p.R, p.temp, p.B, float(p.func_A0(p.temp)), float(p.func_A1(p.temp)), p.XXX, p.kappa_tilde))
     nproc = host_procs or min(len(jobs), utils.get_number_physical_cores() or 1)
     if nproc > 1 and len(jobs) > 1:
-        with mp.get_context("fork").Pool(nproc) as pool:
+        # forkserver: the workers start from a clean process (no CUDA context, no torch threads)
+        with mp.get_context("forkserver").Pool(nproc) as pool:
             scal = pool.map(_host_scalars, jobs, chunksize=max(1, len(jobs) // (4 * nproc)))
     else:
         scal = [_host_scalars(j) for j in jobs]
@@ -238,12 +239,9 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
     return out
 
 
-_EXPORT_JOBS = None      # fork-inherited (Solution objects hold lambdas and cannot be pickled)
-
-
-def _export_member(index):
+def _export_member(job):
     """Per-run files of reference simulator.py:135-156 (yaml scalars + csv matrices)."""
-    fname_sol, yaml_on, export_csv, compress, sol = _EXPORT_JOBS[index]
+    fname_sol, yaml_on, export_csv, compress, sol = job
     if yaml_on:
         sol.yaml_export_scalars(fname=fname_sol + '.yaml')
     if export_csv is not None:
@@ -292,16 +290,12 @@ def main(argv=None):
     if not ep.no_export:
         jobs = [(f"{r['params'].file_id}.solution", init_params.yaml, init_params.export_csv,
                  init_params.compress_csv, r["solution"]) for r in res]
-        global _EXPORT_JOBS
-        _EXPORT_JOBS = jobs
-        nproc = max(1, min(len(jobs), utils.get_number_physical_cores() or 1))
-        if nproc > 1:
-            with mp.get_context("fork").Pool(nproc) as pool:
-                pool.map(_export_member, range(len(jobs)))
-        else:
-            for j in range(len(jobs)):
-                _export_member(j)
-        _EXPORT_JOBS = None
+        # threads, not processes: Solution objects hold lambdas (not picklable) and a CUDA process
+        # should not fork; bz2 compression releases the GIL
+        from concurrent.futures import ThreadPoolExecutor
+        nthr = max(1, min(len(jobs), utils.get_number_physical_cores() or 1))
+        with ThreadPoolExecutor(nthr) as ex_:
+            list(ex_.map(_export_member, jobs))
     tuples = [r["tuple"] for r in res]
     if world > 1:
         import torch.distributed as dist

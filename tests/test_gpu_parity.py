@@ -322,3 +322,45 @@ def test_device_pcg64_is_numpy_bit_exact():
     ref = np.stack([g.random((N, N)) for _ in range(5)])
     assert np.array_equal(noise.cpu().numpy(), ref)
     assert np.abs(mean.cpu().numpy() - ref.reshape(5, -1).mean(axis=1)).max() < 1e-15
+
+
+def test_experiment_main_end_to_end(tmp_path, monkeypatch):
+    """`python -m chsimpy_b200.experiment` flow (reference experiment.py:129-233): factor table,
+    batched solve to the energy stop, per-run exports, results + aggregate CSVs."""
+    import pandas as pd
+    from chsimpy_b200 import experiment as ex
+    monkeypatch.chdir(tmp_path)
+    ex.main(["-N", "64", "-R", "6", "--A-seed", "85972", "--cinit", "0.89", "--threshold", "0.89", "-n", "400",
+             "-f", "exp", "--export-csv", "E2,SA", "-P", "2"])
+    df = pd.read_csv("exp-results.csv", index_col=0)
+    assert list(df.columns) == ex.RESULT_COLUMNS and len(df) == 6 and sorted(df["id"]) == list(range(6))
+    want = np.random.Generator(np.random.PCG64(85972)).uniform(0.995, 1.005, size=(6, 2))
+    assert np.allclose(df.sort_values("id")[["fac_A0", "fac_A1"]].values, want, rtol=0, atol=1e-15)
+    assert (df["ca"] < df["cb"]).all() and (df["sa"] < df["sb"]).all() and (df["tau0"] >= 0).all()
+    agg = pd.read_csv("exp-results-agg.csv", index_col=0)
+    assert "cv" in agg.columns and "mean" in agg.columns
+    assert os.path.exists("exp-run3.solution.yaml") and os.path.exists("exp-run3.solution.E2.csv")
+    assert os.path.exists("exp-metadata.csv")
+
+
+def test_uinit_file_and_nan_field(tmp_path):
+    """--Uinit-file restart path (simulator.py:21-22) and the NaN assertion (timedata.py:10) when
+    the field leaves (0,1)."""
+    import chsimpy_b200 as ch
+    p = ch.Parameters()
+    p.N, p.no_gui, p.kappa_tilde, p.full_sim, p.ntmax = 64, True, 3e-4, True, 30
+    s = ch.Simulator(p)
+    sol = s.solve()
+    f = str(tmp_path / "U.csv")
+    ch.utils.csv_export_matrix(sol.U, f)
+    p2 = p.deepcopy()
+    p2.Uinit_file, p2.ntmax = f, 10
+    s2 = ch.Simulator(p2)
+    assert s2.solver.create_rand is None and np.abs(s2.solver.U_init - sol.U).max() < 1e-15
+    sol2 = s2.solve()
+    assert sol2.computed_steps == 10
+    bad = sol.U.copy()
+    bad[5, 7] = 1.25                          # log(1-U) of a negative number
+    s3 = ch.Solver(p, U_init=bad)
+    with pytest.raises(AssertionError):
+        s3.prepare()
