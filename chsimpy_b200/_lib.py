@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libchs_b200.so")
 SOURCES = ("chs_api.cu", "chs_kernels.cuh", "chs_slab.cuh", "chs_gemm.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
+# (no -split-compile: it builds 2x faster but the kernels measured 6 % slower on B200)
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
 
