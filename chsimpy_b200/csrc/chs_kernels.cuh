@@ -306,7 +306,7 @@ CHS_DEV void col_tile_load_async(double2* scl, const double* __restrict__ g, int
         const int c = t + j * G::TPL;
         int y0, y1;
         col_pair_rows<N>(c, y0, y1);
-        double* d = reinterpret_cast<double*>(scl + c * G::LPC);
+        double* d = reinterpret_cast<double*>(scl + G::idx(c));
         chs_cp_async8(d, g + (size_t)y0 * N);
         chs_cp_async8(d + 1, g + (size_t)y1 * N);
     }
@@ -320,7 +320,7 @@ CHS_DEV void col_tile_store(const double2* scl, double* __restrict__ g, int t) {
         const int c = t + j * G::TPL;
         int y0, y1;
         col_pair_rows<N>(c, y0, y1);
-        const double2 v = scl[c * G::LPC];
+        const double2 v = scl[G::idx(c)];
         g[(size_t)y0 * N] = v.x;
         g[(size_t)y1 * N] = v.y;
     }
@@ -335,7 +335,7 @@ CHS_DEV void row_tile_load_slots_async(double2* sc, const double* __restrict__ g
 #pragma unroll
     for (int j = 0; j < CNT; ++j) {
         const int i = tid + j * G::NT;
-        chs_cp_async16(sc + (i % M) * G::LPC + (i / M), g2 + (size_t)(i / M) * M + (i % M));
+        chs_cp_async16(sc + G::idx(i % M) + (i / M) * G::LOFF, g2 + (size_t)(i / M) * M + (i % M));
     }
 }
 
@@ -347,7 +347,7 @@ CHS_DEV void row_tile_store_slots(const double2* sc, double* __restrict__ g, int
 #pragma unroll 8
     for (int j = 0; j < CNT; ++j) {
         const int i = tid + j * G::NT;
-        g2[(size_t)(i / M) * M + (i % M)] = sc[(i % M) * G::LPC + (i / M)];
+        g2[(size_t)(i / M) * M + (i % M)] = sc[G::idx(i % M) + (i / M) * G::LOFF];
     }
 }
 
@@ -367,7 +367,7 @@ CHS_DEV void row_tile_load_phys(double* sm, const double* __restrict__ g, int ti
 #pragma unroll
         for (int j = 0; j < UNR; ++j) {
             const int i = tid + (j0 + j) * G::NT;
-            sm[real_off<N>(mk_pos<N>(i % N)) + 2 * (i / N)] = v[j];
+            sm[real_off<N>(mk_pos<N>(i % N)) + 2 * G::LOFF * (i / N)] = v[j];
         }
     }
 }
@@ -379,7 +379,7 @@ CHS_DEV void row_tile_store_phys(const double* sm, double* __restrict__ g, int t
 #pragma unroll 8
     for (int j = 0; j < CNT; ++j) {
         const int i = tid + j * G::NT;
-        g[(size_t)(i / N) * N + (i % N)] = sm[real_off<N>(mk_pos<N>(i % N)) + 2 * (i / N)];
+        g[(size_t)(i / N) * N + (i % N)] = sm[real_off<N>(mk_pos<N>(i % N)) + 2 * G::LOFF * (i / N)];
     }
 }
 
@@ -431,14 +431,14 @@ template <int N>
 CHS_DEV void load_block(const double2* scl, int base, double (&xr)[8], double (&xi)[8]) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const double2 v = scl[(base + c) * Geo<N>::LPC];
+        const double2 v = scl[Geo<N>::idx(base) + c * Geo<N>::LPC];
         xr[c] = v.x; xi[c] = v.y;
     }
 }
 template <int N>
 CHS_DEV void store_block(double2* scl, int base, const double (&xr)[8], const double (&xi)[8]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) scl[(base + c) * Geo<N>::LPC] = make_double2(xr[c], xi[c]);
+    for (int c = 0; c < 8; ++c) scl[Geo<N>::idx(base) + c * Geo<N>::LPC] = make_double2(xr[c], xi[c]);
 }
 
 // in-place slot convention of the row kernels: element pos(k) = (C[k], C[N-k])
@@ -566,8 +566,8 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
     const double2* __restrict__ s_tw = a.tw;
     const double2* __restrict__ s_om = a.om;
     const double* __restrict__ s_lam = a.lam;
-    const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
-    double2* scl = sc + l;
+    const int tid = threadIdx.x, l = G::line_of(tid), t = G::t_of(tid);
+    double2* scl = sc + l * G::LOFF;
         const int si = w / G::NTILES, tile = w % G::NTILES, kx0 = tile * LINES;
         const int sim = a.sim_index ? a.sim_index[si] : si;
         Sim* S = a.sims + sim;
@@ -711,8 +711,8 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
     int* flag = reinterpret_cast<int*>(sm + G::OFF_FLAG);
     double* edge = sm + G::OFF_EDGE;
     double* ra_scr = sm + G::OFF_RA;
-    const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
-    double2* scl = sc + l;
+    const int tid = threadIdx.x, l = G::line_of(tid), t = G::t_of(tid);
+    double2* scl = sc + l * G::LOFF;
     const bool control = (MODE == ROW_STEP) || (MODE == ROW_FWD_MU);
     const bool jit = (MODE == ROW_STEP) && (a.noise != nullptr);
     const bool diag = (MODE == ROW_STEP) && !jit;
@@ -801,7 +801,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                         }
 #pragma unroll
                         for (int q = 0; q < R0; ++q) {
-                            const double2 v = scl[(j + q * ST0) * LPC];
+                            const double2 v = scl[G::idx(j) + q * G::step(ST0)];
                             xr[q] = v.x; xi[q] = v.y;
                         }
                         if (!slow) {
@@ -824,7 +824,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                             }
                         }
 #pragma unroll
-                        for (int q = 0; q < R0; ++q) scl[(j + q * ST0) * LPC] = make_double2(xr[q], xi[q]);
+                        for (int q = 0; q < R0; ++q) scl[G::idx(j) + q * G::step(ST0)] = make_double2(xr[q], xi[q]);
                     }
                     if (ra_line) ra_scr[2 + t] = acc.ra;
                     const double v[4] = {acc.f, acc.ab, acc.mu2, acc.cnt};

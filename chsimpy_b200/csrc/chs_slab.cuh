@@ -47,8 +47,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, 1) k_slab_row(SlabArgs a) {
     double2* sc = reinterpret_cast<double2*>(sm);
     double* edge = sm + G::OFF_EDGE;
     double* ra_scr = sm + G::OFF_RA;
-    const int tid = threadIdx.x, l = tid % LINES, t = tid / LINES;
-    double2* scl = sc + l;
+    const int tid = threadIdx.x, l = G::line_of(tid), t = G::t_of(tid);
+    double2* scl = sc + l * G::LOFF;
     const int ntiles = a.rows / LINES;
     const bool physics_on = (MODE == S_MU) || (MODE == S_STEP);
     const bool diag = physics_on && a.diag;
@@ -98,7 +98,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, 1) k_slab_row(SlabArgs a) {
                     double xr[R0], xi[R0];
 #pragma unroll
                     for (int q = 0; q < R0; ++q) {
-                        const double2 v = scl[(j + q * ST0) * LPC];
+                        const double2 v = scl[G::idx(j) + q * G::step(ST0)];
                         xr[q] = v.x; xi[q] = v.y;
                     }
                     physics<N, R0>(xr, xi, j, p, ltab, diag, a.mean_u, ra_line, ra_mean, acc, edge + 4 * l);
@@ -111,7 +111,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, 1) k_slab_row(SlabArgs a) {
                         xi[q] = x * w.y + y * w.x;
                     }
 #pragma unroll
-                    for (int q = 0; q < R0; ++q) scl[(j + q * ST0) * LPC] = make_double2(xr[q], xi[q]);
+                    for (int q = 0; q < R0; ++q) scl[G::idx(j) + q * G::step(ST0)] = make_double2(xr[q], xi[q]);
                 }
                 if (ra_line) ra_scr[2 + t] = acc.ra;
                 const double v[4] = {acc.f, acc.ab, acc.mu2, acc.cnt};

@@ -49,8 +49,34 @@ struct Geo {
     // 8 lines per tile up to N = 2048; larger rows shrink the tile so that it still fits in
     // shared memory (only the row kernels of the slab path are built for N > 1024)
     static constexpr int LINES = (N <= 2048) ? CHS_LINES : (16384 / N);
-    static constexpr int LPC = (LINES == 1) ? 1 : LINES + 1;   // line pitch in double2 (odd: conflict-free transposing I/O)
+    // Two tile layouts (complex point c of line l, in double2 units):
+    //   point-major (N <= 2048): c*LPC + l, the lines of a point adjacent (they are the lanes of
+    //     a warp), odd pitch for the transposing tile I/O;
+    //   line-major (N >= 4096, <= 4 lines): l*LOFF + c + pad(c), every warp works on ONE line so
+    //     that its 16-byte accesses are contiguous; pad() skews the 8-point blocks of the fused
+    //     last stage (block positions of consecutive residues are M/8 or M/16 apart) over the
+    //     banks.  pad is additive over the strides the stages use, see step().
+    static constexpr bool LINE_MAJOR = (LINES <= 4);
+    static constexpr int LPC = LINE_MAJOR ? 1 : LINES + 1;     // point pitch
+    static constexpr int SH1 = 9, SH2 = (M == 2048) ? 6 : ((M == 8192) ? 12 : 30), W2 = (M == 4096) ? 0 : 4;
+    CHS_CX static constexpr int pad(int c) { return LINE_MAJOR ? (c >> SH1) + W2 * (c >> SH2) : 0; }
+    CHS_CX static constexpr int idx(int c) { return LINE_MAJOR ? c + pad(c) : c * LPC; }
+    // idx(base + q*st) = idx(base) + q*step(st) for the points of one butterfly
+    CHS_CX static constexpr int step(int st) { return LINE_MAJOR ? st + pad(st) : st * LPC; }
+    static constexpr int LOFF = LINE_MAJOR ? M + (M >> SH1) + W2 * (M >> SH2) : 1;              // line offset
+    // every stage either strides by a multiple of a pad term's period or stays inside one period
+    CHS_CX static constexpr bool pad_ok() {
+        if (!LINE_MAJOR) return true;
+        for (int s = 0; s < Rad<M>::nst; ++s) {
+            const int Lb = Rad<M>::blocklen(s), st = Lb / Rad<M>::radix(s);
+            if (!(st >= (1 << SH1) || Lb <= (1 << SH1))) return false;
+            if (W2 && !(st >= (1 << SH2) || Lb <= (1 << SH2))) return false;
+        }
+        return true;
+    }
     static constexpr int TPL = M / 16;                         // threads per line: 16 complex points each per stage
+    CHS_CX static constexpr int line_of(int tid) { return LINE_MAJOR ? tid / (M / 16) : tid % LINES; }
+    CHS_CX static constexpr int t_of(int tid) { return LINE_MAJOR ? tid % (M / 16) : tid / LINES; }
     static constexpr int NT = LINES * TPL;                     // threads per CTA
     static constexpr int NTILES = N / LINES;
     static constexpr int MINB = (65536 / 128) / NT > 16 ? 16 : ((65536 / 128) / NT > 0 ? (65536 / 128) / NT : 1);   // CTAs per SM at 128 registers/thread
@@ -62,7 +88,7 @@ struct Geo {
 #endif
     static constexpr int MINB_ROW = (NT == 128) ? CHS_MINB_ROW : MINB;   // N = 512: tuned on B200 (profiles/)
     static constexpr int MINB_COL = (NT == 128) ? CHS_MINB_COL : MINB;
-    static constexpr int TILE_DOUBLES = 2 * M * LPC;
+    static constexpr int TILE_DOUBLES = LINE_MAJOR ? 2 * LINES * LOFF : 2 * M * LPC;
     // scratch after the tile (doubles): flag | x/y edge values | Ra | fast_log table | reduction
     static constexpr int OFF_FLAG = TILE_DOUBLES;
     static constexpr int OFF_EDGE = OFF_FLAG + 2;              // [LINES][4]
@@ -73,6 +99,7 @@ struct Geo {
     static_assert(N >= 32 && (N & (N - 1)) == 0, "FFT path needs a power of two >= 32");
     static_assert(Rad<M>::radix(Rad<M>::nst - 1) == 8 && Rad<M>::nst >= 2, "plan must end with a radix-8 stage");
     static_assert((OFF_LOGTAB % 2) == 0, "double2 alignment");
+    static_assert(pad_ok(), "bank skew is not additive for this radix plan");
 };
 
 // Makhoul reorder: physical index n -> position in v
@@ -81,7 +108,7 @@ CHS_DEV int mk_pos(int n) { return (n & 1) ? (N - 1 - (n >> 1)) : (n >> 1); }
 
 // offset (in doubles) of real element p (= v index: complex p>>1, part p&1) of line 0
 template <int N>
-CHS_DEV int real_off(int p) { return 2 * ((p >> 1) * Geo<N>::LPC) + (p & 1); }
+CHS_DEV int real_off(int p) { return 2 * Geo<N>::idx(p >> 1) + (p & 1); }
 
 // position of frequency k after the in-place DIF (mixed-radix digit reversal)
 template <int M>
@@ -146,12 +173,12 @@ CHS_DEV void dft(double (&xr)[R], double (&xi)[R]) {
 }
 
 // ------------------------------------------------------------------ regular FFT stages
-// scl = (double2*)tile + l (line base), t = thread index within the line,
+// scl = (double2*)tile + l*LOFF (line base), t = thread index within the line,
 // tw[m] = exp(-2 pi i m / M).  Every thread owns 16/r butterflies of radix r.
 template <int N, int S, bool INV>
 CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
     using G = Geo<N>;
-    constexpr int M = G::M, LPC = G::LPC, TPL = G::TPL;
+    constexpr int M = G::M, TPL = G::TPL;
     constexpr int r = Rad<M>::radix(S), Lb = Rad<M>::blocklen(S), st = Lb / r;
     constexpr int NB = 16 / r;
     // all 16 points of the thread are loaded before the first butterfly and stored after the
@@ -164,7 +191,7 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
         const int base = (u / st) * Lb + (u % st);
 #pragma unroll
         for (int q = 0; q < r; ++q) {
-            const double2 v = scl[(base + q * st) * LPC];
+            const double2 v = scl[G::idx(base) + q * G::step(st)];
             xr[i][q] = v.x; xi[i][q] = v.y;
         }
     }
@@ -188,7 +215,7 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
         const int u = t + i * TPL;
         const int base = (u / st) * Lb + (u % st);
 #pragma unroll
-        for (int q = 0; q < r; ++q) scl[(base + q * st) * LPC] = make_double2(xr[i][q], xi[i][q]);
+        for (int q = 0; q < r; ++q) scl[G::idx(base) + q * G::step(st)] = make_double2(xr[i][q], xi[i][q]);
     }
 }
 

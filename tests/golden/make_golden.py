@@ -53,6 +53,9 @@ CASES = {
     "n256_k200": dict(p=dict(N=256, ntmax=200, full_sim=True), keep_U=True),
     "n1024_k50": dict(p=dict(N=1024, ntmax=50, full_sim=True), keep_U=False),
     "n2048_k10": dict(p=dict(N=2048, ntmax=10, full_sim=True), keep_U=False),
+    # BASELINE config 5 sizes (the reference needs about 6.5 s and 8 GiB per step at N=8192)
+    "n4096_k6": dict(p=dict(N=4096, ntmax=6, full_sim=True), keep_U=False),
+    "n8192_k4": dict(p=dict(N=8192, ntmax=4, full_sim=True), keep_U=False),
     "n100_k100": dict(p=dict(N=100, ntmax=100, full_sim=True), keep_U=True),     # benchmark.py -N 100 smoke size
     # other generators / user-supplied field
     "n64_lcg_k100": dict(p=dict(N=64, ntmax=100, full_sim=True, generator="lcg"), keep_U=True, keep_Uinit=True),

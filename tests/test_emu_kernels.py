@@ -137,3 +137,57 @@ def test_pcg64_device_stream_emulated(be):
     noise, mean = st.pcg64_noise(g.bit_generator.state, 2)
     ref = np.stack([g.random((32, 32)) for _ in range(2)])
     assert np.array_equal(noise, ref)
+
+
+def slot_freqs(N):
+    """Frequency held by each slot of an x-spectral row (the `kof` table of chs_api.cu)."""
+    M = N // 2
+    lg = M.bit_length() - 1
+    rad = ([1 << (lg % 3)] if lg % 3 else []) + [8] * (lg // 3)
+    kof = np.empty(N, np.int64)
+    for k in range(M):
+        pos, Lb, kk = 0, M, k
+        for r in rad:
+            pos += (kk % r) * (Lb // r)
+            kk //= r
+            Lb //= r
+        kof[2 * pos] = k
+        kof[2 * pos + 1] = M if k == 0 else N - k
+    return kof
+
+
+@pytest.mark.parametrize("N", [2048, 4096, 8192, 16384])
+def test_slab_row_kernels_large_rows(be, N):
+    """Row kernels of the slab path at the BASELINE config-5 row lengths (line-major tile with
+    bank skew for N >= 4096): forward, inverse and the fused inverse -> physics -> forward pass
+    on two tiles of rows, against scipy's DCT and the chemical potential in numpy."""
+    import ctypes as C
+    lib = be.lib
+    R = 2 * lib.chs_slab_row_granularity(N)
+    ps = unit_params(N)
+    U, A, B, D = (be.empty((R, N)) for _ in range(4))
+    rows = be.empty((4, 9))
+    wbytes = lib.chs_slab_workspace_bytes(N, R)
+    work = be.empty((wbytes,), "u1")
+    lam = np.ascontiguousarray(ch.utils.laplace_spectrum_1d(N))
+    h = lib.chs_slab_create(0, N, R, 0, 1, 0, C.byref(ps), be.ptr(U), be.ptr(rows), 4, be.ptr(work), wbytes,
+                            lam.ctypes.data, be.stream_handle())
+    assert h
+    try:
+        kof = slot_freqs(N)
+        u = 0.85 + 0.1 * (np.random.default_rng(N).random((R, N)) - 0.5)
+        be.upload(U, u)
+        assert lib.chs_slab_row(h, 0, be.ptr(U), be.ptr(A), R, 0, 0, 0.0) == 0          # S_FWD
+        a = be.download(A)
+        ref = fp.dct(u, axis=1, norm="ortho")
+        assert np.abs(a - ref[:, kof]).max() < 1e-12
+        assert lib.chs_slab_row(h, 2, be.ptr(A), be.ptr(B), R, 0, 0, 0.0) == 0          # S_INV
+        assert np.abs(be.download(B) - u).max() < 1e-13
+        be.upload(U, np.zeros((R, N)))
+        assert lib.chs_slab_row(h, 3, be.ptr(A), be.ptr(D), R, 0, 1, float(u.mean())) == 0   # S_STEP
+        assert np.abs(be.download(U) - u).max() < 1e-13                                 # the field it stores
+        d = 1 - 2 * u
+        mu = np.log(u / (1 - u)) - 1 + (1 + d) * d - 2 * u * (1 - u)                     # unit_params: RT=BRT=A0=A1=1
+        assert np.abs(be.download(D) - fp.dct(mu, axis=1, norm="ortho")[:, kof]).max() < 1e-11
+    finally:
+        lib.chs_slab_destroy(h)

@@ -224,7 +224,8 @@ def test_ensemble_corners_and_centre():
     assert abs(ca - 0.8121353) < 5e-7 and abs(cb - 0.9723917) < 5e-7
 
 
-@pytest.mark.parametrize("name,force", [("n2048_k10", False), ("n256_k200", True), ("n1024_k50", True)])
+@pytest.mark.parametrize("name,force", [("n2048_k10", False), ("n256_k200", True), ("n1024_k50", True),
+                                        ("n4096_k6", False), ("n8192_k4", False)])
 def test_slab_path_single_gpu(name, force):
     """Row-slab path (chs_slab.cuh) on one GPU: automatically for N > 1024, forced for smaller N."""
     import chsimpy_b200 as ch
