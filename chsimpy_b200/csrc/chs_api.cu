@@ -663,7 +663,7 @@ static SlabLayout slab_layout(int N, int rows) {
     const size_t npart = (size_t)R_NVAL * ntiles > (size_t)4 * SLAB_PREP_BLOCKS ? (size_t)R_NVAL * ntiles : (size_t)4 * SLAB_PREP_BLOCKS;
     L.sim = o; o = align_up(o + sizeof(Sim));
     L.part = o; o = align_up(o + sizeof(double) * npart);
-    L.part_ge = o; o = align_up(o + sizeof(double) * SLAB_UPD_BLOCKS);
+    L.part_ge = o; o = align_up(o + sizeof(double) * (size_t)(ntiles > SLAB_UPD_BLOCKS ? ntiles : SLAB_UPD_BLOCKS));
     L.yedge = o; o = align_up(o + sizeof(double) * 2);
     L.vec = o; o = align_up(o + sizeof(double) * R_NVAL);
     L.tw = o; o = align_up(o + sizeof(double2) * (size_t)(N / 2));
@@ -706,6 +706,8 @@ static int slab_set_attrs() {
     CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_YFWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_slab_row<N, S_YSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     return 0;
 }
 
@@ -777,11 +779,13 @@ extern "C" double* chs_slab_vec(chs_slab* s) { return s ? s->vec : nullptr; }
 extern "C" int64_t chs_slab_launch_count(const chs_slab* s) { return s ? s->launches : 0; }
 
 template <int N>
-static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int rows, int row_base, int diag, double mean_u) {
+static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int rows, int row_base, int diag, double mean_u,
+                    double* H = nullptr) {
     using G = Geo<N>;
     SlabArgs a;
     a.src = src; a.dst = dst; a.Uout = s->U; a.rows = rows; a.row_base = row_base; a.diag = diag; a.mean_u = mean_u;
     a.part = s->part; a.S = s->sim; a.tw = s->tw; a.om = s->om; a.logtab = s->logtab;
+    a.H = H; a.part_ge = s->part_ge; a.lam = s->lam; a.gsin = s->gsin; a.kof = s->kof;
     const int ntiles = rows / G::LINES;
 #ifdef CHS_EMU
     const dim3 grid(ntiles < 3 ? ntiles : 3);
@@ -794,6 +798,8 @@ static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int r
         case S_MU: CHS_LAUNCH((k_slab_row<N, S_MU>), grid, block, G::SMEM_BYTES, s->stream, a); break;
         case S_INV: CHS_LAUNCH((k_slab_row<N, S_INV>), grid, block, G::SMEM_BYTES, s->stream, a); break;
         case S_STEP: CHS_LAUNCH((k_slab_row<N, S_STEP>), grid, block, G::SMEM_BYTES, s->stream, a); break;
+        case S_YFWD: CHS_LAUNCH((k_slab_row<N, S_YFWD>), grid, block, G::SMEM_BYTES, s->stream, a); break;
+        case S_YSTEP: CHS_LAUNCH((k_slab_row<N, S_YSTEP>), grid, block, G::SMEM_BYTES, s->stream, a); break;
         default: return fail("chs_slab_row: bad mode");
     }
     s->launches += 1;
@@ -807,7 +813,9 @@ static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int r
 extern "C" int chs_slab_row(chs_slab* s, int32_t mode, const double* src, double* dst, int32_t rows, int32_t row_base,
                             int32_t diag, double mean_u) {
     if (!s || !src || !dst || rows < 1 || rows % slab_lines(s->N)) return fail("chs_slab_row: bad argument");
-#define CALL(NN) if (slab_row<NN>(s, mode, src, dst, rows, row_base, diag, mean_u)) return -1;
+    if (mode == S_YSTEP) return fail("chs_slab_row: mode 5 is chs_slab_update");
+    // S_YFWD: dst is hat_U' (x-slot rows, natural ky columns)
+#define CALL(NN) if (slab_row<NN>(s, mode, src, dst, rows, row_base, diag, mean_u, mode == S_YFWD ? dst : nullptr)) return -1;
     CHS_FOR_SLAB_N(s->N, CALL)
 #undef CALL
     return 0;
@@ -822,19 +830,15 @@ extern "C" int chs_slab_transpose(chs_slab* s, const double* in, double* out, in
     return 0;
 }
 
-// H = (H + Seig*B)/CHeig on `rows` local slot-rows (global slot index slot_base + r)
-extern "C" int chs_slab_update(chs_slab* s, double* H, const double* B, int32_t rows, int32_t slot_base) {
-    if (!s || !H || !B) return fail("chs_slab_update: bad argument");
-#ifdef CHS_EMU
-    const int nb = 2, nt = 64;
-#else
-    const int nb = SLAB_UPD_BLOCKS, nt = 256;
-#endif
-    CHS_LAUNCH(k_slab_update, dim3(nb), dim3(nt), nt * sizeof(double), s->stream, H, B, (int)rows, s->N, (int)slot_base,
-               (const int*)s->kof, (const double*)s->lam, (const double*)s->gsin, (const Sim*)s->sim, s->part_ge);
-    s->upd_used = nb;
-    s->launches += 1;
-    CHS_CUDA(cudaGetLastError());
+// The whole y pass of a step on `rows` local x-slot rows (global slot index slot_base + r), B holding
+// the transposed x-transformed mu (physical y along the row) on entry:
+//   H = (H + Seig*rowDCT(B))/CHeig ;  B = rowIDCT(H)      (one kernel, one read of B and H, one write of each)
+extern "C" int chs_slab_update(chs_slab* s, double* H, double* B, int32_t rows, int32_t slot_base) {
+    if (!s || !H || !B || rows < 1 || rows % slab_lines(s->N)) return fail("chs_slab_update: bad argument");
+#define CALL(NN) if (slab_row<NN>(s, S_YSTEP, B, B, rows, slot_base, 0, 0.0, H)) return -1;
+    CHS_FOR_SLAB_N(s->N, CALL)
+#undef CALL
+    s->upd_used = rows / slab_lines(s->N);
     return 0;
 }
 

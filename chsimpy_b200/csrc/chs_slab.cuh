@@ -6,9 +6,10 @@
 //
 //   A  = rowDCT(mu(U))                       k_slab_row<S_STEP> of the previous step / <S_MU>
 //   B  = transpose(A)                        pack -> all-to-all -> unpack   (x-slot rows, y cols)
-//   B  = rowDCT(B)                           k_slab_row<S_FWD>    -> hat_mu'
-//   H  = (H + Seig*B)/CHeig, grad. energy    k_slab_update        (H = hat_U', slot order on both axes)
-//   B  = rowIDCT(H)                          k_slab_row<S_INV>
+//   B  = rowIDCT(H = (H + Seig*rowDCT(B))/CHeig), spectral gradient energy
+//                                            k_slab_row<S_YSTEP>: ONE pass, the spectral update sits
+//                                            between the last forward and the first inverse stage
+//                                            (H = hat_U': x-slot rows, natural ky columns)
 //   A  = transpose(B)                        pack -> all-to-all -> unpack
 //   U, A = rowIDCT(A), physics, rowDCT(mu)   k_slab_row<S_STEP>   (per-tile partial sums)
 //   sums -> all-reduce -> k_slab_control     (TimeData row, NaN flag, stop test, time accounting)
@@ -17,7 +18,7 @@
 
 namespace chs {
 
-enum { S_FWD = 0, S_MU = 1, S_INV = 2, S_STEP = 3 };
+enum { S_FWD = 0, S_MU = 1, S_INV = 2, S_STEP = 3, S_YFWD = 4, S_YSTEP = 5 };
 // reduced vector layout (all-reduced over ranks)
 enum { R_GE = 0, R_EDGE, R_F, R_ABS, R_MU2, R_CNT, R_RA, R_NVAL };
 
@@ -30,6 +31,11 @@ struct SlabArgs {
     int diag;                   // S_MU / S_STEP: accumulate the diagnostics of the field
     double mean_u;              // conserved mean of U (PS)
     double* part;               // [R_NVAL][rows/LINES] per-tile partial sums
+    double* H;                  // S_YFWD / S_YSTEP: hat_U' rows (x-slot row_base + r, natural ky)
+    double* part_ge;            // S_YSTEP: [rows/LINES] spectral gradient-energy sums
+    const double* lam;
+    const double* gsin;
+    const int* kof;
     Sim* S;
     const double2* tw;
     const double2* om;
@@ -57,6 +63,55 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, 1) k_slab_row(SlabArgs a) {
     CHS_TILE_LOOP(tile, ntiles) {
         const int row0 = tile * LINES;
         const size_t goff = (size_t)row0 * N;
+        if (MODE == S_YFWD || MODE == S_YSTEP) {
+            // y pass: rows are x-slots, the row index runs over y.  Forward DCT, then (S_YSTEP) the
+            // spectral update against hat_U' and the inverse DCT without leaving the tile.
+            constexpr int CM = (MODE == S_YFWD) ? COL_FWD : COL_STEP;
+            row_tile_load_phys<N>(sm, a.src + goff, tid);
+            double lam1 = 0, lam2 = 0, lamx = 0, gxs = 0;
+            if (MODE == S_YSTEP) {
+                const double* hp = a.H + goff;                        // consumed mid-tile: pull into L2 now
+                for (int i = tid * 16; i < N * LINES; i += NT * 16) CHS_PREFETCH_L2(hp + i);
+                const double delx2 = a.S->p.delx * a.S->p.delx;
+                lam1 = a.S->delt_coef / delx2;                        // utils.py:41-42
+                lam2 = a.S->p.kappa_tilde * lam1 / delx2;
+                const int kx = a.kof[a.row_base + row0 + l];
+                lamx = a.lam[kx];
+                gxs = a.gsin[kx];
+            }
+            __syncthreads();
+            fft_fwd_range<N, 0, NST - 1>(scl, t, a.tw);
+            int rho_a, rho_b, base_a, base_b;
+            unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
+            double ar[8], ai[8], br[8], bi[8];
+            load_block<N>(scl, base_a, ar, ai);
+            load_block<N>(scl, base_b, br, bi);
+            dft<8, false>(ar, ai);
+            dft<8, false>(br, bi);
+            ColMid<N, CM> mid;
+            mid.om = a.om; mid.lam = a.lam; mid.gsin = a.gsin;
+            mid.hstride = 1;
+            mid.hat = a.H + goff + (size_t)l * N;
+            mid.hat_in = mid.hat;
+            mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
+            for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, mid);
+            if (MODE == S_YSTEP) {
+                dft<8, true>(ar, ai);
+                dft<8, true>(br, bi);
+                store_block<N>(scl, base_a, ar, ai);
+                store_block<N>(scl, base_b, br, bi);
+                const double v[1] = {mid.ge};
+                reduce_stage<1>(v, sm + G::OFF_RED, tid);
+                __syncthreads();
+                fft_inv_range<N, 0, NST - 1>(scl, t, a.tw);
+                if (tid == 0) {
+                    double s1[1];
+                    reduce_final<1>(s1, sm + G::OFF_RED, NT);
+                    a.part_ge[tile] = s1[0];
+                }
+                row_tile_store_phys<N>(sm, a.dst + goff, tid);
+            }
+        } else {
         if (MODE == S_INV || MODE == S_STEP) row_tile_load_slots_async<N>(sc, a.src + goff, tid);
         else row_tile_load_phys<N>(sm, a.src + goff, tid);
         const bool ra_line = diag && (a.row_base + row0 + l == ra_row);
@@ -161,40 +216,10 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, 1) k_slab_row(SlabArgs a) {
             __syncthreads();
             row_tile_store_slots<N>(sc, a.dst + goff, tid);
         }
+        }
         __syncthreads();
     }
     chs_cp_async_wait_all();
-}
-
-// H[r][c] = (H + Seig * B)/CHeig for the local x-slot rows r (global slot slot_base + r) and all
-// y-slots c; accumulates the spectral gradient energy sum (g[kx] + g[ky]) H^2 per block.
-CHS_KERNEL void k_slab_update(double* H, const double* B, int rows, int N, int slot_base, const int* kof,
-                              const double* lam, const double* gsin, const Sim* S, double* part_ge) {
-    const double delx2 = S->p.delx * S->p.delx;
-    const double lam1 = S->delt_coef / delx2;
-    const double lam2 = S->p.kappa_tilde * lam1 / delx2;
-    double ge = 0;
-    const size_t total = (size_t)rows * N;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / N), c = (int)(i % N);
-        const int kx = kof[slot_base + r], ky = kof[c];
-        const double leig = lam[ky] + lam[kx];
-        const double Se = __dmul_rn(lam1, leig);
-        const double CH = __dadd_rn(1.0, __dmul_rn(__dmul_rn(lam2, leig), leig));
-        const double hu = __ddiv_rn(__dadd_rn(H[i], __dmul_rn(Se, B[i])), CH);
-        H[i] = hu;
-        ge += (gsin[kx] + gsin[ky]) * (hu * hu);
-    }
-    // block sum through shared memory (fixed order)
-    CHS_SMEM_DECL
-    double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);
-    red[threadIdx.x] = ge;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0;
-        for (unsigned j = 0; j < blockDim.x; ++j) s += red[j];
-        part_ge[blockIdx.x] = s;
-    }
 }
 
 // out[c][r] = in[r][c] for an R x C row-major block, through a 32x33 shared tile.

@@ -6,7 +6,7 @@ transpose.  With P ranks each rank owns R = N/P rows of U and R x-spectral rows 
 one CH step is (chs_slab.cuh):
 
     B = transpose(A)          local pack kernels + NCCL all-to-all over NVLink (P > 1)
-    B = rowDCT(B); H = (H + Seig*B)/CHeig; B = rowIDCT(H)
+    B = rowIDCT(H = (H + Seig*rowDCT(B))/CHeig)      one kernel
     A = transpose(B)          second all-to-all
     U, A = rowIDCT(A) -> physics, diagnostics -> rowDCT(mu)
     7 diagnostic sums: all-reduce (NCCL) -> device-side control kernel (TimeData row, stop test)
@@ -23,7 +23,7 @@ from . import _lib, utils
 
 
 class SlabEngine:
-    S_FWD, S_MU, S_INV, S_STEP = 0, 1, 2, 3
+    S_FWD, S_MU, S_INV, S_STEP, S_YFWD = 0, 1, 2, 3, 4
 
     def __init__(self, N, param_struct, rows_cap=1024, backend=None, device=None, world=None):
         from .solver import _CudaBackend
@@ -127,7 +127,7 @@ class SlabEngine:
         self._ck(lib.chs_slab_begin(h), "chs_slab_begin")
         self._row(self.S_FWD, self.U, self.A)            # x-transform of U
         self._transpose(self.A, self.B)
-        self._row(self.S_FWD, self.B, self.H)            # y-transform -> hat_U' (solver.py:159)
+        self._row(self.S_YFWD, self.B, self.H)           # y-transform -> hat_U' (solver.py:159)
         self._row(self.S_MU, self.U, self.A)             # mu(U) -> x-transform, ||mu||^2
         self._ck(lib.chs_slab_clear_yedge(h), "chs_slab_clear_yedge")
         self._ck(lib.chs_slab_reduce(h, self.R, 0), "chs_slab_reduce")
@@ -137,9 +137,8 @@ class SlabEngine:
     def _step(self, last):
         lib, h, be, R, N = self.lib, self._h, self.be, self.R, self.N
         self._transpose(self.A, self.B)
-        self._row(self.S_FWD, self.B, self.B)            # hat_mu'
+        # y pass in one kernel: hat_mu' = DCT(B); H = (H + Seig*hat_mu')/CHeig; B = IDCT(H)
         self._ck(lib.chs_slab_update(h, be.ptr(self.H), be.ptr(self.B), R, self.row_base), "chs_slab_update")
-        self._row(self.S_INV, self.H, self.B)
         self._transpose(self.B, self.A)
         self._row(self.S_STEP, self.A, self.A, diag=1)   # U_new stored, diagnostics, mu, x-transform
         esz = 8 * N

@@ -165,11 +165,13 @@ chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, int32_t row_b
                           void* workspace, int64_t workspace_bytes, const double* lambda_host, void* stream);
 void chs_slab_destroy(chs_slab*);
 /* mode 0: physical rows -> row DCT-II (slot order); 1: U rows -> mu -> row DCT-II; 2: row DCT-III ->
- * physical rows; 3: row DCT-III -> U (stored in the handle's U buffer) -> diagnostics + mu -> row DCT-II */
+ * physical rows; 3: row DCT-III -> U (stored in the handle's U buffer) -> diagnostics + mu -> row DCT-II;
+ * 4: physical rows -> row DCT-II in natural frequency order (dst = hat_U' rows, solver.py:159) */
 int chs_slab_row(chs_slab*, int32_t mode, const double* src, double* dst, int32_t rows, int32_t row_base,
                  int32_t diag, double mean_u);
 int chs_slab_transpose(chs_slab*, const double* in, double* out, int32_t R, int32_t C, int32_t in_ld, int32_t out_ld);
-int chs_slab_update(chs_slab*, double* H, const double* B, int32_t rows, int32_t slot_base);   /* solver.py:201-206 */
+/* the y pass of one step in one kernel: H = (H + Seig*rowDCT(B))/CHeig; B = rowIDCT(H)  (solver.py:201-208) */
+int chs_slab_update(chs_slab*, double* H, double* B, int32_t rows, int32_t slot_base);
 int chs_slab_yedge(chs_slab*, const double* row_a, const double* row_b, int32_t accumulate);
 int chs_slab_clear_yedge(chs_slab*);
 int chs_slab_reduce(chs_slab*, int32_t rows, int32_t with_update);    /* local sums -> chs_slab_vec() */

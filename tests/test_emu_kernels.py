@@ -189,5 +189,20 @@ def test_slab_row_kernels_large_rows(be, N):
         d = 1 - 2 * u
         mu = np.log(u / (1 - u)) - 1 + (1 + d) * d - 2 * u * (1 - u)                     # unit_params: RT=BRT=A0=A1=1
         assert np.abs(be.download(D) - fp.dct(mu, axis=1, norm="ortho")[:, kof]).max() < 1e-11
+        # y pass: natural-order forward transform, then the fused DCT -> spectral update -> IDCT
+        H = be.empty((R, N))
+        assert lib.chs_slab_row(h, 4, be.ptr(B), be.ptr(H), R, 0, 0, 0.0) == 0          # S_YFWD (B holds u)
+        assert np.abs(be.download(H) - ref).max() < 1e-12
+        w = np.random.default_rng(N + 1).random((R, N)) - 0.5
+        be.upload(B, w)
+        slot_base = 8
+        assert lib.chs_slab_update(h, be.ptr(H), be.ptr(B), R, slot_base) == 0
+        delx2 = (2 / (N - 1)) ** 2
+        lam1 = 1e-8 / delx2
+        lam2 = lam1 / delx2
+        leig = lam[None, :] + lam[kof[slot_base:slot_base + R]][:, None]
+        Hn = (ref + lam1 * leig * fp.dct(w, axis=1, norm="ortho")) / (1 + lam2 * leig ** 2)
+        assert np.abs(be.download(H) - Hn).max() < 1e-12 * np.abs(Hn).max()
+        assert np.abs(be.download(B) - fp.idct(Hn, axis=1, norm="ortho")).max() < 1e-12
     finally:
         lib.chs_slab_destroy(h)
