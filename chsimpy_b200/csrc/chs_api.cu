@@ -654,7 +654,7 @@ struct chs_slab {
 };
 static const int SLAB_UPD_BLOCKS = 1184, SLAB_PREP_BLOCKS = 1184;
 
-static int slab_lines(int N) { return N <= 2048 ? CHS_LINES : 16384 / N; }
+static int slab_lines(int N) { return geo_lines(N); }
 
 struct SlabLayout { size_t sim, part, part_ge, yedge, vec, tw, om, lam, gsin, kof, logtab, total; };
 static SlabLayout slab_layout(int N, int rows) {

@@ -43,7 +43,7 @@ struct SlabArgs {
 };
 
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT, 1) k_slab_row(SlabArgs a) {
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs a) {
     using G = Geo<N>;
     constexpr int M = G::M, LPC = G::LPC, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;

@@ -41,24 +41,31 @@ struct Rad {
 #ifndef CHS_LINES
 #define CHS_LINES 8
 #endif
+CHS_CX constexpr int geo_lines(int N) { return N <= 1024 ? CHS_LINES : 1; }   // lines (rows / columns) per tile
 
 template <int N_>
 struct Geo {
     static constexpr int N = N_;
     static constexpr int M = N / 2;
-    // 8 lines per tile up to N = 2048; larger rows shrink the tile so that it still fits in
-    // shared memory (only the row kernels of the slab path are built for N > 1024)
-    static constexpr int LINES = (N <= 2048) ? CHS_LINES : (16384 / N);
+    // 8 lines per tile up to N = 1024 (the batched kernels); the long rows of the slab path
+    // (N >= 2048, row kernels only) use ONE line per CTA of M/16 threads, so that several CTAs
+    // are resident per SM and overlap each other's load / transform / store phases
+    static constexpr int LINES = geo_lines(N);
     // Two tile layouts (complex point c of line l, in double2 units):
-    //   point-major (N <= 2048): c*LPC + l, the lines of a point adjacent (they are the lanes of
+    //   point-major (N <= 1024): c*LPC + l, the lines of a point adjacent (they are the lanes of
     //     a warp), odd pitch for the transposing tile I/O;
-    //   line-major (N >= 4096, <= 4 lines): l*LOFF + c + pad(c), every warp works on ONE line so
-    //     that its 16-byte accesses are contiguous; pad() skews the 8-point blocks of the fused
-    //     last stage (block positions of consecutive residues are M/8 or M/16 apart) over the
-    //     banks.  pad is additive over the strides the stages use, see step().
-    static constexpr bool LINE_MAJOR = (LINES <= 4);
+    //   line-major (N >= 2048): l*LOFF + c + pad(c), every warp works on ONE line so that its
+    //     16-byte accesses are contiguous; pad() skews the 8-point blocks of the fused last stage
+    //     (the blocks of 8 consecutive residues lie M/8, M/16, ... apart: the top digits of the
+    //     position) over the banks.  pad is additive over the strides the stages use, see step().
+    static constexpr bool LINE_MAJOR = (N >= 2048);
     static constexpr int LPC = LINE_MAJOR ? 1 : LINES + 1;     // point pitch
-    static constexpr int SH1 = 9, SH2 = (M == 2048) ? 6 : ((M == 8192) ? 12 : 30), W2 = (M == 4096) ? 0 : 4;
+    // first radix 8: the top 3 position bits; 4: top 2 bits + the low bit of the next digit (x4);
+    // 2: the low 2 bits of the second digit + the top bit (x4)
+    static constexpr int LG = ilog2c(M), REM = LG % 3;
+    static constexpr int SH1 = (REM == 0) ? LG - 3 : ((REM == 1) ? LG - 4 : LG - 2);
+    static constexpr int SH2 = (REM == 0) ? 30 : ((REM == 1) ? LG - 1 : LG - 5);
+    static constexpr int W2 = (REM == 0) ? 0 : 4;
     CHS_CX static constexpr int pad(int c) { return LINE_MAJOR ? (c >> SH1) + W2 * (c >> SH2) : 0; }
     CHS_CX static constexpr int idx(int c) { return LINE_MAJOR ? c + pad(c) : c * LPC; }
     // idx(base + q*st) = idx(base) + q*step(st) for the points of one butterfly
