@@ -5,7 +5,9 @@ Every transform pass of the stepper works on contiguous rows; the change of dire
 transpose.  With P ranks each rank owns R = N/P rows of U and R x-spectral rows of hat_U and
 one CH step is (chs_slab.cuh):
 
-    B = transpose(A)          local pack kernels + NCCL all-to-all over NVLink (P > 1)
+    B = transpose(A)          P > 1: tiled transposes that write straight into the peer ranks'
+                              buffers over NVLink (symmetric memory) + a device-side barrier;
+                              NCCL all-to-all with pack/unpack when peer mapping is unavailable
     B = rowIDCT(H = (H + Seig*rowDCT(B))/CHeig)      one kernel
     A = transpose(B)          second all-to-all
     U, A = rowIDCT(A) -> physics, diagnostics -> rowDCT(mu)
@@ -16,6 +18,7 @@ No host synchronisation happens inside a chunk of steps; the host polls the stop
 `BatchStepper` (batch of one), so `Solver` drives either.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -43,14 +46,18 @@ class SlabEngine:
         self.batch, self.rows_cap = 1, int(rows_cap)
         n = self.N
         self.U = self.be.empty((R, n))
-        self.A = self.be.empty((R, n))
-        self.B = self.be.empty((R, n))
         self.H = self.be.empty((R, n))
         self.Uh = None                                   # [R+2][N] halo copy, prepare() only
         self.rows = self.be.empty((self.rows_cap, 9))
-        if self.P > 1:
-            self.send = self.be.empty((self.P, R, R))
-            self.recv = self.be.empty((self.P, R, R))
+        self._peer = None                                # peer-mapped base pointers of the A|B exchange buffer
+        if self.P > 1 and os.environ.get("CHS_SLAB_P2P", "1") != "0":
+            self._setup_peer_buffers()
+        if self._peer is None:
+            self.A = self.be.empty((R, n))
+            self.B = self.be.empty((R, n))
+            if self.P > 1:
+                self.send = self.be.empty((self.P, R, R))
+                self.recv = self.be.empty((self.P, R, R))
         wbytes = lib.chs_slab_workspace_bytes(n, R)
         self.work = self.be.empty((wbytes,), "u1")
         lam = np.ascontiguousarray(utils.laplace_spectrum_1d(n), dtype=np.float64)
@@ -69,6 +76,31 @@ class SlabEngine:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self.lib.chs_slab_destroy(h)
+
+    def _setup_peer_buffers(self):
+        """A and B live in one symmetric allocation that every rank of the box maps (NVLink peer
+        memory, torch.distributed._symmetric_memory): the transposes then WRITE their blocks
+        straight into the destination rank's buffer -- no pack buffer, no all-to-all, no unpack."""
+        try:
+            import torch
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            ab = symm.empty((2, self.R, self.N), dtype=torch.float64, device=self.U.device)
+            hdl = symm.rendezvous(ab, dist.group.WORLD)
+            peers = [int(x) for x in hdl.buffer_ptrs]
+            if len(peers) != self.P or int(hdl.rank) != self.rank:
+                raise RuntimeError("unexpected symmetric-memory group")
+            off = int(getattr(hdl, "offset", 0) or 0)
+            self._ab, self._hdl = ab, hdl
+            self.A, self.B = ab[0], ab[1]
+            self._peer = [x + off for x in peers]
+            self._ab_base = self.be.ptr(ab)
+            hdl.barrier()
+        except Exception as e:                           # noqa: BLE001 -- any failure: NCCL all-to-all path
+            if self.rank == 0:
+                print(f"[chsimpy_b200.slab] peer-memory transposes unavailable ({type(e).__name__}: {e}); "
+                      f"using NCCL all-to-all", flush=True)
+            self._peer = None
 
     # -- helpers ----------------------------------------------------------------------------
     def _ck(self, rc, what):
@@ -89,8 +121,20 @@ class SlabEngine:
         if P == 1:
             self._ck(lib.chs_slab_transpose(h, be.ptr(src), be.ptr(dst), N, N, N, N), "chs_slab_transpose")
             return
-        import torch.distributed as dist
         esz = 8
+        if self._peer is not None:
+            # out_p[c_local][rank*R + r_local] = src[r_local][p*R + c_local], written over NVLink into
+            # rank p's copy of dst; the barrier orders all ranks' writes before anybody reads dst (and,
+            # one transpose later, everybody's reads of src before it is overwritten remotely)
+            doff = be.ptr(dst) - self._ab_base
+            for i in range(P):
+                p = (self.rank + i) % P                  # start with the local block, spread the link load
+                self._ck(lib.chs_slab_transpose(h, be.ptr(src) + p * R * esz,
+                                                self._peer[p] + doff + self.rank * R * esz, R, R, N, N),
+                         "chs_slab_transpose")
+            self._hdl.barrier()
+            return
+        import torch.distributed as dist
         for p in range(P):                               # block p of my rows, transposed, goes to rank p
             self._ck(lib.chs_slab_transpose(h, be.ptr(src) + p * R * esz, be.ptr(self.send) + p * R * R * esz,
                                             R, R, N, R), "chs_slab_transpose")
@@ -133,6 +177,8 @@ class SlabEngine:
         self._ck(lib.chs_slab_reduce(h, self.R, 0), "chs_slab_reduce")
         self._allreduce_vec()
         self._ck(lib.chs_slab_control(h, 0, 0), "chs_slab_control")
+        if self._peer is not None:
+            self._hdl.barrier()                          # every rank is done reading B before step 1 writes it
 
     def _step(self, last):
         lib, h, be, R, N = self.lib, self._h, self.be, self.R, self.N
