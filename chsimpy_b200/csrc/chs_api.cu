@@ -777,13 +777,22 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
 extern "C" void chs_slab_destroy(chs_slab* s) { delete s; }
 extern "C" double* chs_slab_vec(chs_slab* s) { return s ? s->vec : nullptr; }
 extern "C" int64_t chs_slab_launch_count(const chs_slab* s) { return s ? s->launches : 0; }
+extern "C" int chs_slab_set_stream(chs_slab* s, void* stream) {
+    if (!s) return fail("chs_slab_set_stream: null handle");
+    s->stream = (cudaStream_t)stream;
+    return 0;
+}
 
 template <int N>
 static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int rows, int row_base, int diag, double mean_u,
                     double* H = nullptr) {
     using G = Geo<N>;
     SlabArgs a;
-    a.src = src; a.dst = dst; a.Uout = s->U; a.rows = rows; a.row_base = row_base; a.diag = diag; a.mean_u = mean_u;
+    // a launch may cover a sub-range of the rank's rows (pipelined exchange): row_base is global
+    const int local0 = row_base - s->row_base;
+    if (local0 < 0 || local0 % G::LINES || local0 + rows > s->rows) return fail("chs_slab_row: rows outside the slab");
+    a.src = src; a.dst = dst; a.Uout = s->U + (size_t)local0 * N; a.rows = rows; a.row_base = row_base; a.diag = diag; a.mean_u = mean_u;
+    a.tile0 = local0 / G::LINES; a.tiles_total = s->rows / G::LINES;
     a.part = s->part; a.S = s->sim; a.tw = s->tw; a.om = s->om; a.logtab = s->logtab;
     a.H = H; a.part_ge = s->part_ge; a.lam = s->lam; a.gsin = s->gsin; a.kof = s->kof;
     const int ntiles = rows / G::LINES;
@@ -838,7 +847,7 @@ extern "C" int chs_slab_update(chs_slab* s, double* H, double* B, int32_t rows, 
 #define CALL(NN) if (slab_row<NN>(s, S_YSTEP, B, B, rows, slot_base, 0, 0.0, H)) return -1;
     CHS_FOR_SLAB_N(s->N, CALL)
 #undef CALL
-    s->upd_used = rows / slab_lines(s->N);
+    s->upd_used = s->rows / slab_lines(s->N);
     return 0;
 }
 

@@ -26,7 +26,8 @@ struct SlabArgs {
     const double* src;
     double* dst;
     double* Uout;               // S_STEP: U_new rows are stored here
-    int rows;                   // local rows (multiple of LINES)
+    int rows;                   // rows of this launch (multiple of LINES)
+    int tile0, tiles_total;     // position of the launch's first tile among the rank's tiles (partial sums)
     int row_base;               // global index of local row 0
     int diag;                   // S_MU / S_STEP: accumulate the diagnostics of the field
     double mean_u;              // conserved mean of U (PS)
@@ -107,7 +108,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                 if (tid == 0) {
                     double s1[1];
                     reduce_final<1>(s1, sm + G::OFF_RED, NT);
-                    a.part_ge[tile] = s1[0];
+                    a.part_ge[a.tile0 + tile] = s1[0];
                 }
                 row_tile_store_phys<N>(sm, a.dst + goff, tid);
             }
@@ -175,7 +176,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                 if (tid == 0) {
                     double s4[4];
                     reduce_final<4>(s4, sm + G::OFF_RED, NT);
-                    double* pp = a.part + tile;
+                    double* pp = a.part + a.tile0 + tile;
+                    const int nt_all = a.tiles_total;
                     double e = 0, ra = 0;
                     if (diag) {
                         for (int l2 = 0; l2 < LINES; ++l2) {
@@ -187,13 +189,13 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                             ra /= (double)N;
                         }
                     }
-                    pp[R_GE * ntiles] = 0;
-                    pp[R_EDGE * ntiles] = 0.75 * e;
-                    pp[R_F * ntiles] = s4[0];
-                    pp[R_ABS * ntiles] = s4[1];
-                    pp[R_MU2 * ntiles] = s4[2];
-                    pp[R_CNT * ntiles] = s4[3];
-                    pp[R_RA * ntiles] = ra;
+                    pp[R_GE * nt_all] = 0;
+                    pp[R_EDGE * nt_all] = 0.75 * e;
+                    pp[R_F * nt_all] = s4[0];
+                    pp[R_ABS * nt_all] = s4[1];
+                    pp[R_MU2 * nt_all] = s4[2];
+                    pp[R_CNT * nt_all] = s4[3];
+                    pp[R_RA * nt_all] = ra;
                 }
             } else {
                 fft_stage<N, 0, false>(scl, t, a.tw);

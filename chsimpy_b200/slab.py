@@ -5,12 +5,14 @@ Every transform pass of the stepper works on contiguous rows; the change of dire
 transpose.  With P ranks each rank owns R = N/P rows of U and R x-spectral rows of hat_U and
 one CH step is (chs_slab.cuh):
 
-    B = transpose(A)          P > 1: tiled transposes that write straight into the peer ranks'
-                              buffers over NVLink (symmetric memory) + a device-side barrier;
-                              NCCL all-to-all with pack/unpack when peer mapping is unavailable
-    B = rowIDCT(H = (H + Seig*rowDCT(B))/CHeig)      one kernel
-    A = transpose(B)          second all-to-all
+    B = rowIDCT(H = (H + Seig*rowDCT(B))/CHeig)      one kernel (B = transpose(A) of the last step)
+    A = transpose(B)          P > 1: tiled transposes that write straight into the peer ranks'
+                              buffers over NVLink (symmetric memory) + a device-side barrier
+                              (optionally per row chunk on a second stream, CHS_SLAB_CHUNKS > 1:
+                              measured no gain, the row kernels fill the GPU); NCCL all-to-all
+                              with pack/unpack when peer mapping is unavailable
     U, A = rowIDCT(A) -> physics, diagnostics -> rowDCT(mu)
+    B = transpose(A)          same exchange, for the next step
     7 diagnostic sums: all-reduce (NCCL) -> device-side control kernel (TimeData row, stop test)
 
 No host synchronisation happens inside a chunk of steps; the host polls the stop flag every
@@ -50,6 +52,8 @@ class SlabEngine:
         self.Uh = None                                   # [R+2][N] halo copy, prepare() only
         self.rows = self.be.empty((self.rows_cap, 9))
         self._peer = None                                # peer-mapped base pointers of the A|B exchange buffer
+        self._nchunks = 1
+        self._main = self._side = None
         if self.P > 1 and os.environ.get("CHS_SLAB_P2P", "1") != "0":
             self._setup_peer_buffers()
         if self._peer is None:
@@ -96,11 +100,20 @@ class SlabEngine:
             self._peer = [x + off for x in peers]
             self._ab_base = self.be.ptr(ab)
             hdl.barrier()
+            n = int(os.environ.get("CHS_SLAB_CHUNKS", "1"))   # measured on 2 GPUs, N=8192: 1.59 / 1.67 / 1.66 ms for 1 / 2 / 4
+            gran = self.lib.chs_slab_row_granularity(self.N)
+            if n > 1 and self.R % (n * gran) == 0 and self.R // n >= 64:
+                self._nchunks = n
+                self._main = torch.cuda.current_stream()
+                self._side = torch.cuda.Stream()
+                self._ev = [torch.cuda.Event() for _ in range(n)]
+                self._ev_done = torch.cuda.Event()
         except Exception as e:                           # noqa: BLE001 -- any failure: NCCL all-to-all path
             if self.rank == 0:
                 print(f"[chsimpy_b200.slab] peer-memory transposes unavailable ({type(e).__name__}: {e}); "
                       f"using NCCL all-to-all", flush=True)
             self._peer = None
+            self._nchunks = 1
 
     # -- helpers ----------------------------------------------------------------------------
     def _ck(self, rc, what):
@@ -115,32 +128,66 @@ class SlabEngine:
             import torch.distributed as dist
             dist.all_reduce(self._vec)                  # 7 doubles, NCCL; identical on every rank
 
-    def _transpose(self, src, dst):
-        """dst[c_local][r_global] = src[r_local][c_global] (works in both directions)."""
+    def _transpose(self, src, dst, r0=0, rc=None, sync=True):
+        """dst[c_local][r_global] = src[r_local][c_global] for the local rows r0 .. r0+rc (works in
+        both directions).  P > 1: the block for rank p is written into p's buffer; with `sync` a
+        cross-rank barrier follows (all writes have landed, all reads of the old dst are over)."""
         lib, h, be, R, N, P = self.lib, self._h, self.be, self.R, self.N, self.P
-        if P == 1:
-            self._ck(lib.chs_slab_transpose(h, be.ptr(src), be.ptr(dst), N, N, N, N), "chs_slab_transpose")
-            return
+        rc = R if rc is None else rc
         esz = 8
+        if P == 1:
+            self._ck(lib.chs_slab_transpose(h, be.ptr(src) + r0 * N * esz, be.ptr(dst) + r0 * esz, rc, N, N, N),
+                     "chs_slab_transpose")
+            return
         if self._peer is not None:
-            # out_p[c_local][rank*R + r_local] = src[r_local][p*R + c_local], written over NVLink into
-            # rank p's copy of dst; the barrier orders all ranks' writes before anybody reads dst (and,
-            # one transpose later, everybody's reads of src before it is overwritten remotely)
+            # out_p[c_local][rank*R + r_local] = src[r_local][p*R + c_local], over NVLink into rank p's dst
             doff = be.ptr(dst) - self._ab_base
             for i in range(P):
                 p = (self.rank + i) % P                  # start with the local block, spread the link load
-                self._ck(lib.chs_slab_transpose(h, be.ptr(src) + p * R * esz,
-                                                self._peer[p] + doff + self.rank * R * esz, R, R, N, N),
+                self._ck(lib.chs_slab_transpose(h, be.ptr(src) + (r0 * N + p * R) * esz,
+                                                self._peer[p] + doff + (self.rank * R + r0) * esz, rc, R, N, N),
                          "chs_slab_transpose")
-            self._hdl.barrier()
+            if sync:
+                self._hdl.barrier()
             return
         import torch.distributed as dist
+        assert r0 == 0 and rc == R
         for p in range(P):                               # block p of my rows, transposed, goes to rank p
             self._ck(lib.chs_slab_transpose(h, be.ptr(src) + p * R * esz, be.ptr(self.send) + p * R * R * esz,
                                             R, R, N, R), "chs_slab_transpose")
         dist.all_to_all_single(self.recv, self.send)     # NCCL over NVLink / NVSwitch
         # recv[q] = [c_local][r_local of rank q]  ->  dst[c_local][q*R + r_local]
         dst.view(R, P, R).copy_(self.recv.permute(1, 0, 2))
+
+    def _chunks(self):
+        """Row chunks of the pipelined exchange (peer-memory path): the transposes of chunk k run
+        on a second stream while chunk k+1 is transformed."""
+        n = self._nchunks
+        rc = self.R // n
+        return [(k * rc, rc) for k in range(n)]
+
+    def _pass(self, compute, src, dst):
+        """One direction of a step: compute(r0, rc) on every row chunk of `src`, each followed by its
+        transposes into `dst` (on the side stream when pipelined), then the exchange barrier."""
+        if self._nchunks == 1:
+            compute(0, self.R)
+            self._transpose(src, dst)
+            return
+        main, side = self._main, self._side
+        for k, (r0, rc) in enumerate(self._chunks()):
+            compute(r0, rc)
+            if side is None:                             # one stream (single rank): chunked, not overlapped
+                self._transpose(src, dst, r0, rc, sync=False)
+                continue
+            self._ev[k].record(main)
+            side.wait_event(self._ev[k])
+            self._ck(self.lib.chs_slab_set_stream(self._h, side.cuda_stream), "chs_slab_set_stream")
+            self._transpose(src, dst, r0, rc, sync=False)
+            self._ck(self.lib.chs_slab_set_stream(self._h, main.cuda_stream), "chs_slab_set_stream")
+        if side is not None:
+            self._ev_done.record(side)
+            main.wait_event(self._ev_done)
+            self._hdl.barrier()
 
     # -- BatchStepper interface -------------------------------------------------------------
     def set_U(self, U):
@@ -178,16 +225,23 @@ class SlabEngine:
         self._allreduce_vec()
         self._ck(lib.chs_slab_control(h, 0, 0), "chs_slab_control")
         if self._peer is not None:
-            self._hdl.barrier()                          # every rank is done reading B before step 1 writes it
+            self._hdl.barrier()                          # every rank is done reading B before it is rewritten
+        self._transpose(self.A, self.B)                  # every step starts from B = transpose(A)
 
     def _step(self, last):
         lib, h, be, R, N = self.lib, self._h, self.be, self.R, self.N
-        self._transpose(self.A, self.B)
-        # y pass in one kernel: hat_mu' = DCT(B); H = (H + Seig*hat_mu')/CHeig; B = IDCT(H)
-        self._ck(lib.chs_slab_update(h, be.ptr(self.H), be.ptr(self.B), R, self.row_base), "chs_slab_update")
-        self._transpose(self.B, self.A)
-        self._row(self.S_STEP, self.A, self.A, diag=1)   # U_new stored, diagnostics, mu, x-transform
         esz = 8 * N
+
+        def y_pass(r0, rc):      # hat_mu' = DCT(B); H = (H + Seig*hat_mu')/CHeig; B = IDCT(H): one kernel
+            self._ck(lib.chs_slab_update(h, be.ptr(self.H) + r0 * esz, be.ptr(self.B) + r0 * esz, rc,
+                                         self.row_base + r0), "chs_slab_update")
+
+        def x_pass(r0, rc):      # U_new stored, diagnostics, mu, x-transform
+            self._ck(lib.chs_slab_row(h, self.S_STEP, be.ptr(self.A) + r0 * esz, be.ptr(self.A) + r0 * esz, rc,
+                                      self.row_base + r0, 1, float(self._mean)), "chs_slab_row")
+
+        self._pass(y_pass, self.B, self.A)
+        self._pass(x_pass, self.A, self.B)               # B for the next step (its barrier also covers the sums)
         acc = 0
         if self.rank == 0:
             self._ck(lib.chs_slab_yedge(h, be.ptr(self.U), be.ptr(self.U) + esz, 0), "chs_slab_yedge")

@@ -183,6 +183,9 @@ int chs_slab_rewind_rows(chs_slab*);
 int chs_slab_get_state(chs_slab*, chs_state*, int64_t* rows_written, int32_t* halted);
 int chs_slab_set_state(chs_slab*, const chs_state*);
 int64_t chs_slab_launch_count(const chs_slab*);
+/* stream of the following launches (the pipelined exchange issues the transposes of a row chunk on a
+ * second stream while the next chunk is transformed) */
+int chs_slab_set_stream(chs_slab*, void* stream);
 
 const char* chs_last_error(void);
 int32_t chs_abi_version(void);

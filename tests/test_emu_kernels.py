@@ -100,6 +100,7 @@ def test_slab_path_emulated(be):
     assert isinstance(s._stepper, SlabEngine)
     s.prepare()
     s.solve_or_resume(8)
+    s._stepper._nchunks = 2                                      # row-chunked passes (the pipelined exchange's launches)
     sol = s.solve_or_resume(4)
     assert sol.computed_steps == 12
     rows, ref = sol.timedata.data(), z["rows"][:12]
@@ -170,32 +171,33 @@ def test_slab_row_kernels_large_rows(be, N):
     wbytes = lib.chs_slab_workspace_bytes(N, R)
     work = be.empty((wbytes,), "u1")
     lam = np.ascontiguousarray(ch.utils.laplace_spectrum_1d(N))
-    h = lib.chs_slab_create(0, N, R, 0, 1, 0, C.byref(ps), be.ptr(U), be.ptr(rows), 4, be.ptr(work), wbytes,
+    rb = 8                                                 # global index of the first local row
+    h = lib.chs_slab_create(0, N, R, rb, N // R, 0, C.byref(ps), be.ptr(U), be.ptr(rows), 4, be.ptr(work), wbytes,
                             lam.ctypes.data, be.stream_handle())
     assert h
     try:
         kof = slot_freqs(N)
         u = 0.85 + 0.1 * (np.random.default_rng(N).random((R, N)) - 0.5)
         be.upload(U, u)
-        assert lib.chs_slab_row(h, 0, be.ptr(U), be.ptr(A), R, 0, 0, 0.0) == 0          # S_FWD
+        assert lib.chs_slab_row(h, 0, be.ptr(U), be.ptr(A), R, rb, 0, 0.0) == 0          # S_FWD
         a = be.download(A)
         ref = fp.dct(u, axis=1, norm="ortho")
         assert np.abs(a - ref[:, kof]).max() < 1e-12
-        assert lib.chs_slab_row(h, 2, be.ptr(A), be.ptr(B), R, 0, 0, 0.0) == 0          # S_INV
+        assert lib.chs_slab_row(h, 2, be.ptr(A), be.ptr(B), R, rb, 0, 0.0) == 0          # S_INV
         assert np.abs(be.download(B) - u).max() < 1e-13
         be.upload(U, np.zeros((R, N)))
-        assert lib.chs_slab_row(h, 3, be.ptr(A), be.ptr(D), R, 0, 1, float(u.mean())) == 0   # S_STEP
+        assert lib.chs_slab_row(h, 3, be.ptr(A), be.ptr(D), R, rb, 1, float(u.mean())) == 0   # S_STEP
         assert np.abs(be.download(U) - u).max() < 1e-13                                 # the field it stores
         d = 1 - 2 * u
         mu = np.log(u / (1 - u)) - 1 + (1 + d) * d - 2 * u * (1 - u)                     # unit_params: RT=BRT=A0=A1=1
         assert np.abs(be.download(D) - fp.dct(mu, axis=1, norm="ortho")[:, kof]).max() < 1e-11
         # y pass: natural-order forward transform, then the fused DCT -> spectral update -> IDCT
         H = be.empty((R, N))
-        assert lib.chs_slab_row(h, 4, be.ptr(B), be.ptr(H), R, 0, 0, 0.0) == 0          # S_YFWD (B holds u)
+        assert lib.chs_slab_row(h, 4, be.ptr(B), be.ptr(H), R, rb, 0, 0.0) == 0          # S_YFWD (B holds u)
         assert np.abs(be.download(H) - ref).max() < 1e-12
         w = np.random.default_rng(N + 1).random((R, N)) - 0.5
         be.upload(B, w)
-        slot_base = 8
+        slot_base = rb
         assert lib.chs_slab_update(h, be.ptr(H), be.ptr(B), R, slot_base) == 0
         delx2 = (2 / (N - 1)) ** 2
         lam1 = 1e-8 / delx2
