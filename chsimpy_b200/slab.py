@@ -41,8 +41,6 @@ class SlabEngine:
         gran = lib.chs_slab_row_granularity(self.N)
         if self.N % self.P or (self.N // self.P) % gran or self.N // self.P < 2:
             raise ValueError(f"N={N} cannot be split into {self.P} slabs of a multiple of {gran} rows")
-        if self.P > 1 and self.be.name != "cuda":
-            raise ValueError("multi-rank slabs need CUDA + NCCL")
         self.R = R = self.N // self.P
         self.row_base = self.rank * R
         self.batch, self.rows_cap = 1, int(rows_cap)
@@ -54,7 +52,7 @@ class SlabEngine:
         self._peer = None                                # peer-mapped base pointers of the A|B exchange buffer
         self._nchunks = 1
         self._main = self._side = None
-        if self.P > 1 and os.environ.get("CHS_SLAB_P2P", "1") != "0":
+        if self.P > 1 and self.be.name == "cuda" and os.environ.get("CHS_SLAB_P2P", "1") != "0":
             self._setup_peer_buffers()
         if self._peer is None:
             self.A = self.be.empty((R, n))
@@ -72,7 +70,9 @@ class SlabEngine:
                                                        self.be.stream_handle()), "chs_slab_create")
         vec_ptr = lib.chs_slab_vec(self._h)
         off = vec_ptr - self.be.ptr(self.work)
-        self._vec = self.work[off:off + 56].view(self.be.torch.float64) if self.be.name == "cuda" else None
+        # the 7 rank-local sums as a tensor torch.distributed can all-reduce in place (NCCL on the
+        # device; the host-emulated test backend hands out numpy memory -> gloo)
+        self._vec = self._tensor(self.work[off:off + 56]).view(self._torch().float64)
         self._full = None
         self._mean = 0.0
 
@@ -116,6 +116,14 @@ class SlabEngine:
             self._nchunks = 1
 
     # -- helpers ----------------------------------------------------------------------------
+    def _torch(self):
+        import torch
+        return torch
+
+    def _tensor(self, x):
+        """Backend array -> torch tensor sharing its memory."""
+        return x if self.be.name == "cuda" else self._torch().from_numpy(x)
+
     def _ck(self, rc, what):
         return _lib.check(self.lib, rc, what)
 
@@ -155,9 +163,9 @@ class SlabEngine:
         for p in range(P):                               # block p of my rows, transposed, goes to rank p
             self._ck(lib.chs_slab_transpose(h, be.ptr(src) + p * R * esz, be.ptr(self.send) + p * R * R * esz,
                                             R, R, N, R), "chs_slab_transpose")
-        dist.all_to_all_single(self.recv, self.send)     # NCCL over NVLink / NVSwitch
+        dist.all_to_all_single(self._tensor(self.recv), self._tensor(self.send))     # NCCL over NVLink / NVSwitch
         # recv[q] = [c_local][r_local of rank q]  ->  dst[c_local][q*R + r_local]
-        dst.view(R, P, R).copy_(self.recv.permute(1, 0, 2))
+        self._tensor(dst).view(R, P, R).copy_(self._tensor(self.recv).permute(1, 0, 2))
 
     def _chunks(self):
         """Row chunks of the pipelined exchange (peer-memory path): the transposes of chunk k run
@@ -297,8 +305,9 @@ class SlabEngine:
             return self.be.download(self.U)
         import torch
         import torch.distributed as dist
-        parts = [torch.empty_like(self.U) for _ in range(self.P)]
-        dist.all_gather(parts, self.U)
+        mine = self._tensor(self.U)
+        parts = [torch.empty_like(mine) for _ in range(self.P)]
+        dist.all_gather(parts, mine)
         return torch.cat(parts, dim=0).cpu().numpy()
 
     def launch_count(self):
