@@ -153,8 +153,9 @@ int chs_get_timing(chs_solver*, double* ms3, int64_t* n_iters);
 /* ---------------------------------------------------------------------------------------
  * Slab path: ONE large N x N simulation, row-slab decomposed over `world` ranks (world = 1:
  * a single GPU), N in {64 .. 16384}.  Stage-level entry points; the host layer
- * (chsimpy_b200/slab.py) sequences them and performs the transposes (NCCL all-to-all for
- * world > 1) and the all-reduce of the 7 diagnostic sums.  Reference: the same loop body
+ * (chsimpy_b200/slab.py) sequences them; for world > 1 it calls chs_slab_transpose once per peer
+ * with `out` pointing INTO the peer's buffer (symmetric memory mapped over NVLink; NCCL all-to-all
+ * when peer mapping is unavailable) and all-reduces the 7 diagnostic sums.  Reference: the same loop body
  * chsimpy/solver.py:165-249; the reference has no counterpart for the decomposition. */
 typedef struct chs_slab chs_slab;
 int32_t chs_slab_supports_n(int32_t N);
