@@ -666,7 +666,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
 // Per-element physics on the 2*R real values of one radix-R butterfly of stage 0
 // (positions c_q = j + q*st, re = v[2c], im = v[2c+1]):  U -> mu in place, sums in acc.
 struct RowAcc {
-    double f, ab, mu2, cnt, ra;
+    double f, ab, mu2, ra;
+    int cnt;                     // values below the threshold (one FP64 compare + an integer add per value)
 };
 template <int N, int R>
 CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const chs_params& p, const double2* ltab,
@@ -686,7 +687,7 @@ CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const chs_params& 
             if (diag) {
                 acc.f += f;
                 acc.ab += fabs(u - meanU);
-                acc.cnt += (u < p.threshold) ? 1.0 : 0.0;
+                acc.cnt += (u < p.threshold) ? 1 : 0;
                 if (ra_line) acc.ra += fabs(u - ra_mean);
             }
             acc.mu2 += mu * mu;
@@ -734,7 +735,9 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
             halted = (MODE == ROW_STEP) ? S->halted : 0;
             const long long cs_next = S->computed_steps + (MODE == ROW_STEP ? 1 : 0);
             want_cols = S->p.adaptive_time && !a.last && cs_next > 500 && (cs_next % 2) == 0;
-            slow = want_cols || jit || (MODE == ROW_FWD_MU);
+            // the one tile per simulation that holds the Ra row also takes the unfused middle: Ra is
+            // summed from the field in shared memory, so the hot loop carries no per-value Ra work
+            slow = want_cols || jit || (MODE == ROW_FWD_MU) || ra_tile;
         }
         if (MODE == ROW_FWD_U || MODE == ROW_FWD_MU) {
             const double* src = (MODE == ROW_FWD_U && a.src) ? a.src : a.U;
@@ -788,7 +791,15 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                 if (control) {
                     const chs_params p = S->p;
                     const double meanU = hat00 / (double)N;                     // conserved mean (Q4)
-                    const double ra_mean = ra_line ? ra_scr[0] : 0.0;
+                    if (ra_line) {                                              // Ra = mean |U[r,:] - mean U[r,:]| (solver.py:226-227)
+                        const double ra_mean = ra_scr[0];
+                        double s = 0;
+                        for (int i = 0; i < 16; ++i) {
+                            const double2 v = scl[G::idx(t + i * TPL)];
+                            s += fabs(v.x - ra_mean) + fabs(v.y - ra_mean);
+                        }
+                        ra_scr[2 + t] = s;
+                    }
                     RowAcc acc = {0, 0, 0, 0, 0};
 #pragma unroll 1
                     for (int i = 0; i < NB0; ++i) {
@@ -813,7 +824,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                             }
                             dft<R0, true>(xr, xi);
                         }
-                        physics<N, R0>(xr, xi, j, p, ltab, diag, meanU, ra_line, ra_mean, acc, edge + 4 * l);
+                        physics<N, R0>(xr, xi, j, p, ltab, diag, meanU, false, 0.0, acc, edge + 4 * l);
                         if (!slow) {
                             dft<R0, false>(xr, xi);
 #pragma unroll
@@ -826,8 +837,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
 #pragma unroll
                         for (int q = 0; q < R0; ++q) scl[G::idx(j) + q * G::step(ST0)] = make_double2(xr[q], xi[q]);
                     }
-                    if (ra_line) ra_scr[2 + t] = acc.ra;
-                    const double v[4] = {acc.f, acc.ab, acc.mu2, acc.cnt};
+                    const double v[4] = {acc.f, acc.ab, acc.mu2, (double)acc.cnt};
                     reduce_stage<4>(v, sm + G::OFF_RED, tid);
                     __syncthreads();
                     if (tid == 0) {

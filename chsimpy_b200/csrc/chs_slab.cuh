@@ -170,7 +170,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                     for (int q = 0; q < R0; ++q) scl[G::idx(j) + q * G::step(ST0)] = make_double2(xr[q], xi[q]);
                 }
                 if (ra_line) ra_scr[2 + t] = acc.ra;
-                const double v[4] = {acc.f, acc.ab, acc.mu2, acc.cnt};
+                const double v[4] = {acc.f, acc.ab, acc.mu2, (double)acc.cnt};
                 reduce_stage<4>(v, sm + G::OFF_RED, tid);
                 __syncthreads();
                 if (tid == 0) {
