@@ -488,6 +488,9 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
     a.sim_index = s->index;                       // identity list until the first compaction
     a.nsims = s->n_running;
     const dim3 block(G::NT);
+    // programmatic dependent launch of the two step kernels (not while per-kernel events are recorded)
+    static const bool pdl_env = [] { const char* e = getenv("CHS_PDL"); return !e || atoi(e) != 0; }();
+    const bool pdl = pdl_env && !s->timing;
     if (s->n_running == s->batch) a.sim_index = nullptr;
     const dim3 grid(G::NTILES, s->n_running);
     const dim3 gcol = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, a.nsims), grow = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, a.nsims);
@@ -501,9 +504,11 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
             if (s->ev_used + 4 > 65536 && drain_events(s)) return -1;
             cudaEventRecord(next_event(s), s->stream);
         }
-        CHS_LAUNCH((k_col<N, COL_STEP>), gcol, block, G::SMEM_BYTES, s->stream, a);
+        if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP>), gcol, block, G::SMEM_BYTES, s->stream, a);
+        else CHS_LAUNCH((k_col<N, COL_STEP>), gcol, block, G::SMEM_BYTES, s->stream, a);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
-        CHS_LAUNCH((k_row<N, ROW_STEP>), grow, block, G::SMEM_BYTES, s->stream, a);
+        if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP>), grow, block, G::SMEM_BYTES, s->stream, a);
+        else CHS_LAUNCH((k_row<N, ROW_STEP>), grow, block, G::SMEM_BYTES, s->stream, a);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
         s->launches += 2;
         if (noise) {

@@ -654,6 +654,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
     using G = Geo<N>;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    CHS_PDL_TRIGGER();               // the next kernel of the stream may be scheduled from here on ...
+    CHS_PDL_WAIT();                  // ... and this one touches global memory only after its predecessor is complete
     const int total = G::NTILES * a.nsims;
     CHS_TILE_LOOP(w, total) {
         k_col_tile<N, MODE>(a, w, sm);
@@ -931,6 +933,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_row(KArgs a) {
     using G = Geo<N>;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    CHS_PDL_TRIGGER();               // the next kernel of the stream may be scheduled from here on ...
+    CHS_PDL_WAIT();                  // ... and this one touches global memory only after its predecessor is complete
     const int total = G::NTILES * a.nsims;
     CHS_TILE_LOOP(w, total) {
         k_row_tile<N, MODE>(a, w, sm);

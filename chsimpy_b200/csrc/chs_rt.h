@@ -16,6 +16,22 @@
 #define CHS_KERNEL __global__
 #define CHS_CX __host__ __device__
 #define CHS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is
+// still running; it must execute CHS_PDL_WAIT() before it touches anything the predecessor (or, by
+// transitivity, any earlier kernel) writes.  Hides the launch + scheduling latency between the two
+// dependent kernels of a step (matters for small batches, where a kernel runs for 15-20 us).
+#define CHS_LAUNCH_PDL(kern, grid_, block_, smem_, stream_, arg)                                      \
+    do {                                                                                           \
+        cudaLaunchConfig_t cfg_ = {};                                                              \
+        cfg_.gridDim = grid_; cfg_.blockDim = block_; cfg_.dynamicSmemBytes = smem_; cfg_.stream = stream_; \
+        cudaLaunchAttribute at_[1];                                                                \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
+        at_[0].val.programmaticStreamSerializationAllowed = 1;                                     \
+        cfg_.attrs = at_; cfg_.numAttrs = 1;                                                       \
+        cudaLaunchKernelEx(&cfg_, kern, arg);                                                      \
+    } while (0)
+#define CHS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define CHS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define CHS_SMEM_DECL extern __shared__ __align__(16) unsigned char chs_smem_raw[];
 #define CHS_SMEM_PTR (chs_smem_raw)
 // asynchronous global->shared copies (LDGSTS): no register staging, all of a tile in flight
