@@ -158,7 +158,11 @@ CHS_DEV double2* stage_logtab(double* sm, const double2* __restrict__ g, int tid
 // thermodynamics of one value (solver.py:166-175 and :218-221)
 CHS_DEV void thermo(double u, const chs_params& p, const double2* __restrict__ ltab, double& f, double& mu) {
     const double ui = 1.0 - u;
-    const double lu = fast_log(u, ltab), li = fast_log(ui, ltab);
+    double lu = fast_log_unchecked(u, ltab), li = fast_log_unchecked(ui, ltab);
+    if (log_needs_slow_path(u) || log_needs_slow_path(ui)) {      // one (never taken) branch for both logarithms
+        lu = slow_log(u);
+        li = slow_log(ui);
+    }
     const double d = ui - u;
     const double uui = u * ui;
     f = p.RT * (u * (lu - p.B) + ui * li) + (p.A0 + p.A1 * d) * uui;

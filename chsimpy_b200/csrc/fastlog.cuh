@@ -60,10 +60,13 @@ CHS_DEV double div_ge1(double a, double b) {
 #endif
 
 // tab: LOG_TABLE_N entries {invc, logc} (shared or global memory)
-CHS_DEV double fast_log(double x, const double2* __restrict__ tab) {
+// true for arguments the table scheme does not cover: <= 0, subnormal, inf, nan
+CHS_DEV bool log_needs_slow_path(double x) { return (unsigned)(chs_hiword(x) - 0x00100000) >= 0x7fe00000u; }
+
+// fast path only: the caller checks log_needs_slow_path() (garbage, but no trap, for such arguments)
+CHS_DEV double fast_log_unchecked(double x, const double2* __restrict__ tab) {
     // all bit manipulation on the high 32-bit word (sign, exponent, 20 mantissa bits)
     const int hx = chs_hiword(x);
-    if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u) return slow_log(x);   // <=0, subnormal, inf, nan
     const int tmp = hx - 0x3fe60000;                                  // LOG_OFF >> 32
     const int i = (tmp >> 13) & (LOG_TABLE_N - 1);
     const int k = tmp >> 20;                                          // arithmetic shift: floor
@@ -81,6 +84,11 @@ CHS_DEV double fast_log(double x, const double2* __restrict__ tab) {
     const double q = chs_fma(r, 1.0 / 3, -0.5);
     const double y = chs_fma(r2, chs_fma(r2, p, q), lo);
     return y + hi;
+}
+
+CHS_DEV double fast_log(double x, const double2* __restrict__ tab) {
+    if (log_needs_slow_path(x)) return slow_log(x);
+    return fast_log_unchecked(x, tab);
 }
 
 }  // namespace chs
