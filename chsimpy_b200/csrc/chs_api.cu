@@ -879,6 +879,21 @@ extern "C" int chs_slab_reduce(chs_slab* s, int32_t rows, int32_t with_update) {
     return 0;
 }
 
+// the sums of one step in a single launch: per-tile partials + spectral gradient energy + the y-edge
+// terms of the stored field (top_edge: this rank holds rows 0/1 of the domain, bottom_edge: rows N-2/N-1)
+extern "C" int chs_slab_sums(chs_slab* s, int32_t top_edge, int32_t bottom_edge) {
+    if (!s) return fail("chs_slab_sums: null handle");
+    const size_t n = (size_t)s->N;
+    const double* t0 = top_edge ? s->U : nullptr;
+    const double* b0 = bottom_edge ? s->U + (size_t)(s->rows - 2) * n : nullptr;
+    CHS_LAUNCH(k_slab_sums, dim3(1), dim3(128 * (R_NVAL + 1)), 128 * (R_NVAL + 1) * sizeof(double), s->stream,
+               (const double*)s->part, (int)(s->rows / slab_lines(s->N)), (const double*)s->part_ge, s->upd_used,
+               t0, t0 ? t0 + n : nullptr, b0, b0 ? b0 + n : nullptr, s->N, s->vec);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int chs_slab_prepare(chs_slab* s, const double* U_halo, double mean_u) {
     if (!s || !U_halo) return fail("chs_slab_prepare: bad argument");
 #ifdef CHS_EMU

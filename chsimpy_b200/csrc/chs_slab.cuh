@@ -157,7 +157,9 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                         const double2 v = scl[G::idx(j) + q * G::step(ST0)];
                         xr[q] = v.x; xi[q] = v.y;
                     }
-                    physics<N, R0>(xr, xi, j, p, ltab, diag, a.mean_u, ra_line, ra_mean, acc, edge + 4 * l);
+                    // the Ra row is one row of the whole domain: keep its per-value work out of the common copy
+                    if (ra_line) physics<N, R0>(xr, xi, j, p, ltab, diag, a.mean_u, true, ra_mean, acc, edge + 4 * l);
+                    else physics<N, R0>(xr, xi, j, p, ltab, diag, a.mean_u, false, 0.0, acc, edge + 4 * l);
                     dft<R0, false>(xr, xi);
 #pragma unroll
                     for (int q = 1; q < R0; ++q) {
@@ -327,6 +329,36 @@ CHS_KERNEL void k_slab_reduce(const double* part, int ntiles, const double* part
         double t = 0;
         for (int j = 0; j < 32; ++j) t += red[v * 32 + j];
         if (v == R_EDGE) t += yedge[0];
+        vec[v] = t;
+    }
+}
+
+// k_slab_reduce + both k_slab_yedge calls of a step in ONE launch of 1024 threads: 7 groups of 128
+// lanes sum the per-tile partials (lane-strided, fixed order), the last 128 threads the y-edge
+// terms of the stored field (top: rows 0/1 of the domain, bottom: rows N-2/N-1; null = not mine).
+CHS_KERNEL void k_slab_sums(const double* part, int ntiles, const double* part_ge, int nge, const double* top0,
+                            const double* top1, const double* bot0, const double* bot1, int N, double* vec) {
+    CHS_SMEM_DECL
+    double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);      // (R_NVAL + 1) * 128
+    const int v = threadIdx.x / 128, lane = threadIdx.x % 128;
+    double s = 0;
+    if (v < R_NVAL) {
+        for (int i = lane; i < ntiles; i += 128) s += part[v * ntiles + i];
+        if (v == R_GE) for (int i = lane; i < nge; i += 128) s += part_ge[i];
+    } else {
+        if (top0) for (int x = lane; x < N; x += 128) { const double d = top1[x] - top0[x]; s += d * d; }
+        if (bot0) for (int x = lane; x < N; x += 128) { const double d = bot1[x] - bot0[x]; s += d * d; }
+    }
+    red[v * 128 + lane] = s;
+    __syncthreads();
+    if (v < R_NVAL && lane == 0) {
+        double t = 0;
+        for (int j = 0; j < 128; ++j) t += red[v * 128 + j];
+        if (v == R_EDGE) {
+            double e = 0;
+            for (int j = 0; j < 128; ++j) e += red[R_NVAL * 128 + j];
+            t += 0.75 * e;
+        }
         vec[v] = t;
     }
 }

@@ -250,17 +250,8 @@ class SlabEngine:
 
         self._pass(y_pass, self.B, self.A)
         self._pass(x_pass, self.A, self.B)               # B for the next step (its barrier also covers the sums)
-        acc = 0
-        if self.rank == 0:
-            self._ck(lib.chs_slab_yedge(h, be.ptr(self.U), be.ptr(self.U) + esz, 0), "chs_slab_yedge")
-            acc = 1
-        if self.rank == self.P - 1:
-            self._ck(lib.chs_slab_yedge(h, be.ptr(self.U) + (R - 2) * esz, be.ptr(self.U) + (R - 1) * esz, acc),
-                     "chs_slab_yedge")
-            acc = 1
-        if not acc:
-            self._ck(lib.chs_slab_clear_yedge(h), "chs_slab_clear_yedge")
-        self._ck(lib.chs_slab_reduce(h, R, 1), "chs_slab_reduce")
+        # per-tile partials + y-edge terms of the stored field -> the 7 local sums, one launch
+        self._ck(lib.chs_slab_sums(h, int(self.rank == 0), int(self.rank == self.P - 1)), "chs_slab_sums")
         self._allreduce_vec()
         self._ck(lib.chs_slab_control(h, int(bool(last)), 1), "chs_slab_control")
 

@@ -176,6 +176,9 @@ int chs_slab_update(chs_slab*, double* H, double* B, int32_t rows, int32_t slot_
 int chs_slab_yedge(chs_slab*, const double* row_a, const double* row_b, int32_t accumulate);
 int chs_slab_clear_yedge(chs_slab*);
 int chs_slab_reduce(chs_slab*, int32_t rows, int32_t with_update);    /* local sums -> chs_slab_vec() */
+/* reduce + both yedge calls of one step in a single launch (top_edge / bottom_edge: this rank holds rows
+ * 0,1 / N-2,N-1 of the domain) */
+int chs_slab_sums(chs_slab*, int32_t top_edge, int32_t bottom_edge);
 double* chs_slab_vec(chs_slab*);                                      /* device pointer, 7 doubles */
 int chs_slab_prepare(chs_slab*, const double* U_with_halo /*[rows+2][N]*/, double mean_u);   /* solver.py:84-127 */
 int chs_slab_control(chs_slab*, int32_t last, int32_t post);          /* solver.py:195-199, 230-249 */
