@@ -811,9 +811,9 @@ static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int r
         case S_FWD: CHS_LAUNCH((k_slab_row<N, S_FWD>), grid, block, G::SMEM_BYTES, s->stream, a); break;
         case S_MU: CHS_LAUNCH((k_slab_row<N, S_MU>), grid, block, G::SMEM_BYTES, s->stream, a); break;
         case S_INV: CHS_LAUNCH((k_slab_row<N, S_INV>), grid, block, G::SMEM_BYTES, s->stream, a); break;
-        case S_STEP: CHS_LAUNCH((k_slab_row<N, S_STEP>), grid, block, G::SMEM_BYTES, s->stream, a); break;
+        case S_STEP: CHS_LAUNCH_PDL((k_slab_row<N, S_STEP>), grid, block, G::SMEM_BYTES, s->stream, a); break;
         case S_YFWD: CHS_LAUNCH((k_slab_row<N, S_YFWD>), grid, block, G::SMEM_BYTES, s->stream, a); break;
-        case S_YSTEP: CHS_LAUNCH((k_slab_row<N, S_YSTEP>), grid, block, G::SMEM_BYTES, s->stream, a); break;
+        case S_YSTEP: CHS_LAUNCH_PDL((k_slab_row<N, S_YSTEP>), grid, block, G::SMEM_BYTES, s->stream, a); break;
         default: return fail("chs_slab_row: bad mode");
     }
     s->launches += 1;
@@ -837,7 +837,7 @@ extern "C" int chs_slab_row(chs_slab* s, int32_t mode, const double* src, double
 
 extern "C" int chs_slab_transpose(chs_slab* s, const double* in, double* out, int32_t R, int32_t C, int32_t in_ld, int32_t out_ld) {
     if (!s || !in || !out) return fail("chs_slab_transpose: bad argument");
-    CHS_LAUNCH(k_slab_transpose, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 32 * 33 * sizeof(double), s->stream,
+    CHS_LAUNCH_PDL(k_slab_transpose, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 32 * 33 * sizeof(double), s->stream,
                in, out, (int)R, (int)C, (int)in_ld, (int)out_ld);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());
@@ -886,7 +886,7 @@ extern "C" int chs_slab_sums(chs_slab* s, int32_t top_edge, int32_t bottom_edge)
     const size_t n = (size_t)s->N;
     const double* t0 = top_edge ? s->U : nullptr;
     const double* b0 = bottom_edge ? s->U + (size_t)(s->rows - 2) * n : nullptr;
-    CHS_LAUNCH(k_slab_sums, dim3(1), dim3(128 * (R_NVAL + 1)), 128 * (R_NVAL + 1) * sizeof(double), s->stream,
+    CHS_LAUNCH_PDL(k_slab_sums, dim3(1), dim3(128 * (R_NVAL + 1)), 128 * (R_NVAL + 1) * sizeof(double), s->stream,
                (const double*)s->part, (int)(s->rows / slab_lines(s->N)), (const double*)s->part_ge, s->upd_used,
                t0, t0 ? t0 + n : nullptr, b0, b0 ? b0 + n : nullptr, s->N, s->vec);
     s->launches += 1;
@@ -912,7 +912,7 @@ extern "C" int chs_slab_prepare(chs_slab* s, const double* U_halo, double mean_u
 // post: 0 prologue (only ||mu||^2 + pre part), 1 end of an iteration, 2 prepare (row 0)
 extern "C" int chs_slab_control(chs_slab* s, int32_t last, int32_t post) {
     if (!s) return fail("chs_slab_control: null handle");
-    CHS_LAUNCH(k_slab_control, dim3(1), dim3(32), 0, s->stream, s->sim, (const double*)s->vec, s->rowsbuf, s->rows_cap, s->N,
+    CHS_LAUNCH_PDL(k_slab_control, dim3(1), dim3(32), 0, s->stream, s->sim, (const double*)s->vec, s->rowsbuf, s->rows_cap, s->N,
                (int)last, (int)post);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());

@@ -20,7 +20,7 @@
 // still running; it must execute CHS_PDL_WAIT() before it touches anything the predecessor (or, by
 // transitivity, any earlier kernel) writes.  Hides the launch + scheduling latency between the two
 // dependent kernels of a step (matters for small batches, where a kernel runs for 15-20 us).
-#define CHS_LAUNCH_PDL(kern, grid_, block_, smem_, stream_, arg)                                      \
+#define CHS_LAUNCH_PDL(kern, grid_, block_, smem_, stream_, ...)                                      \
     do {                                                                                           \
         cudaLaunchConfig_t cfg_ = {};                                                              \
         cfg_.gridDim = grid_; cfg_.blockDim = block_; cfg_.dynamicSmemBytes = smem_; cfg_.stream = stream_; \
@@ -28,7 +28,7 @@
         at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                            \
         at_[0].val.programmaticStreamSerializationAllowed = 1;                                     \
         cfg_.attrs = at_; cfg_.numAttrs = 1;                                                       \
-        cudaLaunchKernelEx(&cfg_, kern, arg);                                                      \
+        cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__);                                                     \
     } while (0)
 #define CHS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define CHS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")

@@ -45,6 +45,8 @@ struct SlabArgs {
 
 template <int N, int MODE>
 CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs a) {
+    CHS_PDL_TRIGGER();
+    CHS_PDL_WAIT();               // programmatic dependent launch: nothing is read before the predecessor is complete
     using G = Geo<N>;
     constexpr int M = G::M, LPC = G::LPC, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
@@ -230,6 +232,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
 // in_ld / out_ld: leading dimensions; used for the local transpose (P = 1) and for the
 // per-peer blocks around the all-to-all (P > 1).
 CHS_KERNEL void k_slab_transpose(const double* in, double* out, int R, int C, int in_ld, int out_ld) {
+    CHS_PDL_TRIGGER();
+    CHS_PDL_WAIT();
     CHS_SMEM_DECL
     double* tile = reinterpret_cast<double*>(CHS_SMEM_PTR);       // 32*33 doubles
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
@@ -338,6 +342,8 @@ CHS_KERNEL void k_slab_reduce(const double* part, int ntiles, const double* part
 // terms of the stored field (top: rows 0/1 of the domain, bottom: rows N-2/N-1; null = not mine).
 CHS_KERNEL void k_slab_sums(const double* part, int ntiles, const double* part_ge, int nge, const double* top0,
                             const double* top1, const double* bot0, const double* bot1, int N, double* vec) {
+    CHS_PDL_TRIGGER();
+    CHS_PDL_WAIT();
     CHS_SMEM_DECL
     double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);      // (R_NVAL + 1) * 128
     const int v = threadIdx.x / 128, lane = threadIdx.x % 128;
@@ -366,6 +372,8 @@ CHS_KERNEL void k_slab_sums(const double* part, int ntiles, const double* part_g
 // step_control() of the tile path, fed with the rank-reduced sums (one thread; every rank runs
 // it on identical inputs and so keeps an identical Sim image).  post = 0: prologue.
 CHS_KERNEL void k_slab_control(Sim* S, const double* vec, double* rows, long long rows_cap, int N, int last, int post) {
+    CHS_PDL_TRIGGER();
+    CHS_PDL_WAIT();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const chs_params& p = S->p;
     if (post == 2) {                     // Solver.prepare(): row 0 (solver.py:117-135)

@@ -67,7 +67,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
 #define CHS_CX
 #define CHS_LAUNCH(kern, grid, block, smem, stream, ...) \
     emu::launch(grid, block, smem, [&] { kern(__VA_ARGS__); })
-#define CHS_LAUNCH_PDL(kern, grid, block, smem, stream, arg) CHS_LAUNCH(kern, grid, block, smem, stream, arg)
+#define CHS_LAUNCH_PDL(kern, grid, block, smem, stream, ...) CHS_LAUNCH(kern, grid, block, smem, stream, __VA_ARGS__)
 #define CHS_PDL_TRIGGER()
 #define CHS_PDL_WAIT()
 #define CHS_SMEM_DECL
