@@ -709,7 +709,7 @@ CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const chs_params& 
 template <int N, int MODE>
 CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
     using G = Geo<N>;
-    constexpr int M = G::M, LPC = G::LPC, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
+    constexpr int M = G::M, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
     constexpr int R0 = Rad<M>::radix(0), ST0 = M / R0, NB0 = 16 / R0;
     double2* sc = reinterpret_cast<double2*>(sm);

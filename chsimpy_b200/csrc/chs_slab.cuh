@@ -48,7 +48,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
     CHS_PDL_TRIGGER();
     CHS_PDL_WAIT();               // programmatic dependent launch: nothing is read before the predecessor is complete
     using G = Geo<N>;
-    constexpr int M = G::M, LPC = G::LPC, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
+    constexpr int M = G::M, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
     constexpr int R0 = Rad<M>::radix(0), ST0 = M / R0, NB0 = 16 / R0;
     CHS_SMEM_DECL

@@ -73,8 +73,7 @@ struct Geo {
     static constexpr int LOFF = LINE_MAJOR ? M + (M >> SH1) + W2 * (M >> SH2) : 1;              // line offset
     // every stage either strides by a multiple of a pad term's period or stays inside one period
     CHS_CX static constexpr bool pad_ok() {
-        if (!LINE_MAJOR) return true;
-        for (int s = 0; s < Rad<M>::nst; ++s) {
+        for (int s = 0; LINE_MAJOR && s < Rad<M>::nst; ++s) {
             const int Lb = Rad<M>::blocklen(s), st = Lb / Rad<M>::radix(s);
             if (!(st >= (1 << SH1) || Lb <= (1 << SH1))) return false;
             if (W2 && !(st >= (1 << SH2) || Lb <= (1 << SH2))) return false;
