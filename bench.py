@@ -301,6 +301,7 @@ def run_b200(args):
             line["single_sim"] = single_sim_probe(ch)
             line["ensemble_to_stop"] = ensemble_to_stop_probe(ch)
             line["jitter_adaptive"] = jitter_adaptive_probe(ch)
+            line["large_domain"] = large_domain_probe(ch)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -368,6 +369,30 @@ def jitter_adaptive_probe(ch):
     dt = time.perf_counter() - t
     return {"workload": "configs[3]: N=512 jitter 0.01 + adaptive dt (delt_max 2e-10), 700 steps", "steps_per_s": round(699 / dt, 1),
             "wall_s": round(dt, 3), "delt_last": float(sol.delt[-1]), "note": "noise = numpy PCG64 stream reproduced bit-exactly on the device (k_pcg64_fill); diagnostics via k_diag"}
+
+
+def large_domain_probe(ch, N=8192, steps=20):
+    """BASELINE configs[4] on ONE GPU: a single N=8192 domain on the row-slab path (the multi-GPU runs
+    of the same path are tools/slab_check.py under torchrun; profiles/r1d_slab_results.md)."""
+    import torch
+    p = ch.Parameters()
+    p.no_gui, p.full_sim, p.N = True, True, N
+    p.kappa_tilde = 2.989112919661156e-4
+    s = ch.Solver(p)
+    s.prepare()
+    eng = s._stepper
+    eng.run(3)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    eng.run(steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    out = {"workload": f"configs[4] on one GPU: N={N} single domain, {steps} steps (slab path: 4 kernels per step)",
+           "ms_per_step": round(dt / steps * 1e3, 3), "steps_per_s": round(steps / dt, 1),
+           "algorithmic_gbs_32N2": round(32.0 * N * N * steps / dt / 1e9, 1), "launches": eng.launch_count()}
+    del s, eng
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
