@@ -376,6 +376,19 @@ CHS_DEV void row_tile_load_phys(double* sm, const double* __restrict__ g, int ti
     }
 }
 
+// the same as asynchronous 8-byte copies (all in flight at once; complete after
+// chs_cp_async_wait_all() + barrier) -- the long rows of the slab path
+template <int N>
+CHS_DEV void row_tile_load_phys_async(double* sm, const double* __restrict__ g, int tid) {
+    using G = Geo<N>;
+    constexpr int CNT = G::LINES * N / G::NT;
+#pragma unroll 8
+    for (int j = 0; j < CNT; ++j) {
+        const int i = tid + j * G::NT;
+        chs_cp_async8(sm + real_off<N>(mk_pos<N>(i % N)) + 2 * G::LOFF * (i / N), g + (size_t)(i / N) * N + (i % N));
+    }
+}
+
 template <int N>
 CHS_DEV void row_tile_store_phys(const double* sm, double* __restrict__ g, int tid) {
     using G = Geo<N>;

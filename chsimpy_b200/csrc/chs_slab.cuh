@@ -70,7 +70,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
             // y pass: rows are x-slots, the row index runs over y.  Forward DCT, then (S_YSTEP) the
             // spectral update against hat_U' and the inverse DCT without leaving the tile.
             constexpr int CM = (MODE == S_YFWD) ? COL_FWD : COL_STEP;
-            row_tile_load_phys<N>(sm, a.src + goff, tid);
+            row_tile_load_phys_async<N>(sm, a.src + goff, tid);
             double lam1 = 0, lam2 = 0, lamx = 0, gxs = 0;
             if (MODE == S_YSTEP) {
                 const double* hp = a.H + goff;                        // consumed mid-tile: pull into L2 now
@@ -82,6 +82,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                 lamx = a.lam[kx];
                 gxs = a.gsin[kx];
             }
+            chs_cp_async_wait_all();
             __syncthreads();
             fft_fwd_range<N, 0, NST - 1>(scl, t, a.tw);
             int rho_a, rho_b, base_a, base_b;
@@ -116,7 +117,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
             }
         } else {
         if (MODE == S_INV || MODE == S_STEP) row_tile_load_slots_async<N>(sc, a.src + goff, tid);
-        else row_tile_load_phys<N>(sm, a.src + goff, tid);
+        else row_tile_load_phys_async<N>(sm, a.src + goff, tid);
         const bool ra_line = diag && (a.row_base + row0 + l == ra_row);
         const bool ra_tile = diag && (ra_row >= a.row_base + row0) && (ra_row < a.row_base + row0 + LINES);
         chs_cp_async_wait_all();
