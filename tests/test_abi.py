@@ -42,3 +42,22 @@ def test_struct_layout_matches_header():
 def test_kernels_are_sm100a_sass():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def build_c_demo(out_dir):
+    """Compiles examples/c_abi_demo.cpp (a plain C++ client of include/chs_b200.h: dlopen + the CUDA
+    runtime, no Python/PyTorch) and returns the path of the binary."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = os.path.join(str(out_dir), "c_abi_demo")
+    cmd = ["g++", "-std=c++17", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "c_abi_demo.cpp"),
+           "-o", exe, "-I" + os.path.join(cuda, "include"), "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-ldl",
+           "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_cpp_client_compiles_against_the_header(tmp_path):
+    assert os.path.exists(build_c_demo(tmp_path))

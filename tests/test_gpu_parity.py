@@ -365,3 +365,21 @@ def test_uinit_file_and_nan_field(tmp_path):
     s3 = ch.Solver(p, U_init=bad)
     with pytest.raises(AssertionError):
         s3.prepare()
+
+
+@pytest.mark.gpu
+def test_plain_cpp_client_of_the_c_abi(tmp_path):
+    """examples/c_abi_demo.cpp drives libchs_b200.so from C++ alone (dlopen + cudaMalloc): the
+    reference's `-g lcg` run of tests/golden/n64_lcg_k100.npz, row for row."""
+    import subprocess
+    from test_abi import build_c_demo
+    from chsimpy_b200 import _lib
+    z, m = load("n64_lcg_k100")
+    exe = build_c_demo(tmp_path)
+    args = [exe, _lib.LIB_PATH, str(m["N"]), str(m["ntmax"]), str(m["seed"])] + \
+           [repr(float(v)) for v in (m["RT"], m["BRT"], 12.86, m["A0"], m["A1"], m["Amr"], m["kappa_tilde"])]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = np.array([[float(x) for x in ln.split()] for ln in r.stdout.strip().splitlines()])
+    assert "computed_steps=100" in r.stderr
+    check_rows(rows, z["rows"], m["N"])
