@@ -512,7 +512,8 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
         s->launches += 2;
         if (noise) {
-            CHS_LAUNCH((k_diag<N, DIAG_JITTER>), grid, block, G::SMEM_BYTES, s->stream, a);
+            if (pdl) CHS_LAUNCH_PDL((k_diag<N, DIAG_JITTER>), grid, block, G::SMEM_BYTES, s->stream, a);
+            else CHS_LAUNCH((k_diag<N, DIAG_JITTER>), grid, block, G::SMEM_BYTES, s->stream, a);
             s->launches += 1;
         }
         if (s->timing) cudaEventRecord(next_event(s), s->stream);

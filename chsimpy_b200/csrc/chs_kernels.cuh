@@ -735,7 +735,8 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
     double2* scl = sc + l * G::LOFF;
     const bool control = (MODE == ROW_STEP) || (MODE == ROW_FWD_MU);
     const bool jit = (MODE == ROW_STEP) && (a.noise != nullptr);
-    const bool diag = (MODE == ROW_STEP) && !jit;
+    const bool diag = (MODE == ROW_STEP) && !jit;      // spectral gradient energy + edge terms, control in this kernel
+    const bool sums = (MODE == ROW_STEP);              // F, |U - mean|, SA count, Ra: also with jitter (k_diag<JITTER> adds the stencil E2)
     const double2* ltab = control ? stage_logtab<G>(sm, a.logtab, tid) : nullptr;
     const int ra_row = N / 2 + 1;                                           // int(N/2)+1, solver.py:226
         const int si = w / G::NTILES, tile = w % G::NTILES, row0 = tile * LINES;
@@ -744,9 +745,9 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
         const size_t off = (size_t)sim * N * N;
         // tile prologue: every global access is issued before the first dependent use
         if (MODE == ROW_STEP || MODE == ROW_INV) row_tile_load_slots_async<N>(sc, a.T + off + (size_t)row0 * N, tid);
-        const double hat00 = diag ? a.hatU[off] : 0.0;
-        const bool ra_line = diag && (row0 + l == ra_row);
-        const bool ra_tile = diag && (ra_row >= row0) && (ra_row < row0 + LINES);
+        const double hat00 = sums ? a.hatU[off] : 0.0;
+        const bool ra_line = sums && (row0 + l == ra_row);
+        const bool ra_tile = sums && (ra_row >= row0) && (ra_row < row0 + LINES);
         bool slow = false;                  // adaptive-dt column sums / jitter / prologue: unfused middle
         bool want_cols = false;
         int halted = 0;
@@ -797,19 +798,46 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     const double jv = S->p.jitter;
                     const double* nz = a.noise + (size_t)row0 * N;
                     double* dstU = a.U + off + (size_t)row0 * N;
-                    for (int i = tid; i < LINES * N; i += NT) {
-                        const int l2 = i / N, x = i % N;
-                        double* q = sm + real_off<N>(mk_pos<N>(x)) + 2 * l2;
-                        const double u = *q + jv * (2.0 * nz[(size_t)l2 * N + x] - 1.0);
-                        *q = u;
-                        dstU[(size_t)l2 * N + x] = u;
+                    constexpr int CNT = LINES * N / NT, UNR = (CNT % 8 == 0) ? 8 : 1;
+#pragma unroll 1
+                    for (int j0 = 0; j0 < CNT; j0 += UNR) {          // noise loads of a batch in flight together
+                        double z[UNR];
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) z[j] = nz[tid + (j0 + j) * NT];
+#pragma unroll
+                        for (int j = 0; j < UNR; ++j) {
+                            const int i = tid + (j0 + j) * NT;
+                            const int l2 = i / N, x = i % N;
+                            double* q = sm + real_off<N>(mk_pos<N>(x)) + 2 * G::LOFF * l2;
+                            const double u = *q + jv * (2.0 * z[j] - 1.0);
+                            *q = u;
+                            dstU[i] = u;
+                        }
                     }
                     __syncthreads();
+                    if (ra_tile) {                                              // mean of the jittered Ra row
+                        if (ra_line) {
+                            double s = 0;
+                            for (int i = 0; i < 16; ++i) {
+                                const double2 v = scl[G::idx(t + i * TPL)];
+                                s += v.x + v.y;
+                            }
+                            ra_scr[2 + t] = s;
+                        }
+                        __syncthreads();
+                        if (ra_line && t == 0) {
+                            double s = 0;
+                            for (int jj = 0; jj < TPL; ++jj) s += ra_scr[2 + jj];
+                            ra_scr[0] = s / (double)N;
+                        }
+                        __syncthreads();
+                    }
                 }
                 // ============= physics + first forward stage
                 if (control) {
                     const chs_params p = S->p;
-                    const double meanU = hat00 / (double)N;                     // conserved mean (Q4)
+                    // conserved mean (Q4); the jitter shifts it by jitter*(2*mean(noise) - 1)
+                    const double meanU = hat00 / (double)N + (jit ? p.jitter * (2.0 * a.noise_mean[0] - 1.0) : 0.0);
                     if (ra_line) {                                              // Ra = mean |U[r,:] - mean U[r,:]| (solver.py:226-227)
                         const double ra_mean = ra_scr[0];
                         double s = 0;
@@ -843,7 +871,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                             }
                             dft<R0, true>(xr, xi);
                         }
-                        physics<N, R0>(xr, xi, j, p, ltab, diag, meanU, false, 0.0, acc, edge + 4 * l);
+                        physics<N, R0>(xr, xi, j, p, ltab, sums, meanU, false, 0.0, acc, edge + 4 * l);
                         if (!slow) {
                             dft<R0, false>(xr, xi);
 #pragma unroll
@@ -871,6 +899,8 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                                 e += (eg[1] - eg[0]) * (eg[1] - eg[0]) + (eg[3] - eg[2]) * (eg[3] - eg[2]);
                             }
                             pp[P_GXE * G::NTILES] = 0.75 * e;
+                        }
+                        if (sums) {
                             pp[P_F * G::NTILES] = s4[0];
                             pp[P_ABS * G::NTILES] = s4[1];
                             pp[P_CNT * G::NTILES] = s4[3];
@@ -973,35 +1003,58 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
     int* flag = reinterpret_cast<int*>(sm + G::OFF_FLAG);
     const int tid = threadIdx.x;
+    CHS_PDL_TRIGGER();
+    CHS_PDL_WAIT();
     const int sim = a.sim_index ? a.sim_index[blockIdx.y] : (int)blockIdx.y;
     const int tile = blockIdx.x, row0 = tile * LINES;
     Sim* S = a.sims + sim;
     if (MODE == DIAG_JITTER && S->halted) return;
     const chs_params p = S->p;
     const double* U = a.U + (size_t)sim * N * N;
-    double meanU;
-    if (MODE == DIAG_PREPARE) meanU = a.mean_host[sim];
-    else meanU = a.hatU[(size_t)sim * N * N] / (double)N + p.jitter * (2.0 * a.noise_mean[0] - 1.0);
-    const double2* ltab = stage_logtab<G>(sm, a.logtab, tid);
+    // DIAG_JITTER: only the stencil gradient energy is left to this kernel; F, |U - mean|, the SA
+    // count and Ra of the jittered field were summed by k_row<STEP> while it had the values in hand
+    const double meanU = (MODE == DIAG_PREPARE) ? a.mean_host[sim] : 0.0;
+    const double2* ltab = (MODE == DIAG_PREPARE) ? stage_logtab<G>(sm, a.logtab, tid) : nullptr;
     chs_cp_async_wait_all();
     __syncthreads();
     double v[4] = {0, 0, 0, 0};                    // raw grad^2 (x h^2), F, ABS, CNT
-    for (int i = tid; i < LINES * N; i += NT) {
-        const int y = row0 + i / N, x = i % N;
-        const double c = U[(size_t)y * N + x];
-        double gy, gx;
-        if (y == 0) gy = U[(size_t)(y + 1) * N + x] - c;
-        else if (y == N - 1) gy = c - U[(size_t)(y - 1) * N + x];
-        else gy = 0.5 * (U[(size_t)(y + 1) * N + x] - U[(size_t)(y - 1) * N + x]);
-        if (x == 0) gx = U[(size_t)y * N + 1] - c;
-        else if (x == N - 1) gx = c - U[(size_t)y * N + x - 1];
-        else gx = 0.5 * (U[(size_t)y * N + x + 1] - U[(size_t)y * N + x - 1]);
-        double f, mu;
-        thermo(c, p, ltab, f, mu);
-        v[0] += gy * gy + gx * gx;
-        v[1] += f;
-        v[2] += fabs(c - meanU);
-        v[3] += (c < p.threshold) ? 1.0 : 0.0;
+    // all loads of a batch of UNR values are issued before the first use (one simulation is only
+    // NTILES CTAs: the kernel is bound by the latency of these loads, not by their bandwidth)
+    constexpr int CNT = LINES * N / NT, UNR = (CNT % 8 == 0) ? 8 : 1;
+#pragma unroll 1
+    for (int j0 = 0; j0 < CNT; j0 += UNR) {
+        double c[UNR], up[UNR], dn[UNR], lf[UNR], rt[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int i = tid + (j0 + j) * NT;
+            const int y = row0 + i / N, x = i % N;
+            const double* q = U + (size_t)y * N + x;
+            c[j] = q[0];
+            up[j] = (y == 0) ? 0.0 : q[-N];
+            dn[j] = (y == N - 1) ? 0.0 : q[N];
+            lf[j] = (x == 0) ? 0.0 : q[-1];
+            rt[j] = (x == N - 1) ? 0.0 : q[1];
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int i = tid + (j0 + j) * NT;
+            const int y = row0 + i / N, x = i % N;
+            double gy, gx;
+            if (y == 0) gy = dn[j] - c[j];
+            else if (y == N - 1) gy = c[j] - up[j];
+            else gy = 0.5 * (dn[j] - up[j]);
+            if (x == 0) gx = rt[j] - c[j];
+            else if (x == N - 1) gx = c[j] - lf[j];
+            else gx = 0.5 * (rt[j] - lf[j]);
+            v[0] += gy * gy + gx * gx;
+            if (MODE == DIAG_PREPARE) {
+                double f, mu;
+                thermo(c[j], p, ltab, f, mu);
+                v[1] += f;
+                v[2] += fabs(c[j] - meanU);
+                v[3] += (c[j] < p.threshold) ? 1.0 : 0.0;
+            }
+        }
     }
     reduce_stage<4>(v, sm + G::OFF_RED, tid);
     __syncthreads();
@@ -1011,14 +1064,16 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
         pp[P_GE * G::NTILES] = v[0];
         pp[P_GYE * G::NTILES] = 0;
         pp[P_GXE * G::NTILES] = 0;
-        pp[P_F * G::NTILES] = v[1];
-        pp[P_ABS * G::NTILES] = v[2];
-        pp[P_CNT * G::NTILES] = v[3];
+        if (MODE == DIAG_PREPARE) {
+            pp[P_F * G::NTILES] = v[1];
+            pp[P_ABS * G::NTILES] = v[2];
+            pp[P_CNT * G::NTILES] = v[3];
+        }
     }
     __syncthreads();
     // Ra of row int(N/2)+1 (solver.py:115-116 / :226)
     const int ra_row = N / 2 + 1;
-    if (ra_row >= row0 && ra_row < row0 + LINES) {
+    if (MODE == DIAG_PREPARE && ra_row >= row0 && ra_row < row0 + LINES) {
         double s[1] = {0};
         for (int x = tid; x < N; x += NT) s[0] += U[(size_t)ra_row * N + x];
         reduce_stage<1>(s, sm + G::OFF_RED, tid);
