@@ -325,7 +325,7 @@ def single_sim_probe(ch):
             "steps_per_s": round((sol.computed_steps - 1) / dt, 1), "wall_s": round(dt, 4)}
 
 
-def ensemble_to_stop_probe(ch, members=256):
+def ensemble_to_stop_probe(ch, members=1024):
     """BASELINE configs[2] as the reference runs it: every member to ITS energy stop (device-side
     flags, grid compaction at each poll); solve only (kappa_tilde interpolated, no exports)."""
     import torch
