@@ -172,7 +172,8 @@ def initial_field(params):
 
 
 def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_init=None, host_procs=None,
-                   batch_max=2048, poll_every=128, keep_fields=True, backend=None, device=None, timings=None):
+                   batch_max=2048, poll_every=128, keep_fields=True, backend=None, device=None, timings=None,
+                   pipeline_batch=256):
     """Runs the members `run_ids` in lock-step on one GPU.  Returns a list of dicts with the
     reference's 12-tuple (`tuple`), the TimeData (`timedata`), the final field (`U`, optional)
     and the per-member Solution scalars."""
@@ -186,13 +187,18 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
     for p, _, _ in members:
         jobs.append((p.R, p.temp, p.B, float(p.func_A0(p.temp)), float(p.func_A1(p.temp)), p.XXX, p.kappa_tilde))
     nproc = host_procs or min(len(jobs), utils.get_number_physical_cores() or 1)
+    pool = None
     if nproc > 1 and len(jobs) > 1:
-        # forkserver: the workers start from a clean process (no CUDA context, no torch threads)
-        with mp.get_context("forkserver").Pool(nproc) as pool:
-            scal = pool.map(_host_scalars, jobs, chunksize=max(1, len(jobs) // (4 * nproc)))
+        # forkserver: the workers start from a clean process (no CUDA context, no torch threads).
+        # imap streams the results in order: the device runs batch k while the pool is still
+        # working on the scalars of batch k+1 (the sympy work is the larger part of an ensemble)
+        pool = mp.get_context("forkserver").Pool(nproc)
+        scal_iter = pool.imap(_host_scalars, jobs, chunksize=max(1, min(8, len(jobs) // (4 * nproc))))
+        batch_max = min(batch_max, max(int(pipeline_batch), 1))
     else:
-        scal = [_host_scalars(j) for j in jobs]
-    t_host = time.perf_counter() - t0
+        scal_iter = iter([_host_scalars(j) for j in jobs])
+    scal = []
+    t_host = 0.0
     if U_init is None:
         U_init = initial_field(init_params)
     assert U_init.shape == (init_params.N, init_params.N)
@@ -200,6 +206,9 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
     t_dev = 0.0
     for c0 in range(0, len(members), batch_max):
         chunk = list(range(c0, min(c0 + batch_max, len(members))))
+        tw = time.perf_counter()
+        scal.extend(next(scal_iter) for _ in chunk)    # waits for this batch's scalars only
+        t_host += time.perf_counter() - tw
         sols, structs = [], []
         for i in chunk:
             p = members[i][0]
@@ -234,8 +243,11 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
             tup = (sol.A0, sol.A1, ca, cb, sa, sb, sol.tau0, sol.t0, int(np.argmax(sol.E2)), run_ids[i], f0, f1)
             out.append({"tuple": tup, "solution": sol, "params": p, "run_id": run_ids[i]})
         del st
+    if pool is not None:
+        pool.close()
+        pool.join()
     if timings is not None:
-        timings.update(host_scalars_s=t_host, device_s=t_dev, host_procs=nproc)
+        timings.update(host_scalars_s=t_host, device_s=t_dev, host_procs=nproc, total_s=time.perf_counter() - t0)
     return out
 
 
@@ -285,7 +297,8 @@ def main(argv=None):
     tm = {}
     t0 = time.perf_counter()
     res = solve_ensemble(init_params, rand_values, A_list, run_ids=mine,
-                         host_procs=None if ep.processes == -1 else max(1, ep.processes), timings=tm)
+                         host_procs=None if ep.processes == -1 else max(1, ep.processes), timings=tm,
+                         keep_fields=not ep.no_export)
     t_solve = time.perf_counter() - t0
     if not ep.no_export:
         jobs = [(f"{r['params'].file_id}.solution", init_params.yaml, init_params.export_csv,
@@ -313,8 +326,8 @@ def main(argv=None):
         print(agg.T)
         agg.T.to_csv(f"{init_params.file_id}-results-agg.csv")
         print(f"members: {len(tuples)} on {world} GPU(s); rank-0 solve {t_solve:.2f} s "
-              f"(host sympy {tm.get('host_scalars_s', 0):.2f} s on {tm.get('host_procs')} procs, "
-              f"device {tm.get('device_s', 0):.2f} s)")
+              f"(waiting for the host sympy scalars {tm.get('host_scalars_s', 0):.2f} s on {tm.get('host_procs')} procs, "
+              f"device {tm.get('device_s', 0):.2f} s, overlapped)")
         print('Output files:')
         for suffix in ('metadata', 'results-agg', 'results'):
             print(f"  {init_params.file_id}-{suffix}.csv")
