@@ -383,3 +383,24 @@ def test_plain_cpp_client_of_the_c_abi(tmp_path):
     rows = np.array([[float(x) for x in ln.split()] for ln in r.stdout.strip().splitlines()])
     assert "computed_steps=100" in r.stderr
     check_rows(rows, z["rows"], m["N"])
+
+
+@pytest.mark.gpu
+def test_slab_two_gpus_peer_memory_and_nccl():
+    """Row-slab decomposition over two GPUs (needs a box with >= 2): tools/slab_check.py replays the
+    reference fixtures n2048_k10 and n8192_k4 on both ranks, once with the peer-memory transposes
+    and once with the NCCL all-to-all route."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p2p in ("1", "0"):
+        env = dict(os.environ, CHS_SLAB_P2P=p2p)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29577",
+                            os.path.join(root, "tools", "slab_check.py"), "2048", "5"],
+                           capture_output=True, text=True, timeout=900, env=env, cwd=root)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert r.stdout.count("[slab parity] world=2") == 2
