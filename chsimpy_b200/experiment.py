@@ -296,8 +296,11 @@ def main(argv=None):
     mine = shard(n_items, rank, world)
     tm = {}
     t0 = time.perf_counter()
+    # the ranks of a box share its host cores: each gets its share for the sympy pool
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    share = max(1, (utils.get_number_physical_cores() or 1) // max(1, local_world))
     res = solve_ensemble(init_params, rand_values, A_list, run_ids=mine,
-                         host_procs=None if ep.processes == -1 else max(1, ep.processes), timings=tm,
+                         host_procs=(share if world > 1 else None) if ep.processes == -1 else max(1, ep.processes), timings=tm,
                          keep_fields=not ep.no_export)
     t_solve = time.perf_counter() - t0
     if not ep.no_export:
