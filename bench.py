@@ -247,9 +247,12 @@ def run_b200(args):
     step_bytes = ALGO_BYTES_PER_SIM_STEP * B
     achieved = step_bytes / ((col_us + row_us) * 1e-6) / 1e9
     traffic = None
+    fp64_instr = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_step_per_sim")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("dram_bytes_per_step_per_sim")
         traffic = traffic * B if traffic else None
+        fp64_instr = tj.get("fp64_warp_instr_per_step_per_sim")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k_col<512,STEP> + k_row<512,STEP> (the two launches of one step)",
@@ -257,6 +260,7 @@ def run_b200(args):
                 "peak_source": peak_src, "traffic": traffic,
                 "algorithmic_bytes_per_launch_pair": step_bytes,
                 "k_col_us": round(col_us, 2), "k_row_us": round(row_us, 2),
+                "fp64_issue_floor": fp64_floor(fp64_instr, clocks, value / world),
                 "k_col_gbs_own_32N2": round(32 * N_GRID ** 2 * B / (col_us * 1e-6) / 1e9, 1),
                 "k_row_gbs_own_16N2": round(16 * N_GRID ** 2 * B / (row_us * 1e-6) / 1e9, 1)}
 
@@ -305,6 +309,20 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def fp64_floor(instr_per_sim_step, clocks, rate_per_gpu):
+    """The other ceiling of this path: the step needs ~139 FP64 instructions per grid point (ncu), and
+    B200 issues one FP64 warp instruction per 2 cycles per SM sub-partition -- at N=512 that floor
+    (~2 us per sim-step) is ABOVE the HBM time of the 32*N^2 algorithmic bytes (1.3 us)."""
+    if not instr_per_sim_step:
+        return None
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    floor_rate = sms * 4 * 0.5 * mhz * 1e6 / instr_per_sim_step
+    return {"fp64_warp_instr_per_sim_step": instr_per_sim_step, "sim_steps_per_s_at_full_fp64_issue": round(floor_rate, 1),
+            "frac": round(rate_per_gpu / floor_rate, 4), "source": "profiles/traffic.json (ncu sm__inst_executed_pipe_fp64)"}
 
 
 def single_sim_probe(ch):
