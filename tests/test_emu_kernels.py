@@ -208,3 +208,29 @@ def test_slab_row_kernels_large_rows(be, N):
         assert np.abs(be.download(B) - fp.idct(Hn, axis=1, norm="ortho")).max() < 1e-12
     finally:
         lib.chs_slab_destroy(h)
+
+
+def log_errors(stepper, x):
+    """(error in ulp of the result, absolute error) of the kernels' table-driven log against 120-bit mpmath."""
+    import mpmath as mpm
+    y = stepper.debug_log(x)
+    with mpm.workprec(120):
+        exact = [mpm.log(mpm.mpf(float(v))) for v in x]
+        abs_err = np.array([abs(float(mpm.mpf(float(a)) - b)) for a, b in zip(y, exact)])
+        ulp = np.spacing(np.abs(np.array([float(b) for b in exact])))
+    return abs_err / ulp, abs_err
+
+
+def test_fast_log_accuracy(be):
+    """csrc/fastlog.cuh stands in for np.log at solver.py:173,220: within 1.25 ulp over the range of a
+    concentration field and its complement, within 1e-18 absolutely next to 1, libm outside."""
+    st = BatchStepper(32, [unit_params(32)], backend=be)
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(0.005, 0.995, 6000), np.exp(rng.uniform(-40, 40, 2000))])
+    ulp_err, abs_err = log_errors(st, x)
+    big = np.abs(np.log(x)) >= 2.0 ** -7
+    assert ulp_err[big].max() <= 1.25 and abs_err[~big].max() <= 1e-18
+    _, abs_err = log_errors(st, 1 + rng.uniform(-2e-3, 2e-3, 2000))
+    assert abs_err.max() <= 1e-18
+    y = st.debug_log(np.array([0.0, -1.0, np.inf, np.nan, 5e-324]))
+    assert y[0] == -np.inf and np.isnan(y[1]) and y[2] == np.inf and np.isnan(y[3]) and abs(y[4] - np.log(5e-324)) < 1e-12

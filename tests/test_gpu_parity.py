@@ -404,3 +404,21 @@ def test_slab_two_gpus_peer_memory_and_nccl():
                            capture_output=True, text=True, timeout=900, env=env, cwd=root)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert r.stdout.count("[slab parity] world=2") == 2
+
+
+@pytest.mark.gpu
+def test_fast_log_accuracy_on_device():
+    """The device's table-driven log (csrc/fastlog.cuh) against 120-bit mpmath: <= 1.25 ulp over (0.005, 0.995)."""
+    from chsimpy_b200.solver import BatchStepper, make_params_struct
+    import chsimpy_b200 as ch
+    from test_emu_kernels import log_errors
+    p = ch.Parameters()
+    p.N, p.kappa_tilde = 32, 3e-4
+    st = BatchStepper(32, [make_params_struct(p, ch.Solution(p))])
+    rng = np.random.default_rng(7)
+    x = rng.uniform(0.005, 0.995, 4000)
+    ulp_err, abs_err = log_errors(st, x)
+    big = np.abs(np.log(x)) >= 2.0 ** -7
+    assert ulp_err[big].max() <= 1.25 and abs_err[~big].max() <= 1e-18
+    y = st.debug_log(np.array([0.0, -1.0, np.nan]))
+    assert y[0] == -np.inf and np.isnan(y[1]) and np.isnan(y[2])
