@@ -590,7 +590,10 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
         Sim* S = a.sims + sim;
         const size_t off = (size_t)sim * N * N;
         // all global traffic of the tile prologue is issued before the first dependent use
-        if (MODE != COL_INV) col_tile_load_async<N>(scl, a.T + off + kx0 + l, t);
+        // tile I/O keeps the 8 adjacent columns in adjacent lanes (64-byte segments) whatever the compute mapping
+        const int lio = G::WARP_LINES ? tid % LINES : l, tio = G::WARP_LINES ? tid / LINES : t;
+        double2* scio = sc + lio * G::LOFF;
+        if (MODE != COL_INV) col_tile_load_async<N>(scio, a.T + off + kx0 + lio, tio);
         if (MODE == COL_STEP) {
             // the hat_U tile is consumed in the middle of the tile's work: pull it into L2 now
             const double* hp = a.hatU + off + (size_t)tile * N * LINES;          // contiguous 8*N*LINES bytes
@@ -612,7 +615,7 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
         __syncthreads();
         if (!halted) {
             // -------- forward column DCT-II up to the last stage
-            if (MODE != COL_INV) fft_fwd_range<N, 0, NST - 1>(scl, t, s_tw);
+            if (MODE != COL_INV) fft_fwd_range<N, 0, NST - 1, true>(scl, t, s_tw);
             // -------- fused: last forward stage + post + spectral update + pre + first inverse stage
             int rho_a, rho_b, base_a, base_b;
             unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
@@ -628,8 +631,10 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
             // hat_U is stored tile-major ([tile][ky][LINES]): the tile of a CTA is one contiguous block;
             // the stand-alone transforms use natural row-major arrays on the far side
             const bool nat = (MODE != COL_STEP) && a.natural;
-            mid.hstride = nat ? N : LINES;
-            const size_t toff = nat ? off + col : off + (size_t)tile * N * LINES + l;
+            // (warp-line geometry: the lanes of a warp are consecutive frequencies of ONE line, so the tile
+            // is stored line by line, [tile][LINES][ky], and a warp reads 128 contiguous bytes)
+            mid.hstride = nat ? N : (G::WARP_LINES ? 1 : LINES);
+            const size_t toff = nat ? off + col : off + (size_t)tile * N * LINES + (G::WARP_LINES ? (size_t)l * N : (size_t)l);
             mid.hat = ((MODE == COL_FWD && a.dst) ? a.dst : a.hatU) + toff;
             mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + toff;
             mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
@@ -643,17 +648,18 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
                     const double v[1] = {mid.ge};
                     reduce_stage<1>(v, sm + G::OFF_RED, tid);
                 }
-                __syncthreads();
+                line_barrier<N, true>();
                 // -------- remaining inverse stages
-                fft_inv_range<N, 0, NST - 1>(scl, t, s_tw);
+                fft_inv_range<N, 0, NST - 1, true>(scl, t, s_tw);
+                if (G::WARP_LINES) __syncthreads();              // what follows crosses lines (edge terms, transposing store)
                 // -------- partial sums: spectral gradient energy + one-sided y-edge terms
                 if (MODE == COL_STEP && tid == 0) {
                     double v[1];
                     reduce_final<1>(v, sm + G::OFF_RED, NT);
                     double e = 0;
                     for (int l2 = 0; l2 < LINES; ++l2) {
-                        const double u0 = sm[real_off<N>(mk_pos<N>(0)) + 2 * l2], u1 = sm[real_off<N>(mk_pos<N>(1)) + 2 * l2];
-                        const double v0 = sm[real_off<N>(mk_pos<N>(N - 1)) + 2 * l2], v1 = sm[real_off<N>(mk_pos<N>(N - 2)) + 2 * l2];
+                        const double u0 = sm[real_off<N>(mk_pos<N>(0)) + 2 * G::LOFF * l2], u1 = sm[real_off<N>(mk_pos<N>(1)) + 2 * G::LOFF * l2];
+                        const double v0 = sm[real_off<N>(mk_pos<N>(N - 1)) + 2 * G::LOFF * l2], v1 = sm[real_off<N>(mk_pos<N>(N - 2)) + 2 * G::LOFF * l2];
                         e += (u1 - u0) * (u1 - u0) + (v0 - v1) * (v0 - v1);
                     }
                     double* pp = a.part + (size_t)sim * P_NSLOT * G::NTILES + tile;
@@ -661,7 +667,7 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
                     pp[P_GYE * G::NTILES] = 0.75 * e;
                 }
                 // -------- store T tile
-                col_tile_store<N>(scl, a.T + off + kx0 + l, t);
+                col_tile_store<N>(scio, a.T + off + kx0 + lio, tio);
             }
         }
 }
@@ -782,8 +788,8 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     store_block<N>(scl, base_a, ar, ai);
                     store_block<N>(scl, base_b, br, bi);
                 }
-                __syncthreads();
-                fft_inv_range<N, 1, NST - 1>(scl, t, s_tw);
+                line_barrier<N, true>();
+                fft_inv_range<N, 1, NST - 1, true>(scl, t, s_tw);
                 if (MODE == ROW_INV || slow) {
                     fft_stage<N, 0, true>(scl, t, s_tw);
                     __syncthreads();
@@ -928,7 +934,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                                 double s = 0;
 #pragma unroll
                                 for (int l2 = 0; l2 < LINES; ++l2) {
-                                    const double m = colp[2 * l2];
+                                    const double m = colp[2 * G::LOFF * l2];
                                     s += p.delt_max / sqrt(1.0 + 62.5 * (m * m));
                                 }
                                 a.colpart[((size_t)sim * G::NTILES + tile) * N + x] = s;
@@ -943,7 +949,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     __syncthreads();
                 }
                 // ============= forward half: remaining stages, fused last stage + post, store
-                fft_fwd_range<N, 1, NST - 1>(scl, t, s_tw);
+                fft_fwd_range<N, 1, NST - 1, true>(scl, t, s_tw);
                 {
                     int rho_a, rho_b, base_a, base_b;
                     unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);

@@ -58,7 +58,19 @@ struct Geo {
     //     16-byte accesses are contiguous; pad() skews the 8-point blocks of the fused last stage
     //     (the blocks of 8 consecutive residues lie M/8, M/16, ... apart: the top digits of the
     //     position) over the banks.  pad is additive over the strides the stages use, see step().
-    static constexpr bool LINE_MAJOR = (N >= 2048);
+#ifndef CHS_WARP_LINES
+#define CHS_WARP_LINES 0
+#endif
+    // Optional geometry for N = 256 .. 1024 (batched kernels, -DCHS_WARP_LINES=1): line-major too, with
+    // the M/16 <= 32 threads of a line inside ONE warp -- the FFT stages of a line then need only
+    // __syncwarp, and the warps of a CTA drift apart instead of meeting at a block barrier after every
+    // stage.  Correct (parity suite, ThreadSanitizer on the host emulation) but measured SLOWER on
+    // B200 (195 k vs 224 k sim-steps/s): k_row gains 3 % (barrier stalls 9.4 -> 5.5 %), k_col loses
+    // 33 % -- with the lines of a point in adjacent lanes every twiddle / lambda / hat_U table load is
+    // one address per 8 lanes (a broadcast); with the points of a line in adjacent lanes each lane
+    // loads its own entry and the L1 pipe saturates (l1tex 70-84 %).  Off by default.
+    static constexpr bool WARP_LINES = CHS_WARP_LINES && (N >= 256) && (N <= 1024);
+    static constexpr bool LINE_MAJOR = (N >= 2048) || WARP_LINES;
     static constexpr int LPC = LINE_MAJOR ? 1 : LINES + 1;     // point pitch
     // first radix 8: the top 3 position bits; 4: top 2 bits + the low bit of the next digit (x4);
     // 2: the low 2 bits of the second digit + the top bit (x4)
@@ -70,7 +82,8 @@ struct Geo {
     CHS_CX static constexpr int idx(int c) { return LINE_MAJOR ? c + pad(c) : c * LPC; }
     // idx(base + q*st) = idx(base) + q*step(st) for the points of one butterfly
     CHS_CX static constexpr int step(int st) { return LINE_MAJOR ? st + pad(st) : st * LPC; }
-    static constexpr int LOFF = LINE_MAJOR ? M + (M >> SH1) + W2 * (M >> SH2) : 1;              // line offset
+    static constexpr int LOFF_MIN = M + (M >> SH1) + W2 * (M >> SH2);
+    static constexpr int LOFF = LINE_MAJOR ? (WARP_LINES ? ((LOFF_MIN + 6) / 8) * 8 + 1 : LOFF_MIN) : 1;   // line offset (= 1 mod 8 when lines share a CTA)
     // every stage either strides by a multiple of a pad term's period or stays inside one period
     CHS_CX static constexpr bool pad_ok() {
         for (int s = 0; LINE_MAJOR && s < Rad<M>::nst; ++s) {
@@ -106,6 +119,8 @@ struct Geo {
     static_assert(Rad<M>::radix(Rad<M>::nst - 1) == 8 && Rad<M>::nst >= 2, "plan must end with a radix-8 stage");
     static_assert((OFF_LOGTAB % 2) == 0, "double2 alignment");
     static_assert(pad_ok(), "bank skew is not additive for this radix plan");
+    static_assert(!LINE_MAJOR || (SH1 >= 3 && (W2 == 0 || SH2 >= 3)), "skew must be constant inside an 8-point block");
+    static_assert(!WARP_LINES || (32 % TPL == 0), "the threads of a line must share a warp");
 };
 
 // Makhoul reorder: physical index n -> position in v
@@ -225,22 +240,29 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
     }
 }
 
-// forward stages [S0, S1): each followed by a block barrier
-template <int N, int S0, int S1>
+// barrier between two passes over ONE line: the threads of a line share a warp in the WARP_LINES
+// geometry (WARP = true; callers whose next access crosses lines use the block barrier)
+template <int N, bool WARP>
+CHS_DEV void line_barrier() {
+    if constexpr (WARP && Geo<N>::WARP_LINES) __syncwarp();
+    else __syncthreads();
+}
+// forward stages [S0, S1): each followed by a barrier (block, or line with WARP)
+template <int N, int S0, int S1, bool WARP = false>
 CHS_DEV void fft_fwd_range(double2* scl, int t, const double2* __restrict__ tw) {
     if constexpr (S0 < S1) {
         fft_stage<N, S0, false>(scl, t, tw);
-        __syncthreads();
-        fft_fwd_range<N, S0 + 1, S1>(scl, t, tw);
+        line_barrier<N, WARP>();
+        fft_fwd_range<N, S0 + 1, S1, WARP>(scl, t, tw);
     }
 }
-// inverse stages S1-1 down to S0: each followed by a block barrier
-template <int N, int S0, int S1>
+// inverse stages S1-1 down to S0: each followed by a barrier
+template <int N, int S0, int S1, bool WARP = false>
 CHS_DEV void fft_inv_range(double2* scl, int t, const double2* __restrict__ tw) {
     if constexpr (S0 < S1) {
         fft_stage<N, S1 - 1, true>(scl, t, tw);
-        __syncthreads();
-        fft_inv_range<N, S0, S1 - 1>(scl, t, tw);
+        line_barrier<N, WARP>();
+        fft_inv_range<N, S0, S1 - 1, WARP>(scl, t, tw);
     }
 }
 

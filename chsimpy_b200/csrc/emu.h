@@ -24,6 +24,7 @@ inline thread_local dim3 t_threadIdx, t_blockIdx;
 inline dim3 g_blockDim, g_gridDim;
 inline unsigned char* g_smem = nullptr;
 inline std::barrier<>* g_bar = nullptr;
+inline thread_local std::barrier<>* t_wbar = nullptr;     // the 32 threads of this thread's warp
 
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
@@ -38,12 +39,16 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 std::barrier<> bar((std::ptrdiff_t)nthreads);
                 g_bar = &bar;
+                std::vector<std::unique_ptr<std::barrier<>>> wbar;
+                for (unsigned w0 = 0; w0 < nthreads; w0 += 32)
+                    wbar.emplace_back(new std::barrier<>((std::ptrdiff_t)(nthreads - w0 < 32 ? nthreads - w0 : 32)));
                 std::vector<std::thread> th;
                 th.reserve(nthreads);
                 for (unsigned t = 0; t < nthreads; ++t)
                     th.emplace_back([&, t] {
                         t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
                         t_blockIdx = dim3(bx, by, bz);
+                        t_wbar = wbar[t / 32].get();
                         body();
                     });
                 for (auto& x : th) x.join();
@@ -58,6 +63,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
 #define blockDim (emu::g_blockDim)
 #define gridDim (emu::g_gridDim)
 #define __syncthreads() emu::g_bar->arrive_and_wait()
+#define __syncwarp() emu::t_wbar->arrive_and_wait()
 #define __restrict__
 #define __launch_bounds__(...)
 #define CHS_DEV static inline

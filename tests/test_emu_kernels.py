@@ -27,7 +27,7 @@ def unit_params(N):
                        delt_max=1e-8, M_tilde=1, threshold=0.5, time_limit_s=0, jitter=0, full_sim=1, adaptive_time=0)
 
 
-@pytest.mark.parametrize("N", [32, 64, 128])
+@pytest.mark.parametrize("N", [32, 64, 128, 256, 512])
 def test_dctn_idctn(be, N):
     st = BatchStepper(N, [unit_params(N)] * 2, backend=be)
     x = np.random.default_rng(N).random((2, N, N)) - 0.4
@@ -55,6 +55,13 @@ def run_fixture(be, name, limit=None):
     rel[ref == 0] = np.abs(rows[ref == 0])
     assert rel.max() < 1e-11, rel.max(axis=0)
     return sol, z, m
+
+
+@pytest.mark.parametrize("name,steps", [("n256_k200", 6), ("n512_full2000", 3)])
+def test_step_n256_n512(be, name, steps):
+    """The tile geometry of the sizes that matter (N = 256, 512), a few steps against the fixtures."""
+    sol, z, m = run_fixture(be, name, limit=steps)
+    assert sol.computed_steps == steps
 
 
 def test_step_n32_full(be):
