@@ -148,6 +148,31 @@ extern "C" int64_t chs_workspace_bytes(int32_t N, int32_t batch) {
         default: return fail("unsupported N"); \
     }
 
+// FFT twiddles for the kernels of size N: the natural table tw[m] = exp(-2 pi i m / M) for the point-major
+// tile geometry, the per-stage tables of Rad<M>::tws_off (same values, warp-contiguous order) for the
+// line-major one.  Always fewer than M entries.
+static void fill_twiddles(int N, std::vector<double2>& tw) {
+    const int M = N / 2;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    std::vector<double2> nat(M);
+    for (int m = 0; m < M; ++m) { const long double a = -2.0L * pi * m / M; nat[m] = make_double2((double)cosl(a), (double)sinl(a)); }
+    const bool line_major = (N >= 2048) || (CHS_WARP_LINES && N >= 256 && N <= 1024);
+    tw.assign(M, make_double2(0.0, 0.0));
+    if (!line_major) { tw = nat; return; }
+    std::vector<int> rad; int lg = 0;
+    while ((1 << lg) < M) ++lg;
+    if (lg % 3) rad.push_back(1 << (lg % 3));
+    for (int i = 0; i < lg / 3; ++i) rad.push_back(8);
+    size_t o = 0; int Lb = M;
+    for (size_t s = 0; s + 1 < rad.size(); ++s) {
+        const int r = rad[s], st = Lb / r;
+        for (int p = 1; p < r; ++p)
+            for (int j = 0; j < st; ++j) tw[o + (size_t)(p - 1) * st + j] = nat[(size_t)j * p * (M / Lb)];
+        o += (size_t)(r - 1) * st;
+        Lb /= r;
+    }
+}
+
 template <class K>
 static int resident_ctas(K kern, int threads, int smem, int num_sms) {
     int per_sm = 0;
@@ -248,10 +273,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     std::vector<double> cm, ct;
     const long double pi = 3.14159265358979323846264338327950288L;
     if (!s->gemm) {
-        for (int m = 0; m < M; ++m) {
-            const long double a = -2.0L * pi * m / M;
-            tw[m] = make_double2((double)cosl(a), (double)sinl(a));
-        }
+        fill_twiddles(N, tw);
         for (int m = 0; m < N; ++m) {
             const long double a = -pi * m / (2.0L * N);
             om[m] = make_double2((double)cosl(a), (double)sinl(a));
@@ -740,7 +762,7 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     std::vector<double> gs(N);
     std::vector<int> kof(N);
     const long double pi = 3.14159265358979323846264338327950288L;
-    for (int m = 0; m < M; ++m) { const long double a = -2.0L * pi * m / M; tw[m] = make_double2((double)cosl(a), (double)sinl(a)); }
+    fill_twiddles(N, tw);
     for (int m = 0; m < N; ++m) { const long double a = -pi * m / (2.0L * N); om[m] = make_double2((double)cosl(a), (double)sinl(a)); }
     for (int k = 0; k < N; ++k) { const long double sn = sinl(pi * k / N); gs[k] = (double)(sn * sn); }
     {

@@ -38,7 +38,7 @@ struct SlabArgs {
     const double* gsin;
     const int* kof;
     Sim* S;
-    const double2* tw;
+    const double2* tw;          // natural table (point-major geometry), or the per-stage tables (line-major)
     const double2* om;
     const double2* logtab;
 };
@@ -166,7 +166,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                     dft<R0, false>(xr, xi);
 #pragma unroll
                     for (int q = 1; q < R0; ++q) {
-                        const double2 w = __ldg(a.tw + j * q);
+                        const double2 w = G::LINE_MAJOR ? __ldg(a.tw + (q - 1) * ST0 + j) : __ldg(a.tw + j * q);
                         const double x = xr[q], y = xi[q];
                         xr[q] = x * w.x - y * w.y;
                         xi[q] = x * w.y + y * w.x;

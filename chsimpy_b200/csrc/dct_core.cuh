@@ -36,6 +36,15 @@ struct Rad {
         for (int i = 0; i < s; ++i) Lb /= radix(i);
         return Lb;
     }
+    // Per-stage twiddle tables of the line-major geometry: stage s, power p, butterfly j at
+    // tws[tws_off(s) + (p-1)*st + j] = exp(-2 pi i j p / Lb) -- the lanes of a warp are consecutive j
+    // there, so a warp reads contiguous entries (the natural table tw[j*p*M/Lb] is a strided gather)
+    CHS_CX static constexpr int tws_off(int s) {
+        int o = 0;
+        for (int i = 0; i < s; ++i) o += (radix(i) - 1) * (blocklen(i) / radix(i));
+        return o;
+    }
+    static constexpr int tws_len = tws_off(nst - 1);      // the last stage has no twiddles
 };
 
 #ifndef CHS_LINES
@@ -195,7 +204,8 @@ CHS_DEV void dft(double (&xr)[R], double (&xi)[R]) {
 
 // ------------------------------------------------------------------ regular FFT stages
 // scl = (double2*)tile + l*LOFF (line base), t = thread index within the line,
-// tw[m] = exp(-2 pi i m / M).  Every thread owns 16/r butterflies of radix r.
+// tw[m] = exp(-2 pi i m / M) -- or, in the line-major geometry, the per-stage tables Rad<M>::tws_off
+// describes.  Every thread owns 16/r butterflies of radix r.
 template <int N, int S, bool INV>
 CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
     using G = Geo<N>;
@@ -223,7 +233,7 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
         if (st > 1) {
 #pragma unroll
             for (int p = 1; p < r; ++p) {
-                const double2 w = __ldg(tw + j * p * (M / Lb));
+                const double2 w = G::LINE_MAJOR ? __ldg(tw + Rad<M>::tws_off(S) + (p - 1) * st + j) : __ldg(tw + j * p * (M / Lb));
                 const double a = xr[i][p], b = xi[i][p];
                 if (!INV) { xr[i][p] = a * w.x - b * w.y; xi[i][p] = a * w.y + b * w.x; }
                 else      { xr[i][p] = a * w.x + b * w.y; xi[i][p] = b * w.x - a * w.y; }     // conj(w)
