@@ -111,7 +111,7 @@ static Layout layout(int N, int batch) {
     L.part = o; o = align_up(o + sizeof(double) * (size_t)batch * P_NSLOT * ntiles);
     L.colpart = o; o = align_up(o + sizeof(double) * (size_t)batch * ntiles * N);
     L.tw = o; o = align_up(o + sizeof(double2) * (size_t)(N / 2));
-    L.om = o; o = align_up(o + sizeof(double2) * (size_t)N);
+    L.om = o; o = align_up(o + sizeof(double2) * (size_t)(N + N / 4));      // om[N] + the contiguous copy of om[4k], k < N/4
     L.lam = o; o = align_up(o + sizeof(double) * (size_t)N);
     L.gsin = o; o = align_up(o + sizeof(double) * (size_t)N);
     L.kof = o; o = align_up(o + sizeof(int) * (size_t)N);
@@ -266,7 +266,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     s->t_ms[0] = s->t_ms[1] = s->t_ms[2] = 0;
     // twiddle tables in extended precision, rounded once
     const int M = N / 2;
-    std::vector<double2> tw(M), om(N);
+    std::vector<double2> tw(M), om(N + N / 4);
     std::vector<double> gs(N);
     std::vector<int> kof(N);
     std::vector<double2> lt(LOG_TABLE_N);
@@ -278,6 +278,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
             const long double a = -pi * m / (2.0L * N);
             om[m] = make_double2((double)cosl(a), (double)sinl(a));
         }
+        for (int k = 0; k < N / 4; ++k) om[N + k] = om[4 * k];
         // gradient-energy weights sin^2(pi k/N) and the slot -> frequency map of the FFT plan
         for (int k = 0; k < N; ++k) {
             const long double sn = sinl(pi * k / N);
@@ -320,7 +321,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     bool ok = true;
     ok &= cudaMemsetAsync(workspace, 0, L.total, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->tw, tw.data(), sizeof(double2) * M, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
-    ok &= cudaMemcpyAsync(s->om, om.data(), sizeof(double2) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->om, om.data(), sizeof(double2) * om.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->gsin, gs.data(), sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
@@ -695,7 +696,7 @@ static SlabLayout slab_layout(int N, int rows) {
     L.yedge = o; o = align_up(o + sizeof(double) * 2);
     L.vec = o; o = align_up(o + sizeof(double) * R_NVAL);
     L.tw = o; o = align_up(o + sizeof(double2) * (size_t)(N / 2));
-    L.om = o; o = align_up(o + sizeof(double2) * (size_t)N);
+    L.om = o; o = align_up(o + sizeof(double2) * (size_t)(N + N / 4));      // om[N] + the contiguous copy of om[4k], k < N/4
     L.lam = o; o = align_up(o + sizeof(double) * (size_t)N);
     L.gsin = o; o = align_up(o + sizeof(double) * (size_t)N);
     L.kof = o; o = align_up(o + sizeof(int) * (size_t)N);
@@ -758,12 +759,13 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     std::memset(&s->hsim, 0, sizeof(Sim));
     s->hsim.p = *p; s->hsim.delt = p->delt; s->hsim.delt_coef = p->delt;
     const int M = N / 2;
-    std::vector<double2> tw(M), om(N), lt(LOG_TABLE_N);
+    std::vector<double2> tw(M), om(N + N / 4), lt(LOG_TABLE_N);
     std::vector<double> gs(N);
     std::vector<int> kof(N);
     const long double pi = 3.14159265358979323846264338327950288L;
     fill_twiddles(N, tw);
     for (int m = 0; m < N; ++m) { const long double a = -pi * m / (2.0L * N); om[m] = make_double2((double)cosl(a), (double)sinl(a)); }
+    for (int k = 0; k < N / 4; ++k) om[N + k] = om[4 * k];
     for (int k = 0; k < N; ++k) { const long double sn = sinl(pi * k / N); gs[k] = (double)(sn * sn); }
     {
         std::vector<int> rad; int lg = 0;
@@ -784,7 +786,7 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     }
     bool ok = cudaMemsetAsync(workspace, 0, L.total, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->tw, tw.data(), sizeof(double2) * M, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
-    ok &= cudaMemcpyAsync(s->om, om.data(), sizeof(double2) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= cudaMemcpyAsync(s->om, om.data(), sizeof(double2) * om.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->gsin, gs.data(), sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;

@@ -285,7 +285,8 @@ template <int N>
 CHS_DEV void post_pair(int k, const double2* __restrict__ om, double ar, double ai, double br, double bi,
                        double (&c)[4]) {
     constexpr int M = N / 2;
-    const double2 t = __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    // om[N + k] repeats om[4k] in contiguous order for the line-major geometry (adjacent lanes = adjacent k)
+    const double2 t = Geo<N>::LINE_MAJOR ? __ldg(om + N + k) : __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
     const double sc = 0.5 * sqrt(2.0 / N);
     const double er = ar + br, ei = ai - bi;                  // 2E
     const double o_r = ai + bi, o_i = br - ar;                // 2O = -i (a - conj b)
@@ -314,7 +315,8 @@ template <int N>
 CHS_DEV void pre_pair(int k, const double2* __restrict__ om, const double (&c)[4], double& ar, double& ai,
                       double& br, double& bi) {
     constexpr int M = N / 2;
-    const double2 t = __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    // om[N + k] repeats om[4k] in contiguous order for the line-major geometry (adjacent lanes = adjacent k)
+    const double2 t = Geo<N>::LINE_MAJOR ? __ldg(om + N + k) : __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
     const double sc = 1.0 / (sqrt(2.0 / N) * N);              // 1/(2 s M)
     const double vr = wk.x * c[0] - wk.y * c[1], vi = -wk.x * c[1] - wk.y * c[0];       // conj(wk)(c0 - i c1)
     const double v2r = wm.x * c[2] - wm.y * c[3], v2i = -wm.x * c[3] - wm.y * c[2];
