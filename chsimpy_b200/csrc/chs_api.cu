@@ -156,7 +156,7 @@ static void fill_twiddles(int N, std::vector<double2>& tw) {
     const long double pi = 3.14159265358979323846264338327950288L;
     std::vector<double2> nat(M);
     for (int m = 0; m < M; ++m) { const long double a = -2.0L * pi * m / M; nat[m] = make_double2((double)cosl(a), (double)sinl(a)); }
-    const bool line_major = (N >= 2048) || (CHS_WARP_LINES && N >= 256 && N <= 1024);
+    const bool line_major = (N >= 2048) || (CHS_WARP_LINES && N >= 256 && N <= 1024) || CHS_STAGED_TABLES;   // = Geo<N>::STAGED_TABLES
     tw.assign(M, make_double2(0.0, 0.0));
     if (!line_major) { tw = nat; return; }
     std::vector<int> rad; int lg = 0;

@@ -861,7 +861,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                         double2 wv[R0];
                         if (!slow) {
 #pragma unroll
-                            for (int q = 1; q < R0; ++q) wv[q] = G::LINE_MAJOR ? __ldg(s_tw + (q - 1) * ST0 + j) : __ldg(s_tw + j * q);
+                            for (int q = 1; q < R0; ++q) wv[q] = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : __ldg(s_tw + j * q);
                         }
 #pragma unroll
                         for (int q = 0; q < R0; ++q) {

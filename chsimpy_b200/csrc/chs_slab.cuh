@@ -166,7 +166,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                     dft<R0, false>(xr, xi);
 #pragma unroll
                     for (int q = 1; q < R0; ++q) {
-                        const double2 w = G::LINE_MAJOR ? __ldg(a.tw + (q - 1) * ST0 + j) : __ldg(a.tw + j * q);
+                        const double2 w = G::STAGED_TABLES ? __ldg(a.tw + (q - 1) * ST0 + j) : __ldg(a.tw + j * q);
                         const double x = xr[q], y = xi[q];
                         xr[q] = x * w.x - y * w.y;
                         xi[q] = x * w.y + y * w.x;

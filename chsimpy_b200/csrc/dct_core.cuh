@@ -80,6 +80,14 @@ struct Geo {
     // loads its own entry and the L1 pipe saturates (l1tex 70-84 %).  Off by default.
     static constexpr bool WARP_LINES = CHS_WARP_LINES && (N >= 256) && (N <= 1024);
     static constexpr bool LINE_MAJOR = (N >= 2048) || WARP_LINES;
+#ifndef CHS_STAGED_TABLES
+#define CHS_STAGED_TABLES 0
+#endif
+    // twiddles read from per-stage tables (Rad<M>::tws_off) and the contiguous copy of om[4k]: the
+    // entries adjacent lanes need are adjacent in memory.  Always on for the line-major geometry; for the
+    // point-major one (4 distinct entries per warp load) measured 216.5 k vs 222 k sim-steps/s at N=512,
+    // batch 1024 (-DCHS_STAGED_TABLES=1), so the natural tables stay the default there
+    static constexpr bool STAGED_TABLES = LINE_MAJOR || CHS_STAGED_TABLES;
     static constexpr int LPC = LINE_MAJOR ? 1 : LINES + 1;     // point pitch
     // first radix 8: the top 3 position bits; 4: top 2 bits + the low bit of the next digit (x4);
     // 2: the low 2 bits of the second digit + the top bit (x4)
@@ -233,7 +241,7 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
         if (st > 1) {
 #pragma unroll
             for (int p = 1; p < r; ++p) {
-                const double2 w = G::LINE_MAJOR ? __ldg(tw + Rad<M>::tws_off(S) + (p - 1) * st + j) : __ldg(tw + j * p * (M / Lb));
+                const double2 w = G::STAGED_TABLES ? __ldg(tw + Rad<M>::tws_off(S) + (p - 1) * st + j) : __ldg(tw + j * p * (M / Lb));
                 const double a = xr[i][p], b = xi[i][p];
                 if (!INV) { xr[i][p] = a * w.x - b * w.y; xi[i][p] = a * w.y + b * w.x; }
                 else      { xr[i][p] = a * w.x + b * w.y; xi[i][p] = b * w.x - a * w.y; }     // conj(w)
@@ -286,7 +294,7 @@ CHS_DEV void post_pair(int k, const double2* __restrict__ om, double ar, double 
                        double (&c)[4]) {
     constexpr int M = N / 2;
     // om[N + k] repeats om[4k] in contiguous order for the line-major geometry (adjacent lanes = adjacent k)
-    const double2 t = Geo<N>::LINE_MAJOR ? __ldg(om + N + k) : __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    const double2 t = Geo<N>::STAGED_TABLES ? __ldg(om + N + k) : __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
     const double sc = 0.5 * sqrt(2.0 / N);
     const double er = ar + br, ei = ai - bi;                  // 2E
     const double o_r = ai + bi, o_i = br - ar;                // 2O = -i (a - conj b)
@@ -316,7 +324,7 @@ CHS_DEV void pre_pair(int k, const double2* __restrict__ om, const double (&c)[4
                       double& br, double& bi) {
     constexpr int M = N / 2;
     // om[N + k] repeats om[4k] in contiguous order for the line-major geometry (adjacent lanes = adjacent k)
-    const double2 t = Geo<N>::LINE_MAJOR ? __ldg(om + N + k) : __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    const double2 t = Geo<N>::STAGED_TABLES ? __ldg(om + N + k) : __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
     const double sc = 1.0 / (sqrt(2.0 / N) * N);              // 1/(2 s M)
     const double vr = wk.x * c[0] - wk.y * c[1], vi = -wk.x * c[1] - wk.y * c[0];       // conj(wk)(c0 - i c1)
     const double v2r = wm.x * c[2] - wm.y * c[3], v2i = -wm.x * c[3] - wm.y * c[2];
