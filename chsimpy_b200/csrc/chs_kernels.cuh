@@ -1196,8 +1196,17 @@ CHS_KERNEL void k_row_means(const double* in, long long cols, double* out) {
     CHS_SMEM_DECL
     double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);
     const double* p = in + (size_t)blockIdx.x * cols;
-    double s = 0;
-    for (long long i = threadIdx.x; i < cols; i += blockDim.x) s += p[i];
+    // 8 independent partial sums per thread: the loads of a batch are in flight together
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long nt = blockDim.x;
+    for (long long i0 = threadIdx.x; i0 < cols; i0 += 8 * nt) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long i = i0 + j * nt;
+            if (i < cols) acc[j] += p[i];
+        }
+    }
+    const double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     red[threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
