@@ -257,6 +257,10 @@ def test_cli_and_simulator_chunked(tmp_path, monkeypatch):
     U = ch.utils.csv_import_matrix("t1.solution.U.csv")
     assert np.allclose(U, sol.U, rtol=0, atol=1e-15)
     assert os.path.exists("t1.solution.yaml") and os.path.exists("t1.solution.E2.csv")
+    # the module entry point itself, in-process
+    from chsimpy_b200 import __main__ as cli_main
+    sol_cli = cli_main.run(["-N", "128", "-n", "61", "--full-sim", "--no-gui", "-K", "3e-4"])
+    assert sol_cli.computed_steps == 61 and np.array_equal(sol_cli.E, sol.E)
     # chunked: a view is "required" (png) -> headless stand-in, solve in chunks of 20
     p2 = ch.CLIParser().get_parameters(["-N", "128", "-n", "60", "--full-sim", "--no-gui", "--png", "--update-every", "20",
                                         "-K", "3e-4"])
