@@ -175,8 +175,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 stepper has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (no "NCCL version ..." banner)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs (its version banner) go to stdout by default: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, K, W = args.batch, args.steps, args.warmup
 
