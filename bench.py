@@ -175,8 +175,19 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 stepper has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL logs (its version banner) go to stdout by default: keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator is created: send fd 1 to stderr
+        # for that moment so that stdout carries nothing but the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     B, K, W = args.batch, args.steps, args.warmup
 
     # ---- members of this rank (weak scaling: B per GPU, run ids rank*B .. rank*B+B-1)
