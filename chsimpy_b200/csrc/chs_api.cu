@@ -36,6 +36,7 @@ struct chs_solver {
     double2* om;
     double* lam;
     double* gsin;
+    double2* lamg;
     int* kof;
     double2* logtab;
     int* index;
@@ -86,7 +87,7 @@ static int drain_events(chs_solver* s) {
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t sims, part, colpart, tw, om, lam, gsin, kof, logtab, index, mean, cm, ct, total;
+    size_t sims, part, colpart, tw, om, lam, gsin, lamg, kof, logtab, index, mean, cm, ct, total;
 };
 static bool fft_supports(int N) { return N == 32 || N == 64 || N == 128 || N == 256 || N == 512 || N == 1024; }
 static bool gemm_supports(int N) { return N >= GEMM_MIN_N && N <= GEMM_MAX_N; }
@@ -114,6 +115,7 @@ static Layout layout(int N, int batch) {
     L.om = o; o = align_up(o + sizeof(double2) * (size_t)(N + N / 4));      // om[N] + the contiguous copy of om[4k], k < N/4
     L.lam = o; o = align_up(o + sizeof(double) * (size_t)N);
     L.gsin = o; o = align_up(o + sizeof(double) * (size_t)N);
+    L.lamg = o; o = align_up(o + sizeof(double2) * (size_t)(3 * (N / 4) + 3));
     L.kof = o; o = align_up(o + sizeof(int) * (size_t)N);
     L.logtab = o; o = align_up(o + sizeof(double2) * (size_t)LOG_TABLE_N);
     L.index = o; o = align_up(o + sizeof(int) * (size_t)batch);
@@ -148,6 +150,59 @@ extern "C" int64_t chs_workspace_bytes(int32_t N, int32_t batch) {
         default: return fail("unsupported N"); \
     }
 
+
+// radix plan of the M-point FFT: the host mirror of Rad<M> (dct_core.cuh)
+static std::vector<int> plan_radices(int M) {
+    std::vector<int> rad;
+    int lg = 0;
+    while ((1 << lg) < M) ++lg;
+    const int rem = lg % 3, nst = lg / 3 + (rem ? 1 : 0);
+    const bool last4 = CHS_LAST4 && rem == 2 && M <= 512;
+    for (int s = 0; s < nst; ++s) rad.push_back(last4 ? (s == nst - 1 ? 4 : 8) : ((rem != 0 && s == 0) ? (1 << rem) : 8));
+    return rad;
+}
+
+// post/pre tables (dct_core.cuh): om[m] = sc exp(-i pi m/(2N)), m < N, sc = sqrt(2/N)/2; om[N + k] = exp(-2 pi i k/N), k < N/4
+static void fill_om(int N, std::vector<double2>& om) {
+    const long double pi = 3.14159265358979323846264338327950288L;
+    const long double sc = sqrtl(2.0L / N) * 0.5L;
+    om.assign((size_t)N + N / 4, make_double2(0.0, 0.0));
+    for (int m = 0; m < N; ++m) {
+        const long double a = -pi * m / (2.0L * N);
+        om[m] = make_double2((double)(sc * cosl(a)), (double)(sc * sinl(a)));
+    }
+    for (int k = 0; k < N / 4; ++k) {
+        const long double a = -2.0L * pi * k / N;
+        om[N + k] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+}
+
+// packed per-item table of the spectral update (ColMid): for k < M/2 three double2
+//   {lam[k], lam[N-k]}, {lam[M-k], lam[M+k]}, {g[k], g[M-k]}       (k = 0: rows 0, M, M/2, 3M/2; g = {0, 1/2})
+static void fill_lamg(int N, const double* lam, const std::vector<double>& gs, std::vector<double2>& t) {
+    const int M = N / 2;
+    t.assign((size_t)3 * (M / 2), make_double2(0.0, 0.0));
+    for (int k = 0; k < M / 2; ++k) {
+        const int r0 = k, r1 = (k == 0) ? M : N - k, r2 = (k == 0) ? M / 2 : M - k, r3 = (k == 0) ? M + M / 2 : M + k;
+        t[3 * k] = make_double2(lam[r0], lam[r1]);
+        t[3 * k + 1] = make_double2(lam[r2], lam[r3]);
+        t[3 * k + 2] = make_double2(gs[r0], gs[r2]);
+    }
+}
+
+// slot -> frequency map of the plan: slot 2 pos(k) holds k, slot 2 pos(k) + 1 holds N - k (k = 0: M)
+static void fill_kof(int N, std::vector<int>& kof) {
+    const int M = N / 2;
+    const std::vector<int> rad = plan_radices(M);
+    kof.assign(N, 0);
+    for (int k = 0; k < M; ++k) {
+        int pos = 0, Lb = M, kk = k;
+        for (int r : rad) { pos += (kk % r) * (Lb / r); kk /= r; Lb /= r; }
+        kof[2 * pos] = k;
+        kof[2 * pos + 1] = (k == 0) ? M : N - k;
+    }
+}
+
 // FFT twiddles for the kernels of size N: the natural table tw[m] = exp(-2 pi i m / M) for the point-major
 // tile geometry, the per-stage tables of Rad<M>::tws_off (same values, warp-contiguous order) for the
 // line-major one.  Always fewer than M entries.
@@ -159,10 +214,7 @@ static void fill_twiddles(int N, std::vector<double2>& tw) {
     const bool line_major = (N >= 2048) || (CHS_WARP_LINES && N >= 256 && N <= 1024) || CHS_STAGED_TABLES;   // = Geo<N>::STAGED_TABLES
     tw.assign(M, make_double2(0.0, 0.0));
     if (!line_major) { tw = nat; return; }
-    std::vector<int> rad; int lg = 0;
-    while ((1 << lg) < M) ++lg;
-    if (lg % 3) rad.push_back(1 << (lg % 3));
-    for (int i = 0; i < lg / 3; ++i) rad.push_back(8);
+    const std::vector<int> rad = plan_radices(M);
     size_t o = 0; int Lb = M;
     for (size_t s = 0; s + 1 < rad.size(); ++s) {
         const int r = rad[s], st = Lb / r;
@@ -225,7 +277,7 @@ static KArgs base_args(chs_solver* s) {
     a.rows = s->rows; a.rows_cap = s->rows_cap;
     a.part = s->part; a.colpart = s->colpart;
     a.tw = s->tw; a.om = s->om; a.lam = s->lam; a.logtab = s->logtab;
-    a.gsin = s->gsin; a.kof = s->kof;
+    a.gsin = s->gsin; a.kof = s->kof; a.lamg = s->lamg;
     a.mean_host = s->mean;
     return a;
 }
@@ -251,6 +303,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     s->lam = (double*)(w + L.lam);
     s->logtab = (double2*)(w + L.logtab);
     s->gsin = (double*)(w + L.gsin);
+    s->lamg = (double2*)(w + L.lamg);
     s->kof = (int*)(w + L.kof);
     s->index = (int*)(w + L.index);
     s->mean = (double*)(w + L.mean);
@@ -274,27 +327,13 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     const long double pi = 3.14159265358979323846264338327950288L;
     if (!s->gemm) {
         fill_twiddles(N, tw);
-        for (int m = 0; m < N; ++m) {
-            const long double a = -pi * m / (2.0L * N);
-            om[m] = make_double2((double)cosl(a), (double)sinl(a));
-        }
-        for (int k = 0; k < N / 4; ++k) om[N + k] = om[4 * k];
+        fill_om(N, om);
         // gradient-energy weights sin^2(pi k/N) and the slot -> frequency map of the FFT plan
         for (int k = 0; k < N; ++k) {
             const long double sn = sinl(pi * k / N);
             gs[k] = (double)(sn * sn);
         }
-        std::vector<int> rad;                       // same plan as Rad<M> (dct_core.cuh)
-        int lg = 0;
-        while ((1 << lg) < M) ++lg;
-        if (lg % 3) rad.push_back(1 << (lg % 3));
-        for (int i = 0; i < lg / 3; ++i) rad.push_back(8);
-        for (int k = 0; k < M; ++k) {
-            int pos = 0, Lb = M, kk = k;
-            for (int r : rad) { pos += (kk % r) * (Lb / r); kk /= r; Lb /= r; }
-            kof[2 * pos] = k;
-            kof[2 * pos + 1] = (k == 0) ? M : N - k;
-        }
+        fill_kof(N, kof);
     } else {
         // orthonormal DCT-II matrix C[k][n] = f_k cos(pi k (2n+1) / (2N)), zero padded to N8 x N8
         const int n8 = s->N8;
@@ -326,6 +365,11 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    std::vector<double2> lamg;
+    if (!s->gemm) {
+        fill_lamg(N, lambda_host, gs, lamg);
+        ok &= cudaMemcpyAsync(s->lamg, lamg.data(), sizeof(double2) * lamg.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    }
     if (s->gemm) {
         ok &= cudaMemcpyAsync(s->Cm, cm.data(), sizeof(double) * cm.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
         ok &= cudaMemcpyAsync(s->Ct, ct.data(), sizeof(double) * ct.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
@@ -385,6 +429,7 @@ extern "C" int chs_set_params(chs_solver* s, int32_t sim, const chs_params* p) {
     h.p = *p;
     h.delt = p->delt;
     h.delt_coef = p->delt;
+    sim_derive(h);
     CHS_CUDA(cudaMemcpyAsync(s->sims + sim, &h, sizeof(Sim), cudaMemcpyHostToDevice, s->stream));
     CHS_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
@@ -676,6 +721,7 @@ struct chs_slab {
     double* vec;         // [R_NVAL]
     double2 *tw, *om, *logtab;
     double *lam, *gsin;
+    double2* lamg;
     int* kof;
     Sim hsim;
     long long launches;
@@ -685,7 +731,7 @@ static const int SLAB_UPD_BLOCKS = 1184, SLAB_PREP_BLOCKS = 1184;
 
 static int slab_lines(int N) { return geo_lines(N); }
 
-struct SlabLayout { size_t sim, part, part_ge, yedge, vec, tw, om, lam, gsin, kof, logtab, total; };
+struct SlabLayout { size_t sim, part, part_ge, yedge, vec, tw, om, lam, gsin, lamg, kof, logtab, total; };
 static SlabLayout slab_layout(int N, int rows) {
     SlabLayout L; size_t o = 0;
     const int ntiles = rows / slab_lines(N);
@@ -699,6 +745,7 @@ static SlabLayout slab_layout(int N, int rows) {
     L.om = o; o = align_up(o + sizeof(double2) * (size_t)(N + N / 4));      // om[N] + the contiguous copy of om[4k], k < N/4
     L.lam = o; o = align_up(o + sizeof(double) * (size_t)N);
     L.gsin = o; o = align_up(o + sizeof(double) * (size_t)N);
+    L.lamg = o; o = align_up(o + sizeof(double2) * (size_t)(3 * (N / 4) + 3));
     L.kof = o; o = align_up(o + sizeof(int) * (size_t)N);
     L.logtab = o; o = align_up(o + sizeof(double2) * (size_t)LOG_TABLE_N);
     L.total = o;
@@ -755,29 +802,20 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     s->yedge = (double*)(w + L.yedge); s->vec = (double*)(w + L.vec);
     s->tw = (double2*)(w + L.tw); s->om = (double2*)(w + L.om); s->lam = (double*)(w + L.lam);
     s->gsin = (double*)(w + L.gsin); s->kof = (int*)(w + L.kof); s->logtab = (double2*)(w + L.logtab);
+    s->lamg = (double2*)(w + L.lamg);
     s->launches = 0; s->upd_used = 0;
     std::memset(&s->hsim, 0, sizeof(Sim));
     s->hsim.p = *p; s->hsim.delt = p->delt; s->hsim.delt_coef = p->delt;
+    sim_derive(s->hsim);
     const int M = N / 2;
     std::vector<double2> tw(M), om(N + N / 4), lt(LOG_TABLE_N);
     std::vector<double> gs(N);
     std::vector<int> kof(N);
     const long double pi = 3.14159265358979323846264338327950288L;
     fill_twiddles(N, tw);
-    for (int m = 0; m < N; ++m) { const long double a = -pi * m / (2.0L * N); om[m] = make_double2((double)cosl(a), (double)sinl(a)); }
-    for (int k = 0; k < N / 4; ++k) om[N + k] = om[4 * k];
+    fill_om(N, om);
     for (int k = 0; k < N; ++k) { const long double sn = sinl(pi * k / N); gs[k] = (double)(sn * sn); }
-    {
-        std::vector<int> rad; int lg = 0;
-        while ((1 << lg) < M) ++lg;
-        if (lg % 3) rad.push_back(1 << (lg % 3));
-        for (int i = 0; i < lg / 3; ++i) rad.push_back(8);
-        for (int k = 0; k < M; ++k) {
-            int pos = 0, Lb = M, kk = k;
-            for (int r : rad) { pos += (kk % r) * (Lb / r); kk /= r; Lb /= r; }
-            kof[2 * pos] = k; kof[2 * pos + 1] = (k == 0) ? M : N - k;
-        }
-    }
+    fill_kof(N, kof);
     for (int i = 0; i < LOG_TABLE_N; ++i) {
         const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << 45), b1 = LOG_OFF + ((unsigned long long)(i + 1) << 45);
         double z0, z1; std::memcpy(&z0, &b0, 8); std::memcpy(&z1, &b1, 8);
@@ -791,6 +829,9 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    std::vector<double2> lamg;
+    fill_lamg(N, lambda_host, gs, lamg);
+    ok &= cudaMemcpyAsync(s->lamg, lamg.data(), sizeof(double2) * lamg.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->sim, &s->hsim, sizeof(Sim), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaStreamSynchronize(s->stream) == cudaSuccess;
     int rc = 0;
@@ -824,7 +865,7 @@ static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int r
     a.src = src; a.dst = dst; a.Uout = s->U + (size_t)local0 * N; a.rows = rows; a.row_base = row_base; a.diag = diag; a.mean_u = mean_u;
     a.tile0 = local0 / G::LINES; a.tiles_total = s->rows / G::LINES;
     a.part = s->part; a.S = s->sim; a.tw = s->tw; a.om = s->om; a.logtab = s->logtab;
-    a.H = H; a.part_ge = s->part_ge; a.lam = s->lam; a.gsin = s->gsin; a.kof = s->kof;
+    a.H = H; a.part_ge = s->part_ge; a.lam = s->lam; a.gsin = s->gsin; a.kof = s->kof; a.lamg = s->lamg;
     const int ntiles = rows / G::LINES;
 #ifdef CHS_EMU
     const dim3 grid(ntiles < 3 ? ntiles : 3);

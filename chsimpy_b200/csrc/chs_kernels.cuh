@@ -43,17 +43,42 @@ namespace chs {
 //   P_GYE / P_GXE : 3/4 * edge terms from k_col / k_row
 enum { P_GE = 0, P_GYE, P_GXE, P_F, P_ABS, P_MU2, P_CNT, P_NSLOT };
 
+// per-simulation constants the hot loops need, derived once (sim_derive) so that no kernel divides
+// or re-reads chs_params: 16 doubles, copied into shared memory with the tile (Geo::OFF_SIM)
+struct SimK {
+    double RT, mBRT, A0, A1, m2A1, threshold, B, jitter, delt_max;
+    double lam1, lam2;           // utils.py:41-42 with the current delt_coef
+    double hat00;                // hat_U[0,0] of the state (conserved by the update, Q4): mean(U) = hat00/N
+    double rsv[4];
+};
+static_assert(sizeof(SimK) == CHS_SIMK * sizeof(double), "SimK size");
+
 // device-resident image of one simulation
 struct Sim {
     chs_params p;
+    SimK k;
     double delt, delt_coef, time_delta_sum, time_passed, tau0, t0;
     double e2_first, e2_prev, mu2_pending, ra;
+    double mean_u;               // mean of the field whose sums are pending (F correction -RT*B*sum(U), see physics())
     long long computed_steps;
     long long rows_written;
     int skip_check, stop_reason, halted, u_stale;
     unsigned ticket;
     int pad_;
 };
+static_assert(sizeof(chs_params) % 16 == 0 && sizeof(Sim) % 16 == 0, "Sim::k must be 16-byte aligned");
+
+// fills the derived constants from p and delt_coef (host: chs_set_params; device: k_begin, step_control)
+CHS_HD void sim_derive_lam(Sim& S) {
+    const double delx2 = S.p.delx * S.p.delx;
+    S.k.lam1 = S.delt_coef / delx2;                           // utils.py:41-42
+    S.k.lam2 = S.p.kappa_tilde * S.k.lam1 / delx2;
+}
+CHS_HD void sim_derive(Sim& S) {
+    S.k.RT = S.p.RT; S.k.mBRT = -S.p.BRT; S.k.A0 = S.p.A0; S.k.A1 = S.p.A1; S.k.m2A1 = -2.0 * S.p.A1;
+    S.k.threshold = S.p.threshold; S.k.B = S.p.B; S.k.jitter = S.p.jitter; S.k.delt_max = S.p.delt_max;
+    sim_derive_lam(S);
+}
 
 enum { COL_FWD = 0, COL_STEP = 1, COL_INV = 2 };
 enum { ROW_FWD_U = 0, ROW_FWD_MU = 1, ROW_STEP = 2, ROW_INV = 3 };
@@ -75,6 +100,7 @@ struct KArgs {
     const double2* om;           // exp(-i pi m / (2N)), m < N
     const double* lam;           // 2 cos(pi k/(N-1)) - 2
     const double* gsin;          // sin^2(pi k / N)
+    const double2* lamg;         // per item k < M/2: {lam[k], lam[N-k]}, {lam[M-k], lam[M+k]}, {g[k], g[M-k]} (k = 0: rows 0, M, M/2, 3M/2)
     const int* kof;              // slot -> frequency
     const double2* logtab;       // fast_log table {1/c, log c}
     const double* noise;         // [N][N] uniform draws of this step, or null
@@ -146,20 +172,29 @@ CHS_DEV void reduce_final(double (&v)[NV], const double* scratch, int nthreads) 
     }
 }
 
-// asynchronous copy of the 2 KB fast_log table (complete after chs_cp_async_wait_all() + barrier)
+// asynchronous copy of the 2 KB fast_log table (complete after chs_cp_async_wait_all() + barrier);
+// entry i at t[i * G::LOG_STRIDE] (the pad slots of the point-major tile, see Geo::LOG_IN_PAD)
 template <class G>
 CHS_DEV double2* stage_logtab(double* sm, const double2* __restrict__ g, int tid) {
-    double2* t = reinterpret_cast<double2*>(sm + G::OFF_LOGTAB);
-    for (int i = tid; i < LOG_TABLE_N; i += G::NT) chs_cp_async16(t + i, g + i);
+    double2* t = reinterpret_cast<double2*>(sm + G::log_off());
+    for (int i = tid; i < LOG_TABLE_N; i += G::NT) chs_cp_async16(t + i * G::LOG_STRIDE, g + i);
     return t;
+}
+// asynchronous copy of the simulation's derived constants (SimK) to sm + G::OFF_SIM
+template <class G>
+CHS_DEV void stage_simk(double* sm, const Sim* S, int tid) {
+    const double2* g = reinterpret_cast<const double2*>(&S->k);
+    double2* d = reinterpret_cast<double2*>(sm + G::OFF_SIM);
+    for (int i = tid; i < CHS_SIMK / 2; i += G::NT) chs_cp_async16(d + i, g + i);
 }
 
 // ---------------------------------------------------------------------------------------
-// thermodynamics of one value (solver.py:166-175 and :218-221)
+// thermodynamics of one value (solver.py:166-175 and :218-221): cold paths (prepare, GEMM path)
+template <int LS = 1>
 CHS_DEV void thermo(double u, const chs_params& p, const double2* __restrict__ ltab, double& f, double& mu) {
     const double ui = 1.0 - u;
-    double lu = fast_log_unchecked(u, ltab), li = fast_log_unchecked(ui, ltab);
-    if (log_needs_slow_path(u) || log_needs_slow_path(ui)) {      // one (never taken) branch for both logarithms
+    double lu = log_abs_unchecked<LS>(u, ltab), li = log_abs_unchecked<LS>(ui, ltab);
+    if (!in_open_unit_interval(u)) {                              // one (never taken) branch for both logarithms
         lu = slow_log(u);
         li = slow_log(ui);
     }
@@ -167,6 +202,30 @@ CHS_DEV void thermo(double u, const chs_params& p, const double2* __restrict__ l
     const double uui = u * ui;
     f = p.RT * (u * (lu - p.B) + ui * li) + (p.A0 + p.A1 * d) * uui;
     mu = p.RT * (lu - li) - p.BRT + (p.A0 + p.A1 * d) * d - 2.0 * p.A1 * uui;
+}
+
+// The same for the hot loops, 37 FP64 instructions per value with the sums:
+//   mu  = RT (ln u - ln(1-u)) - BRT + g d - 2 A1 u(1-u),   g = A0 + A1 d, d = 1 - 2u
+//   sum f = RT [sum u ln u + sum (1-u) ln(1-u)] + sum g u(1-u)  - RT B sum u
+// fa, fb, fp accumulate the three sums; the last term needs no per-value work when the caller knows
+// sum u (the batched kernels: N^2 * mean(U), conserved, Q4 -- step_control subtracts it); BTERM = true
+// folds it into fa instead (slab kernels).  k: SimK constants (registers).
+struct ThermoK { double RT, mBRT, A0, A1, m2A1, B; };
+template <int LS, bool BTERM>
+CHS_DEV double thermo_acc(double u, const ThermoK& k, const double2* __restrict__ ltab, double& fa, double& fb, double& fp) {
+    const double ui = 1.0 - u;
+    double lu = log_abs_unchecked<LS>(u, ltab), li = log_abs_unchecked<LS>(ui, ltab);
+    if (!in_open_unit_interval(u)) {
+        lu = slow_log(u);
+        li = slow_log(ui);
+    }
+    const double d = ui - u;
+    const double uui = u * ui;
+    const double g = chs_fma(k.A1, d, k.A0);
+    fa = chs_fma(u, BTERM ? lu - k.B : lu, fa);
+    fb = chs_fma(ui, li, fb);
+    fp = chs_fma(g, uui, fp);
+    return chs_fma(k.RT, lu - li, chs_fma(k.m2A1, uui, chs_fma(g, d, k.mBRT)));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -216,7 +275,8 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
         const double L2sq = p.L * p.L;
         const double grad2 = (acc[P_GE] + acc[P_GYE] + acc[P_GXE]) / (p.delx * p.delx);
         const double E2 = 0.5 * p.Amr * p.kappa_tilde * L2sq * (grad2 / N2);
-        const double E = p.Amr * L2sq * (acc[P_F] / N2) + E2;
+        // P_F holds sum f + RT B sum U (physics()); sum U = N^2 mean(U) is known exactly (Q4)
+        const double E = p.Amr * L2sq * (acc[P_F] / N2 - p.RT * p.B * S->mean_u) + E2;
         const double PS = acc[P_ABS] / N2;
         const double L2 = sqrt(S->mu2_pending) / N2;
         const double SA = acc[P_CNT] / N2;
@@ -264,6 +324,7 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
         if (dnew / S->delt > 1.15) S->delt = 0.75 * S->delt + 0.25 * dnew;
         else S->delt = dnew;
         S->delt_coef = S->delt;
+        sim_derive_lam(*S);
     }
     S->time_delta_sum += S->delt;
     S->time_passed = S->time_delta_sum / p.M_tilde;
@@ -401,61 +462,96 @@ CHS_DEV void row_tile_store_phys(const double* sm, double* __restrict__ g, int t
 }
 
 // ---------------------------------------------------------------------------------------
-// The 8 work items of a thread in the fused last stage.  A/B = the two 8-point blocks
-// (natural order within the block: frequency rho + (M/8)*c).  Item c of group 1 couples
-// Z[k] = A[c] with Z[M-k] = B[7-c], k = rho_a + (M/8)c; group 2 the same with A and B
-// swapped and rho_b; always k < M/2.  Thread 0 owns the two self-paired blocks (rho = 0 and
-// M/16): swapping their upper halves first makes the same pairing pattern apply, with
-// k = 0 (Z[0] with Z[M/2]) as the one special item.
+// The work items of one pairing unit (Pairing<N>, dct_core.cuh) in the fused last stage.  A/B = the two
+// RL-point blocks (natural order within the block: frequency rho + Q c).  Item c of group 1 couples
+// Z[k] = A[c] with Z[M-k] = B[RL-1-c], k = rho_a + Q c, c < RL/2; group 2 the same with A and B swapped
+// and rho_b; always k < M/2.  Unit 0 holds the two self-paired blocks (rho = 0 and Q/2): swapping their
+// upper halves first makes the same pairing pattern apply, with k = 0 (Z[0] with Z[M/2]) as the one
+// special item.
 //   f.begin(k0)                      first item's frequency (lets f start its global loads)
 //   f.first(k, knext, X, Y)          item that may be the special one (k == 0)
 //   f.pair(k, knext, X, Y)           knext < 0: no further item
 template <int N, class F>
-CHS_DEV void for_each_item(int t, int rho_a, int rho_b, double (&ar)[8], double (&ai)[8], double (&br)[8],
-                           double (&bi)[8], F& f) {
-    constexpr int Q = N / 16;                       // M/8
-    if (t == 0) {
+CHS_DEV void unit_items(bool self, int rho_a, int rho_b, int k_after, double (&ar)[Pairing<N>::RL], double (&ai)[Pairing<N>::RL],
+                        double (&br)[Pairing<N>::RL], double (&bi)[Pairing<N>::RL], F& f) {
+    using P = Pairing<N>;
+    constexpr int RL = P::RL, H = P::H, Q = P::Q;
+    if (self) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            double (&A)[8] = h ? ai : ar;
-            double (&B)[8] = h ? bi : br;
-            const double a4 = A[4], a5 = A[5], a6 = A[6], a7 = A[7];
-            A[4] = B[4]; A[5] = B[5]; A[6] = B[6]; A[7] = B[7];
-            B[4] = a5; B[5] = a6; B[6] = a7; B[7] = a4;
+            double (&A)[RL] = h ? ai : ar;
+            double (&B)[RL] = h ? bi : br;
+            const double ah = A[H];
+#pragma unroll
+            for (int j = 0; j < H - 1; ++j) { const double a = A[H + 1 + j]; A[H + j] = B[H + j]; B[H + j] = a; }
+            A[RL - 1] = B[RL - 1];
+            B[RL - 1] = ah;
         }
     }
-    f.begin(rho_a);
-    f.first(rho_a, rho_a + Q, ar[0], ai[0], br[7], bi[7]);
+    f.first(rho_a, rho_a + Q, ar[0], ai[0], br[RL - 1], bi[RL - 1]);
 #pragma unroll
-    for (int c = 1; c < 4; ++c)
-        f.pair(rho_a + Q * c, (c < 3) ? rho_a + Q * (c + 1) : rho_b, ar[c], ai[c], br[7 - c], bi[7 - c]);
+    for (int c = 1; c < H; ++c)
+        f.pair(rho_a + Q * c, (c < H - 1) ? rho_a + Q * (c + 1) : rho_b, ar[c], ai[c], br[RL - 1 - c], bi[RL - 1 - c]);
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-        f.pair(rho_b + Q * c, (c < 3) ? rho_b + Q * (c + 1) : -1, br[c], bi[c], ar[7 - c], ai[7 - c]);
-    if (t == 0) {
+    for (int c = 0; c < H; ++c)
+        f.pair(rho_b + Q * c, (c < H - 1) ? rho_b + Q * (c + 1) : k_after, br[c], bi[c], ar[RL - 1 - c], ai[RL - 1 - c]);
+    if (self) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            double (&A)[8] = h ? ai : ar;
-            double (&B)[8] = h ? bi : br;
-            const double b4 = B[4], b5 = B[5], b6 = B[6], b7 = B[7];
-            B[4] = A[4]; B[5] = A[5]; B[6] = A[6]; B[7] = A[7];
-            A[5] = b4; A[6] = b5; A[7] = b6; A[4] = b7;
+            double (&A)[RL] = h ? ai : ar;
+            double (&B)[RL] = h ? bi : br;
+            const double bl = B[RL - 1];
+            B[RL - 1] = A[RL - 1];
+#pragma unroll
+            for (int j = H - 2; j >= 0; --j) { const double b2 = B[H + j]; B[H + j] = A[H + j]; A[H + 1 + j] = b2; }
+            A[H] = bl;
         }
     }
 }
 
-template <int N>
-CHS_DEV void load_block(const double2* scl, int base, double (&xr)[8], double (&xi)[8]) {
+template <int N, int R>
+CHS_DEV void load_block(const double2* scl, int base, double (&xr)[R], double (&xi)[R]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < R; ++c) {
         const double2 v = scl[Geo<N>::idx(base) + c * Geo<N>::LPC];
         xr[c] = v.x; xi[c] = v.y;
     }
 }
-template <int N>
-CHS_DEV void store_block(double2* scl, int base, const double (&xr)[8], const double (&xi)[8]) {
+template <int N, int R>
+CHS_DEV void store_block(double2* scl, int base, const double (&xr)[R], const double (&xi)[R]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) scl[Geo<N>::idx(base) + c * Geo<N>::LPC] = make_double2(xr[c], xi[c]);
+    for (int c = 0; c < R; ++c) scl[Geo<N>::idx(base) + c * Geo<N>::LPC] = make_double2(xr[c], xi[c]);
+}
+
+// One fused pass over the pairing units of thread t:
+//   [FWD: last forward FFT stage] -> items (post / update / pre in registers, functor f) -> [INV: first
+//   inverse FFT stage], in place in the tile.  Units are processed one after the other (2 * RL complex
+//   points live).
+template <int N, bool FWD, bool INV, class F>
+CHS_DEV void fused_units(double2* scl, int t, F& f) {
+    using P = Pairing<N>;
+    constexpr int M = N / 2, RL = P::RL;
+    f.begin(t);
+#pragma unroll 1
+    for (int i = 0; i < P::NU; ++i) {
+        const int u = t + i * P::TPL;
+        const int rho_a = u, rho_b = (u == 0) ? P::Q / 2 : P::Q - u;
+        const int base_a = freq_pos<M>(rho_a), base_b = freq_pos<M>(rho_b);
+        double ar[RL], ai[RL], br[RL], bi[RL];
+        load_block<N, RL>(scl, base_a, ar, ai);
+        load_block<N, RL>(scl, base_b, br, bi);
+        if (FWD) {
+            dft<RL, false>(ar, ai);
+            dft<RL, false>(br, bi);
+        }
+        unit_items<N>(u == 0, rho_a, rho_b, (i + 1 < P::NU) ? u + P::TPL : -1, ar, ai, br, bi, f);
+        if (INV) {
+            dft<RL, true>(ar, ai);
+            dft<RL, true>(br, bi);
+        }
+        store_block<N, RL>(scl, base_a, ar, ai);
+        store_block<N, RL>(scl, base_b, br, bi);
+    }
 }
 
 // in-place slot convention of the row kernels: element pos(k) = (C[k], C[N-k])
@@ -498,13 +594,13 @@ struct RowPre {
 template <int N, int MODE>
 struct ColMid {
     const double2* om;
-    const double* lam;
-    const double* gsin;
+    const double2* lamg;         // packed per-item table (KArgs::lamg)
     double* hat;                 // + column
     const double* hat_in;        // + column (COL_INV)
     int hstride;                 // LINES (tile-major hat_U) or N (natural row-major, stand-alone transforms)
     double lam1, lam2, lamx, gx;
     double ge;
+    double* hat00;               // COL_FWD on the state: where C[0,0] is recorded (Sim::k.hat00), else null
     double hn[4];                // hat_U of the next item (prefetched one item ahead)
     CHS_MEM void rows_of(int k, int (&idx)[4]) {
         constexpr int M = N / 2;
@@ -534,18 +630,21 @@ struct ColMid {
         if (MODE == COL_FWD) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) hat[(size_t)idx[j] * hstride] = c[j];
+            if (k == 0 && hat00) *hat00 = c[0];
         } else if (MODE == COL_STEP) {
-            // g[k] = sin^2(pi k/N): g[N-k] = g[k], g[M-k] = g[M+k] = 1 - g[k]  (one lookup per item)
-            const double g0 = __ldg(gsin + idx[0]);
-            const double gs[4] = {g0, (k == 0) ? 1.0 : g0, (k == 0) ? 0.5 : 1.0 - g0, (k == 0) ? 0.5 : 1.0 - g0};
+            // one packed table entry per item: lam of the four rows, and g[k] = sin^2(pi k/N) with
+            // g[N-k] = g[k], g[M-k] = g[M+k] = 1 - g[k]  (k = 0: rows 0, M, M/2, 3M/2 -> 0, 1, 1/2, 1/2)
+            const double2 l01 = __ldg(lamg + 3 * k), l23 = __ldg(lamg + 3 * k + 1), gg = __ldg(lamg + 3 * k + 2);
+            const double lm[4] = {l01.x, l01.y, l23.x, l23.y};
+            const double gs[4] = {gg.x + gx, ((k == 0) ? 1.0 : gg.x) + gx, gg.y + gx, gg.y + gx};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const double leig = __ldg(lam + idx[j]) + lamx;
+                const double leig = lm[j] + lamx;
                 const double Se = __dmul_rn(lam1, leig);
                 const double CH = __dadd_rn(1.0, __dmul_rn(__dmul_rn(lam2, leig), leig));
                 const double hu = div_ge1(__dadd_rn(h[j], __dmul_rn(Se, c[j])), CH);
                 hat[(size_t)idx[j] * hstride] = hu;
-                ge += (gs[j] + gx) * (hu * hu);
+                ge = chs_fma(gs[j], hu * hu, ge);
                 c[j] = hu;
             }
         } else {
@@ -581,8 +680,6 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
     constexpr int NST = Rad<M>::nst;
     double2* sc = reinterpret_cast<double2*>(sm);
     const double2* __restrict__ s_tw = a.tw;
-    const double2* __restrict__ s_om = a.om;
-    const double* __restrict__ s_lam = a.lam;
     const int tid = threadIdx.x, l = G::line_of(tid), t = G::t_of(tid);
     double2* scl = sc + l * G::LOFF;
         const int si = w / G::NTILES, tile = w % G::NTILES, kx0 = tile * LINES;
@@ -604,9 +701,8 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
         int halted = 0;
         if (MODE == COL_STEP) {
             halted = S->halted;
-            const double delx2 = S->p.delx * S->p.delx;
-            lam1 = S->delt_coef / delx2;                          // utils.py:41-42
-            lam2 = S->p.kappa_tilde * lam1 / delx2;
+            lam1 = S->k.lam1;                                     // utils.py:41-42 (sim_derive_lam)
+            lam2 = S->k.lam2;
             const int kx = a.kof[kx0 + l];
             lamx = a.lam[kx];
             gxs = a.gsin[kx];
@@ -617,17 +713,8 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
             // -------- forward column DCT-II up to the last stage
             if (MODE != COL_INV) fft_fwd_range<N, 0, NST - 1, true>(scl, t, s_tw);
             // -------- fused: last forward stage + post + spectral update + pre + first inverse stage
-            int rho_a, rho_b, base_a, base_b;
-            unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-            double ar[8], ai[8], br[8], bi[8];
-            if (MODE != COL_INV) {
-                load_block<N>(scl, base_a, ar, ai);
-                load_block<N>(scl, base_b, br, bi);
-                dft<8, false>(ar, ai);
-                dft<8, false>(br, bi);
-            }
             ColMid<N, MODE> mid;
-            mid.om = s_om; mid.lam = s_lam; mid.gsin = a.gsin;
+            mid.om = a.om; mid.lamg = a.lamg;
             // hat_U is stored tile-major ([tile][ky][LINES]): the tile of a CTA is one contiguous block;
             // the stand-alone transforms use natural row-major arrays on the far side
             const bool nat = (MODE != COL_STEP) && a.natural;
@@ -638,12 +725,9 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
             mid.hat = ((MODE == COL_FWD && a.dst) ? a.dst : a.hatU) + toff;
             mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + toff;
             mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
-            for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, mid);
+            mid.hat00 = (MODE == COL_FWD && !a.dst && tile == 0 && l == 0) ? &S->k.hat00 : nullptr;
+            fused_units<N, MODE != COL_INV, MODE != COL_FWD>(scl, t, mid);
             if (MODE != COL_FWD) {
-                dft<8, true>(ar, ai);
-                dft<8, true>(br, bi);
-                store_block<N>(scl, base_a, ar, ai);
-                store_block<N>(scl, base_b, br, bi);
                 if (MODE == COL_STEP) {
                     const double v[1] = {mid.ge};
                     reduce_stage<1>(v, sm + G::OFF_RED, tid);
@@ -690,13 +774,18 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
 // ---------------------------------------------------------------------------------------
 // Per-element physics on the 2*R real values of one radix-R butterfly of stage 0
 // (positions c_q = j + q*st, re = v[2c], im = v[2c+1]):  U -> mu in place, sums in acc.
+// acc.fa/fb/fp: see thermo_acc (P_F = RT (fa + fb) + fp, without the -RT B sum U term unless BTERM).
 struct RowAcc {
-    double f, ab, mu2, ra;
+    double fa, fb, fp, ab, mu2, ra;
     int cnt;                     // values below the threshold (one FP64 compare + an integer add per value)
 };
-template <int N, int R>
-CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const chs_params& p, const double2* ltab,
-                     bool diag, double meanU, bool ra_line, double ra_mean, RowAcc& acc, double* edge /* line's 4 */) {
+struct PhysK {                   // constants of the loop, in registers
+    ThermoK th;
+    double threshold, meanU;
+};
+template <int N, int R, int LS, bool BTERM>
+CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const PhysK& k, const double2* ltab,
+                     bool diag, bool ra_line, double ra_mean, RowAcc& acc, double* edge /* line's 4 */) {
     constexpr int st = (N / 2) / R;
     if (diag) {
         if (j == 0) { edge[0] = xr[0]; edge[3] = xr[R / 2]; }                 // U[0], U[N-1]
@@ -707,15 +796,13 @@ CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const chs_params& 
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const double u = h ? xi[q] : xr[q];
-            double f, mu;
-            thermo(u, p, ltab, f, mu);
+            const double mu = thermo_acc<LS, BTERM>(u, k.th, ltab, acc.fa, acc.fb, acc.fp);
             if (diag) {
-                acc.f += f;
-                acc.ab += fabs(u - meanU);
-                acc.cnt += (u < p.threshold) ? 1 : 0;
+                acc.ab += fabs(u - k.meanU);
+                acc.cnt += (u < k.threshold) ? 1 : 0;
                 if (ra_line) acc.ra += fabs(u - ra_mean);
             }
-            acc.mu2 += mu * mu;
+            acc.mu2 = chs_fma(mu, mu, acc.mu2);
             if (h) xi[q] = mu; else xr[q] = mu;
         }
     }
@@ -751,7 +838,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
         const size_t off = (size_t)sim * N * N;
         // tile prologue: every global access is issued before the first dependent use
         if (MODE == ROW_STEP || MODE == ROW_INV) row_tile_load_slots_async<N>(sc, a.T + off + (size_t)row0 * N, tid);
-        const double hat00 = sums ? a.hatU[off] : 0.0;
+        if (control) stage_simk<G>(sm, S, tid);
         const bool ra_line = sums && (row0 + l == ra_row);
         const bool ra_tile = sums && (ra_row >= row0) && (ra_row < row0 + LINES);
         bool slow = false;                  // adaptive-dt column sums / jitter / prologue: unfused middle
@@ -774,19 +861,10 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
         if (!halted) {
             // ============= inverse half: T rows (slot order) -> U rows (Makhoul order in smem)
             if (MODE == ROW_STEP || MODE == ROW_INV) {
-                {   // fused: pre + first inverse stage (two 8-point blocks per thread)
-                    int rho_a, rho_b, base_a, base_b;
-                    unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-                    double ar[8], ai[8], br[8], bi[8];
-                    load_block<N>(scl, base_a, ar, ai);
-                    load_block<N>(scl, base_b, br, bi);
-                    if (ra_line && t == 0) ra_scr[0] = ar[0] * sqrt(1.0 / N);       // row mean = C[0]/sqrt(N)
+                if (ra_line && t == 0) ra_scr[0] = scl[G::idx(0)].x * sqrt(1.0 / N);   // row mean = C[0]/sqrt(N)
+                {   // fused: pre + first inverse stage
                     RowPre<N> pre{s_om};
-                    for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, pre);
-                    dft<8, true>(ar, ai);
-                    dft<8, true>(br, bi);
-                    store_block<N>(scl, base_a, ar, ai);
-                    store_block<N>(scl, base_b, br, bi);
+                    fused_units<N, false, true>(scl, t, pre);
                 }
                 line_barrier<N, true>();
                 fft_inv_range<N, 1, NST - 1, true>(scl, t, s_tw);
@@ -799,9 +877,10 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                 double* dstU = (a.dst ? a.dst : a.U) + off + (size_t)row0 * N;
                 row_tile_store_phys<N>(sm, dstU, tid);
             } else {
+                const double* K = sm + G::OFF_SIM;                 // SimK image (stage_simk)
                 // ============= jitter (solver.py:210-211): U += jitter*(2*noise - 1); U is state now
                 if (jit) {
-                    const double jv = S->p.jitter;
+                    const double jv = K[7];
                     const double* nz = a.noise + (size_t)row0 * N;
                     double* dstU = a.U + off + (size_t)row0 * N;
                     constexpr int CNT = LINES * N / NT, UNR = (CNT % 8 == 0) ? 8 : 1;
@@ -841,9 +920,11 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                 }
                 // ============= physics + first forward stage
                 if (control) {
-                    const chs_params p = S->p;
+                    PhysK pk;
+                    pk.th.RT = K[0]; pk.th.mBRT = K[1]; pk.th.A0 = K[2]; pk.th.A1 = K[3]; pk.th.m2A1 = K[4]; pk.th.B = K[6];
+                    pk.threshold = K[5];
                     // conserved mean (Q4); the jitter shifts it by jitter*(2*mean(noise) - 1)
-                    const double meanU = hat00 / (double)N + (jit ? p.jitter * (2.0 * a.noise_mean[0] - 1.0) : 0.0);
+                    pk.meanU = K[11] / (double)N + (jit ? K[7] * (2.0 * a.noise_mean[0] - 1.0) : 0.0);
                     if (ra_line) {                                              // Ra = mean |U[r,:] - mean U[r,:]| (solver.py:226-227)
                         const double ra_mean = ra_scr[0];
                         double s = 0;
@@ -853,44 +934,42 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                         }
                         ra_scr[2 + t] = s;
                     }
-                    RowAcc acc = {0, 0, 0, 0, 0};
+                    RowAcc acc = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
                     for (int i = 0; i < NB0; ++i) {
                         const int j = t + i * TPL;
+                        double2* pj = scl + G::idx(j);
                         double xr[R0], xi[R0];
-                        double2 wv[R0];
-                        if (!slow) {
-#pragma unroll
-                            for (int q = 1; q < R0; ++q) wv[q] = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : __ldg(s_tw + j * q);
-                        }
 #pragma unroll
                         for (int q = 0; q < R0; ++q) {
-                            const double2 v = scl[G::idx(j) + q * G::step(ST0)];
+                            const double2 v = pj[q * G::step(ST0)];
                             xr[q] = v.x; xi[q] = v.y;
                         }
                         if (!slow) {
 #pragma unroll
                             for (int q = 1; q < R0; ++q) {
+                                const double2 wv = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : __ldg(s_tw + j * q);
                                 const double x = xr[q], y = xi[q];
-                                xr[q] = x * wv[q].x + y * wv[q].y;               // conj twiddle, then inverse DFT
-                                xi[q] = y * wv[q].x - x * wv[q].y;
+                                xr[q] = x * wv.x + y * wv.y;               // conj twiddle, then inverse DFT
+                                xi[q] = y * wv.x - x * wv.y;
                             }
                             dft<R0, true>(xr, xi);
                         }
-                        physics<N, R0>(xr, xi, j, p, ltab, sums, meanU, false, 0.0, acc, edge + 4 * l);
+                        physics<N, R0, G::LOG_STRIDE, false>(xr, xi, j, pk, ltab, sums, false, 0.0, acc, edge + 4 * l);
                         if (!slow) {
                             dft<R0, false>(xr, xi);
 #pragma unroll
                             for (int q = 1; q < R0; ++q) {
+                                const double2 wv = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : __ldg(s_tw + j * q);   // (L1 hit)
                                 const double x = xr[q], y = xi[q];
-                                xr[q] = x * wv[q].x - y * wv[q].y;
-                                xi[q] = x * wv[q].y + y * wv[q].x;
+                                xr[q] = x * wv.x - y * wv.y;
+                                xi[q] = x * wv.y + y * wv.x;
                             }
                         }
 #pragma unroll
-                        for (int q = 0; q < R0; ++q) scl[G::idx(j) + q * G::step(ST0)] = make_double2(xr[q], xi[q]);
+                        for (int q = 0; q < R0; ++q) pj[q * G::step(ST0)] = make_double2(xr[q], xi[q]);
                     }
-                    const double v[4] = {acc.f, acc.ab, acc.mu2, (double)acc.cnt};
+                    const double v[4] = {chs_fma(pk.th.RT, acc.fa + acc.fb, acc.fp), acc.ab, acc.mu2, (double)acc.cnt};
                     reduce_stage<4>(v, sm + G::OFF_RED, tid);
                     __syncthreads();
                     if (tid == 0) {
@@ -910,6 +989,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                             pp[P_F * G::NTILES] = s4[0];
                             pp[P_ABS * G::NTILES] = s4[1];
                             pp[P_CNT * G::NTILES] = s4[3];
+                            if (tile == 0) S->mean_u = pk.meanU;
                             if (ra_tile) {
                                 double s = 0;
                                 for (int jj = 0; jj < TPL; ++jj) s += ra_scr[2 + jj];
@@ -929,13 +1009,14 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     if (slow) {
                         // adaptive dt: column sums of delt_max/sqrt(1 + 62.5 mu^2) over this tile's rows (solver.py:182-183)
                         if (want_cols) {
+                            const double dmax = K[8];
                             for (int x = tid; x < N; x += NT) {
                                 const double* colp = sm + real_off<N>(mk_pos<N>(x));
                                 double s = 0;
 #pragma unroll
                                 for (int l2 = 0; l2 < LINES; ++l2) {
                                     const double m = colp[2 * G::LOFF * l2];
-                                    s += p.delt_max / sqrt(1.0 + 62.5 * (m * m));
+                                    s += dmax / sqrt(1.0 + 62.5 * (m * m));
                                 }
                                 a.colpart[((size_t)sim * G::NTILES + tile) * N + x] = s;
                             }
@@ -951,17 +1032,8 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                 // ============= forward half: remaining stages, fused last stage + post, store
                 fft_fwd_range<N, 1, NST - 1, true>(scl, t, s_tw);
                 {
-                    int rho_a, rho_b, base_a, base_b;
-                    unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-                    double ar[8], ai[8], br[8], bi[8];
-                    load_block<N>(scl, base_a, ar, ai);
-                    load_block<N>(scl, base_b, br, bi);
-                    dft<8, false>(ar, ai);
-                    dft<8, false>(br, bi);
                     RowPost<N> post{s_om};
-                    for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, post);
-                    store_block<N>(scl, base_a, ar, ai);
-                    store_block<N>(scl, base_b, br, bi);
+                    fused_units<N, true, false>(scl, t, post);
                 }
                 __syncthreads();
                 row_tile_store_slots<N>(sc, ((MODE == ROW_FWD_U && a.dst) ? a.dst : a.T) + off + (size_t)row0 * N, tid);
@@ -1055,7 +1127,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
             v[0] += gy * gy + gx * gx;
             if (MODE == DIAG_PREPARE) {
                 double f, mu;
-                thermo(c[j], p, ltab, f, mu);
+                thermo<G::LOG_STRIDE>(c[j], p, ltab, f, mu);
                 v[1] += f;
                 v[2] += fabs(c[j] - meanU);
                 v[3] += (c[j] < p.threshold) ? 1.0 : 0.0;
@@ -1137,6 +1209,7 @@ CHS_KERNEL void k_begin(Sim* sims, int batch) {
     S->rows_written = 0;
     S->halted = 0;
     S->delt_coef = S->p.delt;          // solver.py:151-152: multipliers of the *initial* delt
+    sim_derive_lam(*S);
     S->ticket = 0;
 }
 

@@ -36,6 +36,7 @@ struct SlabArgs {
     double* part_ge;            // S_YSTEP: [rows/LINES] spectral gradient-energy sums
     const double* lam;
     const double* gsin;
+    const double2* lamg;        // packed per-item lambda / g table (KArgs::lamg)
     const int* kof;
     Sim* S;
     const double2* tw;          // natural table (point-major geometry), or the per-stage tables (line-major)
@@ -85,25 +86,15 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
             chs_cp_async_wait_all();
             __syncthreads();
             fft_fwd_range<N, 0, NST - 1>(scl, t, a.tw);
-            int rho_a, rho_b, base_a, base_b;
-            unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-            double ar[8], ai[8], br[8], bi[8];
-            load_block<N>(scl, base_a, ar, ai);
-            load_block<N>(scl, base_b, br, bi);
-            dft<8, false>(ar, ai);
-            dft<8, false>(br, bi);
             ColMid<N, CM> mid;
-            mid.om = a.om; mid.lam = a.lam; mid.gsin = a.gsin;
+            mid.om = a.om; mid.lamg = a.lamg;
             mid.hstride = 1;
             mid.hat = a.H + goff + (size_t)l * N;
             mid.hat_in = mid.hat;
+            mid.hat00 = nullptr;
             mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
-            for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, mid);
+            fused_units<N, true, MODE == S_YSTEP>(scl, t, mid);
             if (MODE == S_YSTEP) {
-                dft<8, true>(ar, ai);
-                dft<8, true>(br, bi);
-                store_block<N>(scl, base_a, ar, ai);
-                store_block<N>(scl, base_b, br, bi);
                 const double v[1] = {mid.ge};
                 reduce_stage<1>(v, sm + G::OFF_RED, tid);
                 __syncthreads();
@@ -123,19 +114,10 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
         chs_cp_async_wait_all();
         __syncthreads();
         if (MODE == S_INV || MODE == S_STEP) {
+            if (ra_line && t == 0) ra_scr[0] = scl[G::idx(0)].x * sqrt(1.0 / N);
             {
-                int rho_a, rho_b, base_a, base_b;
-                unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-                double ar[8], ai[8], br[8], bi[8];
-                load_block<N>(scl, base_a, ar, ai);
-                load_block<N>(scl, base_b, br, bi);
-                if (ra_line && t == 0) ra_scr[0] = ar[0] * sqrt(1.0 / N);
                 RowPre<N> pre{a.om};
-                for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, pre);
-                dft<8, true>(ar, ai);
-                dft<8, true>(br, bi);
-                store_block<N>(scl, base_a, ar, ai);
-                store_block<N>(scl, base_b, br, bi);
+                fused_units<N, false, true>(scl, t, pre);
             }
             __syncthreads();
             fft_inv_range<N, 0, NST - 1>(scl, t, a.tw);        // includes stage 0: the field is stored below
@@ -149,8 +131,11 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
             }
             if (physics_on) {
                 const chs_params p = a.S->p;
+                PhysK pk;
+                pk.th.RT = p.RT; pk.th.mBRT = -p.BRT; pk.th.A0 = p.A0; pk.th.A1 = p.A1; pk.th.m2A1 = -2.0 * p.A1; pk.th.B = p.B;
+                pk.threshold = p.threshold; pk.meanU = a.mean_u;
                 const double ra_mean = ra_line ? ra_scr[0] : 0.0;
-                RowAcc acc = {0, 0, 0, 0, 0};
+                RowAcc acc = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
                 for (int i = 0; i < NB0; ++i) {
                     const int j = t + i * TPL;
@@ -161,8 +146,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                         xr[q] = v.x; xi[q] = v.y;
                     }
                     // the Ra row is one row of the whole domain: keep its per-value work out of the common copy
-                    if (ra_line) physics<N, R0>(xr, xi, j, p, ltab, diag, a.mean_u, true, ra_mean, acc, edge + 4 * l);
-                    else physics<N, R0>(xr, xi, j, p, ltab, diag, a.mean_u, false, 0.0, acc, edge + 4 * l);
+                    if (ra_line) physics<N, R0, G::LOG_STRIDE, true>(xr, xi, j, pk, ltab, diag, true, ra_mean, acc, edge + 4 * l);
+                    else physics<N, R0, G::LOG_STRIDE, true>(xr, xi, j, pk, ltab, diag, false, 0.0, acc, edge + 4 * l);
                     dft<R0, false>(xr, xi);
 #pragma unroll
                     for (int q = 1; q < R0; ++q) {
@@ -175,7 +160,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                     for (int q = 0; q < R0; ++q) scl[G::idx(j) + q * G::step(ST0)] = make_double2(xr[q], xi[q]);
                 }
                 if (ra_line) ra_scr[2 + t] = acc.ra;
-                const double v[4] = {acc.f, acc.ab, acc.mu2, (double)acc.cnt};
+                const double v[4] = {chs_fma(pk.th.RT, acc.fa + acc.fb, acc.fp), acc.ab, acc.mu2, (double)acc.cnt};
                 reduce_stage<4>(v, sm + G::OFF_RED, tid);
                 __syncthreads();
                 if (tid == 0) {
@@ -208,17 +193,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
             }
             fft_fwd_range<N, 1, NST - 1>(scl, t, a.tw);
             {
-                int rho_a, rho_b, base_a, base_b;
-                unit_blocks<N>(t, rho_a, rho_b, base_a, base_b);
-                double ar[8], ai[8], br[8], bi[8];
-                load_block<N>(scl, base_a, ar, ai);
-                load_block<N>(scl, base_b, br, bi);
-                dft<8, false>(ar, ai);
-                dft<8, false>(br, bi);
                 RowPost<N> post{a.om};
-                for_each_item<N>(t, rho_a, rho_b, ar, ai, br, bi, post);
-                store_block<N>(scl, base_a, ar, ai);
-                store_block<N>(scl, base_b, br, bi);
+                fused_units<N, true, false>(scl, t, post);
             }
             __syncthreads();
             row_tile_store_slots<N>(sc, a.dst + goff, tid);
@@ -291,7 +267,7 @@ CHS_KERNEL void k_slab_prepare(const double* Uh, int rows, int row_base, int N, 
         else if (x == N - 1) gx = c - U[i - 1];
         else gx = 0.5 * (U[i + 1] - U[i - 1]);
         double f, mu;
-        thermo(c, p, logtab, f, mu);
+        thermo<1>(c, p, logtab, f, mu);
         v[0] += gy * gy + gx * gx;
         v[1] += f;
         v[2] += fabs(c - mean_u);

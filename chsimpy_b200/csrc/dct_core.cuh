@@ -24,13 +24,30 @@ namespace chs {
 
 CHS_CX constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 
-// radix plan of the M-point complex FFT: an optional leading radix-2/4 stage, then radix-8
+#ifdef CHS_EMU
+static inline double chs_fmad(double a, double b, double c) { return std::fma(a, b, c); }
+#else
+CHS_DEV double chs_fmad(double a, double b, double c) { return __fma_rn(a, b, c); }
+#endif
+
+// Radix plan of the M-point complex FFT.  Default: an optional leading radix-2/4 stage, then radix-8.
+// For M = 4 * 8^j of the point-major (batched) geometry -- N = 64 and N = 512 -- the radix-4 stage comes
+// LAST instead (8 .. 8 4): the fused post/pre passes then hold two 4-point blocks (32 registers of data)
+// instead of two 8-point blocks per pairing unit, which is what lets the step kernels run at 80 registers.
+// Host mirror: plan_radices() in chs_api.cu.
+#ifndef CHS_LAST4
+#define CHS_LAST4 1
+#endif
 template <int M>
 struct Rad {
     static constexpr int lg = ilog2c(M);
     static constexpr int rem = lg % 3;
     static constexpr int nst = lg / 3 + (rem ? 1 : 0);
-    CHS_CX static constexpr int radix(int s) { return (rem != 0 && s == 0) ? (1 << rem) : 8; }
+    static constexpr bool LAST4 = CHS_LAST4 && rem == 2 && M <= 512;
+    CHS_CX static constexpr int radix(int s) {
+        return LAST4 ? (s == nst - 1 ? 4 : 8) : ((rem != 0 && s == 0) ? (1 << rem) : 8);
+    }
+    static constexpr int RL = radix(nst - 1);               // radix of the last stage (4 or 8)
     CHS_CX static constexpr int blocklen(int s) {
         int Lb = M;
         for (int i = 0; i < s; ++i) Lb /= radix(i);
@@ -51,6 +68,8 @@ struct Rad {
 #define CHS_LINES 8
 #endif
 CHS_CX constexpr int geo_lines(int N) { return N <= 1024 ? CHS_LINES : 1; }   // lines (rows / columns) per tile
+#define CHS_LOG_N 128       // entries of the fast_log table (fastlog.cuh)
+#define CHS_SIMK 16         // doubles of the per-simulation constants image staged in shared memory
 
 template <int N_>
 struct Geo {
@@ -115,26 +134,40 @@ struct Geo {
     CHS_CX static constexpr int t_of(int tid) { return LINE_MAJOR ? tid % (M / 16) : tid / LINES; }
     static constexpr int NT = LINES * TPL;                     // threads per CTA
     static constexpr int NTILES = N / LINES;
-    static constexpr int MINB = (65536 / 128) / NT > 16 ? 16 : ((65536 / 128) / NT > 0 ? (65536 / 128) / NT : 1);   // CTAs per SM at 128 registers/thread
+#ifndef CHS_SEQ_STAGES
+#define CHS_SEQ_STAGES 1
+#endif
+    // register-light stages for the batched geometry: the butterflies (and pairing units) of a thread are
+    // processed one after the other instead of all loads first; latency is hidden by the 6 resident CTAs
+    // per SM that 80 registers allow, not by the memory-level parallelism of one thread
+    static constexpr bool SEQ = CHS_SEQ_STAGES && !LINE_MAJOR;
+    static constexpr int REGS = SEQ ? 80 : 128;
+    static constexpr int MINB = (65536 / REGS) / NT > 16 ? 16 : ((65536 / REGS) / NT > 0 ? (65536 / REGS) / NT : 1);   // CTAs per SM
 #ifndef CHS_MINB_ROW
-#define CHS_MINB_ROW 4
+#define CHS_MINB_ROW MINB
 #endif
 #ifndef CHS_MINB_COL
-#define CHS_MINB_COL 4
+#define CHS_MINB_COL MINB
 #endif
     static constexpr int MINB_ROW = (NT == 128) ? CHS_MINB_ROW : MINB;   // N = 512: tuned on B200 (profiles/)
     static constexpr int MINB_COL = (NT == 128) ? CHS_MINB_COL : MINB;
     static constexpr int TILE_DOUBLES = LINE_MAJOR ? 2 * LINES * LOFF : 2 * M * LPC;
-    // scratch after the tile (doubles): flag | x/y edge values | Ra | fast_log table | reduction
+    // fast_log table (CHS_LOG_N double2): in the point-major tile it lives in the PAD slot of the first
+    // CHS_LOG_N points (slot LINES of point c, never touched by the transforms), otherwise after the tile
+    static constexpr bool LOG_IN_PAD = !LINE_MAJOR && M >= CHS_LOG_N;
+    static constexpr int LOG_STRIDE = LOG_IN_PAD ? LPC : 1;    // in double2
+    // scratch after the tile (doubles): flag | x/y edge values | Ra | Sim image | fast_log table | reduction
     static constexpr int OFF_FLAG = TILE_DOUBLES;
     static constexpr int OFF_EDGE = OFF_FLAG + 2;              // [LINES][4]
     static constexpr int OFF_RA = OFF_EDGE + 4 * LINES;        // mean, spare, then TPL partials
-    static constexpr int OFF_LOGTAB = OFF_RA + 2 + TPL + (TPL & 1);      // fast_log table, 128 double2 (keeps double2 alignment)
-    static constexpr int OFF_RED = OFF_LOGTAB + 2 * 128;       // (NT/32+1)*8 doubles on the GPU; NT*8 in the host emulation
-    static constexpr int SMEM_BYTES = (OFF_RED + (NT / 32 + 1) * 8 + 8) * 8;
+    static constexpr int OFF_SIM = OFF_RA + 2 + TPL + (TPL & 1);         // staged per-simulation constants (CHS_SIMK doubles)
+    static constexpr int OFF_LOGTAB = OFF_SIM + CHS_SIMK;      // (keeps double2 alignment)
+    static constexpr int OFF_RED = OFF_LOGTAB + (LOG_IN_PAD ? 0 : 2 * CHS_LOG_N);   // (NT/32)*4 + 4 doubles on the GPU; NT*8 in the host emulation
+    static constexpr int SMEM_BYTES = (OFF_RED + (NT / 32) * 4 + 4) * 8;
+    CHS_CX static constexpr int log_off() { return LOG_IN_PAD ? 2 * LINES : OFF_LOGTAB; }   // doubles from the tile base
     static_assert(N >= 32 && (N & (N - 1)) == 0, "FFT path needs a power of two >= 32");
-    static_assert(Rad<M>::radix(Rad<M>::nst - 1) == 8 && Rad<M>::nst >= 2, "plan must end with a radix-8 stage");
-    static_assert((OFF_LOGTAB % 2) == 0, "double2 alignment");
+    static_assert((Rad<M>::RL == 8 || Rad<M>::RL == 4) && Rad<M>::nst >= 2, "plan must end with a radix-8 or radix-4 stage");
+    static_assert((OFF_LOGTAB % 2) == 0 && (OFF_SIM % 2) == 0, "double2 alignment");
     static_assert(pad_ok(), "bank skew is not additive for this radix plan");
     static_assert(!LINE_MAJOR || (SH1 >= 3 && (W2 == 0 || SH2 >= 3)), "skew must be constant inside an 8-point block");
     static_assert(!WARP_LINES || (32 % TPL == 0), "the threads of a line must share a warp");
@@ -186,26 +219,34 @@ CHS_DEV void dft(double (&xr)[R], double (&xi)[R]) {
     } else {
         static_assert(R == 8, "radix");
         constexpr double h = 0.70710678118654752440;
-        double ar[4], ai[4], br[4], bi[4];
+        // even half: a_q = x_q + x_{q+4};  odd half: b_q = (x_q - x_{q+4}) * W8^q, W8 = exp(-/+ i pi/4).
+        // The factor h = 1/sqrt2 of W8 and W8^3 is not applied to b_1, b_3 but folded into the last
+        // layer of the odd 4-point DFT (8 FMAs instead of 4 multiplications + 8 additions).
+        double ar[4], ai[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            ar[q] = xr[q] + xr[q + 4]; ai[q] = xi[q] + xi[q + 4];
-            br[q] = xr[q] - xr[q + 4]; bi[q] = xi[q] - xi[q + 4];
-        }
-        // b_q *= W8^q,  W8 = exp(-/+ i pi/4)
-        double x, y;
-        x = br[1]; y = bi[1];
-        if (INV) { br[1] = (x - y) * h; bi[1] = (x + y) * h; } else { br[1] = (x + y) * h; bi[1] = (y - x) * h; }
-        x = br[2]; y = bi[2];
-        if (INV) { br[2] = -y; bi[2] = x; } else { br[2] = y; bi[2] = -x; }
-        x = br[3]; y = bi[3];
-        if (INV) { br[3] = (-x - y) * h; bi[3] = (x - y) * h; } else { br[3] = (y - x) * h; bi[3] = (-x - y) * h; }
+        for (int q = 0; q < 4; ++q) { ar[q] = xr[q] + xr[q + 4]; ai[q] = xi[q] + xi[q + 4]; }
+        const double b0r = xr[0] - xr[4], b0i = xi[0] - xi[4];
+        const double d1r = xr[1] - xr[5], d1i = xi[1] - xi[5];
+        const double d2r = xr[2] - xr[6], d2i = xi[2] - xi[6];
+        const double d3r = xr[3] - xr[7], d3i = xi[3] - xi[7];
+        // u1 = b_1/h, u3 = b_3/h, b2 = b_2
+        const double u1r = INV ? d1r - d1i : d1r + d1i, u1i = INV ? d1r + d1i : d1i - d1r;
+        const double u3r = INV ? -(d3r + d3i) : d3i - d3r, u3i = INV ? d3r - d3i : -(d3r + d3i);
+        const double b2r = INV ? -d2i : d2i, b2i = INV ? d2r : -d2r;
+        const double c0r = b0r + b2r, c0i = b0i + b2i, c1r = b0r - b2r, c1i = b0i - b2i;
+        const double sr = u1r + u3r, si = u1i + u3i;              // (b_1 + b_3)/h
+        const double er = u1r - u3r, ei = u1i - u3i;              // (b_1 - b_3)/h
         dft4<INV>(ar, ai);
-        dft4<INV>(br, bi);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            xr[2 * m] = ar[m]; xi[2 * m] = ai[m];
-            xr[2 * m + 1] = br[m]; xi[2 * m + 1] = bi[m];
+        for (int m = 0; m < 4; ++m) { xr[2 * m] = ar[m]; xi[2 * m] = ai[m]; }
+        xr[1] = chs_fmad(h, sr, c0r);  xi[1] = chs_fmad(h, si, c0i);
+        xr[5] = chs_fmad(-h, sr, c0r); xi[5] = chs_fmad(-h, si, c0i);
+        if (INV) {                                                // c3 = i (b_1 - b_3)
+            xr[3] = chs_fmad(-h, ei, c1r); xi[3] = chs_fmad(h, er, c1i);
+            xr[7] = chs_fmad(h, ei, c1r);  xi[7] = chs_fmad(-h, er, c1i);
+        } else {                                                  // c3 = -i (b_1 - b_3)
+            xr[3] = chs_fmad(h, ei, c1r);  xi[3] = chs_fmad(-h, er, c1i);
+            xr[7] = chs_fmad(-h, ei, c1r); xi[7] = chs_fmad(h, er, c1i);
         }
     }
 }
@@ -220,6 +261,34 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
     constexpr int M = G::M, TPL = G::TPL;
     constexpr int r = Rad<M>::radix(S), Lb = Rad<M>::blocklen(S), st = Lb / r;
     constexpr int NB = 16 / r;
+    if constexpr (G::SEQ) {
+        // register-light form: one butterfly at a time (r points live)
+#pragma unroll 1
+        for (int i = 0; i < NB; ++i) {
+            const int u = t + i * TPL;
+            const int j = u % st;
+            double2* p = scl + G::idx((u / st) * Lb + j);
+            double xr[r], xi[r];
+#pragma unroll
+            for (int q = 0; q < r; ++q) {
+                const double2 v = p[q * G::step(st)];
+                xr[q] = v.x; xi[q] = v.y;
+            }
+            if (!INV) dft<r, false>(xr, xi);
+            if (st > 1) {
+#pragma unroll
+                for (int q = 1; q < r; ++q) {
+                    const double2 w = G::STAGED_TABLES ? __ldg(tw + Rad<M>::tws_off(S) + (q - 1) * st + j) : __ldg(tw + j * q * (M / Lb));
+                    const double a = xr[q], b = xi[q];
+                    if (!INV) { xr[q] = a * w.x - b * w.y; xi[q] = a * w.y + b * w.x; }
+                    else      { xr[q] = a * w.x + b * w.y; xi[q] = b * w.x - a * w.y; }     // conj(w)
+                }
+            }
+            if (INV) dft<r, true>(xr, xi);
+#pragma unroll
+            for (int q = 0; q < r; ++q) p[q * G::step(st)] = make_double2(xr[q], xi[q]);
+        }
+    } else {
     // all 16 points of the thread are loaded before the first butterfly and stored after the
     // last one: the compiler cannot prove that the in-place stores of one butterfly do not
     // alias the loads of the next, so this is what exposes the memory-level parallelism
@@ -256,6 +325,7 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
 #pragma unroll
         for (int q = 0; q < r; ++q) scl[G::idx(base) + q * G::step(st)] = make_double2(xr[i][q], xi[i][q]);
     }
+    }
 }
 
 // barrier between two passes over ONE line: the threads of a line share a warp in the WARP_LINES
@@ -285,7 +355,9 @@ CHS_DEV void fft_inv_range(double2* scl, int t, const double2* __restrict__ tw) 
 }
 
 // ------------------------------------------------------------------ post / pre algebra (registers)
-// om[m] = exp(-i pi m / (2N)).  For 1 <= k < M/2:
+// Tables (host: fill_om in chs_api.cu):  om[m] = sc * exp(-i pi m / (2N)), m < N, with the common
+// scale sc = sqrt(2/N)/2 of the forward untangle and of the inverse (1/(2 s M) = sc) folded in;
+// om[N + k] = exp(-2 pi i k / N) (= the unscaled om[4k]), k < N/4.  For 1 <= k < M/2:
 //   post: Z[k]=(ar,ai), Z[M-k]=(br,bi)  ->  c = {C[k], C[N-k], C[M-k], C[M+k]}
 //   pre : the inverse map, including the 1/M of the unnormalised inverse FFT.
 // special: Z[0], Z[M/2] <-> {C[0], C[M], C[M/2], C[3M/2]}.
@@ -293,14 +365,12 @@ template <int N>
 CHS_DEV void post_pair(int k, const double2* __restrict__ om, double ar, double ai, double br, double bi,
                        double (&c)[4]) {
     constexpr int M = N / 2;
-    // om[N + k] repeats om[4k] in contiguous order for the line-major geometry (adjacent lanes = adjacent k)
-    const double2 t = Geo<N>::STAGED_TABLES ? __ldg(om + N + k) : __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
-    const double sc = 0.5 * sqrt(2.0 / N);
+    const double2 t = __ldg(om + N + k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
     const double er = ar + br, ei = ai - bi;                  // 2E
     const double o_r = ai + bi, o_i = br - ar;                // 2O = -i (a - conj b)
     const double tr = t.x * o_r - t.y * o_i, ti = t.x * o_i + t.y * o_r;
-    const double pr = (er + tr) * sc, pi = (ei + ti) * sc;
-    const double qr = (er - tr) * sc, qi = (ei - ti) * sc;
+    const double pr = er + tr, pi = ei + ti;
+    const double qr = er - tr, qi = ei - ti;
     c[0] = wk.x * pr - wk.y * pi;
     c[1] = -(wk.x * pi + wk.y * pr);
     c[2] = wm.x * qr + wm.y * qi;                             // Re(wm * conj(Q))
@@ -311,25 +381,23 @@ template <int N>
 CHS_DEV void post_special(const double2* __restrict__ om, double ar, double ai, double hr, double hi,
                           double (&c)[4]) {
     constexpr int M = N / 2;
-    const double rn = sqrt(1.0 / N), s = sqrt(2.0 / N);
-    const double2 w = __ldg(om + M / 2);
+    const double rn = sqrt(1.0 / N);
+    const double2 w = __ldg(om + M / 2);       // sc * exp(-i pi/8), sc = s/2
     c[0] = rn * (ar + ai);
     c[1] = rn * (ar - ai);
-    c[2] = s * (w.x * hr + w.y * hi);          // Re(w * conj(Zh))
-    c[3] = -s * (w.y * hr - w.x * hi);         // -Im(w * conj(Zh))
+    c[2] = 2.0 * (w.x * hr + w.y * hi);        // s Re(w * conj(Zh))
+    c[3] = -2.0 * (w.y * hr - w.x * hi);       // -s Im(w * conj(Zh))
 }
 
 template <int N>
 CHS_DEV void pre_pair(int k, const double2* __restrict__ om, const double (&c)[4], double& ar, double& ai,
                       double& br, double& bi) {
     constexpr int M = N / 2;
-    // om[N + k] repeats om[4k] in contiguous order for the line-major geometry (adjacent lanes = adjacent k)
-    const double2 t = Geo<N>::STAGED_TABLES ? __ldg(om + N + k) : __ldg(om + 4 * k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
-    const double sc = 1.0 / (sqrt(2.0 / N) * N);              // 1/(2 s M)
-    const double vr = wk.x * c[0] - wk.y * c[1], vi = -wk.x * c[1] - wk.y * c[0];       // conj(wk)(c0 - i c1)
+    const double2 t = __ldg(om + N + k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    const double vr = wk.x * c[0] - wk.y * c[1], vi = -wk.x * c[1] - wk.y * c[0];       // sc conj(wk)(c0 - i c1)
     const double v2r = wm.x * c[2] - wm.y * c[3], v2i = -wm.x * c[3] - wm.y * c[2];
-    const double er = (vr + v2r) * sc, ei = (vi - v2i) * sc;  // E
-    const double dr = (vr - v2r) * sc, di = (vi + v2i) * sc;  // V - conj(V2)
+    const double er = vr + v2r, ei = vi - v2i;                // E
+    const double dr = vr - v2r, di = vi + v2i;                // V - conj(V2)
     const double o_r = dr * t.x + di * t.y, o_i = di * t.x - dr * t.y;   // O = D * conj(t)
     ar = er - o_i; ai = ei + o_r;
     br = er + o_i; bi = o_r - ei;
@@ -339,25 +407,26 @@ template <int N>
 CHS_DEV void pre_special(const double2* __restrict__ om, const double (&c)[4], double& ar, double& ai,
                          double& hr, double& hi) {
     constexpr int M = N / 2;
-    const double rn = sqrt(1.0 / N), is = 1.0 / (sqrt(2.0 / N) * M);
-    const double2 w = __ldg(om + M / 2);
+    const double rn = sqrt(1.0 / N);
+    const double2 w = __ldg(om + M / 2);       // sc * exp(-i pi/8); 1/(s M) = 2 sc
     ar = rn * (c[0] + c[1]);
     ai = rn * (c[0] - c[1]);
-    const double u = c[2] * is, v = -c[3] * is;               // A/(sM) = u + i v
+    const double u = 2.0 * c[2], v = -2.0 * c[3];             // A/(sM) = (u + i v) * sc
     const double vr = w.x * u + w.y * v, vi = w.x * v - w.y * u;   // conj(w) * A
     hr = vr; hi = -vi;
 }
 
-// The two blocks of the last radix-8 stage owned by thread t, and the frequency residues
-// (k mod M/8) they hold: the block of residue rho starts at complex position freq_pos(rho).
+// Pairing units of the fused last stage.  The last stage has radix RL (8, or 4 with Rad<M>::LAST4); its
+// block of residue rho (frequencies rho + Q c, Q = M/RL, natural order after the RL-point DFT) starts at
+// complex position freq_pos(rho).  The post/pre step couples frequency k with M - k, i.e. the blocks of
+// residues rho and Q - rho: unit u (1 <= u < Q/2) = blocks {u, Q - u}, unit 0 = the two self-paired blocks
+// {0, Q/2}.  A thread owns 16 points per stage = NU = 16/(2 RL) units: u = t + i*TPL.
 template <int N>
-CHS_DEV void unit_blocks(int t, int& rho_a, int& rho_b, int& base_a, int& base_b) {
-    constexpr int M = N / 2;
-    rho_a = (t == 0) ? 0 : t;
-    rho_b = (t == 0) ? (M / 16) : (M / 8 - t);
-    base_a = freq_pos<M>(rho_a);
-    base_b = freq_pos<M>(rho_b);
-}
+struct Pairing {
+    static constexpr int M = N / 2, RL = Rad<M>::RL, Q = M / RL, H = RL / 2;
+    static constexpr int NU = 16 / (2 * RL), TPL = M / 16;
+    static_assert(NU * TPL == Q / 2, "units must cover all residues");
+};
 
 // Column slot s (PERM order used by T and hat_U along the x-spectral axis) holds frequency:
 //   s = 2*pos(k) + 0 -> k ;  s = 2*pos(k) + 1 -> N-k  (k = 0: M).   Host table `kof`.
