@@ -211,7 +211,7 @@ static void fill_twiddles(int N, std::vector<double2>& tw) {
     const long double pi = 3.14159265358979323846264338327950288L;
     std::vector<double2> nat(M);
     for (int m = 0; m < M; ++m) { const long double a = -2.0L * pi * m / M; nat[m] = make_double2((double)cosl(a), (double)sinl(a)); }
-    const bool line_major = (N >= 2048) || (CHS_WARP_LINES && N >= 256 && N <= 1024) || CHS_STAGED_TABLES;   // = Geo<N>::STAGED_TABLES
+    const bool line_major = (N >= 2048) || CHS_STAGED_TABLES;   // = Geo<N>::STAGED_TABLES
     tw.assign(M, make_double2(0.0, 0.0));
     if (!line_major) { tw = nat; return; }
     const std::vector<int> rad = plan_radices(M);
@@ -223,6 +223,19 @@ static void fill_twiddles(int N, std::vector<double2>& tw) {
         o += (size_t)(r - 1) * st;
         Lb /= r;
     }
+}
+
+// constant-memory image of the twiddle tables (dct_core.cuh, CHS_CONST_TABLES): region of size N
+static int upload_const_tables(int N, const std::vector<double2>& tw, const std::vector<double2>& om, cudaStream_t stream) {
+#if CHS_CONST_TABLES && !defined(CHS_EMU)
+    if (N > 1024 || N < 32) return 0;
+    const size_t off = sizeof(double2) * (size_t)ctab_off(N);
+    CHS_CUDA(cudaMemcpyToSymbolAsync(c_tab, tw.data(), sizeof(double2) * (N / 2), off, cudaMemcpyHostToDevice, stream));
+    CHS_CUDA(cudaMemcpyToSymbolAsync(c_tab, om.data(), sizeof(double2) * (N + N / 4), off + sizeof(double2) * (N / 2), cudaMemcpyHostToDevice, stream));
+#else
+    (void)N; (void)tw; (void)om; (void)stream;
+#endif
+    return 0;
 }
 
 template <class K>
@@ -244,6 +257,13 @@ static int set_attrs(chs_solver* s) {
     CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_PREPARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_JITTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+#ifndef CHS_EMU
+    // tuning experiment: shared-memory carve-out of the two step kernels in percent (default: the driver's choice)
+    if (const char* e = getenv("CHS_CARVEOUT")) {
+        CHS_CUDA(cudaFuncSetAttribute(k_col<N, COL_STEP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_STEP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+    }
+#endif
     const int nt = Geo<N>::NT, ns = s->num_sms;
     s->cap_col[COL_FWD] = resident_ctas(k_col<N, COL_FWD>, nt, b, ns);
     s->cap_col[COL_STEP] = resident_ctas(k_col<N, COL_STEP>, nt, b, ns);
@@ -365,6 +385,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    if (!s->gemm) ok &= upload_const_tables(N, tw, om, s->stream) == 0;
     std::vector<double2> lamg;
     if (!s->gemm) {
         fill_lamg(N, lambda_host, gs, lamg);
@@ -829,6 +850,7 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    ok &= upload_const_tables(N, tw, om, s->stream) == 0;
     std::vector<double2> lamg;
     fill_lamg(N, lambda_host, gs, lamg);
     ok &= cudaMemcpyAsync(s->lamg, lamg.data(), sizeof(double2) * lamg.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;

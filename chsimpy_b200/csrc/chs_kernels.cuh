@@ -352,46 +352,51 @@ CHS_DEV bool last_cta(Sim* S, int ntiles, int* flag_smem, int tid, bool all_wrot
 }
 
 // ---------------------------------------------------------------------------------------
-// Tile I/O (loads batched before first use).
-// column tile: all N rows x 16 adjacent slots, physical y -> Makhoul position, one complex
-// element (two rows) per thread and step.
+// Tile I/O.
+//
+// "Pair-major T" (batched kernels, N <= 1024): the row<->column intermediate T lives in HBM as
+//     T[sim][X][c][l]   (double2),  X = column tile (8 slots), c = Makhoul pair index along y, l = slot in tile
+//     element = ( T[y0(c)][8X+l], T[y1(c)][8X+l] ),  rows y0/y1 = the two rows the packed column FFT puts
+//     into one complex point (col_pair_rows)
+// i.e. one column tile is ONE contiguous block of 16*M*8 bytes in exactly the shared-memory layout of the
+// column kernel: k_col moves its tile with a single bulk asynchronous copy each way (TMA unit, SASS
+// UBLKCP) -- no LSU instruction, no L1 wavefront, no register for T.  The row kernel pays for it with a
+// 2x2 exchange in its first and last pass (64-bit instead of 128-bit shared accesses there): a row tile =
+// rows 8r .. 8r+7 = the four pairs c = 2r, 2r+1, M-1-2r, M-2-2r; line lambda = pi + 4h of the tile is row
+// y_h of pair pi (ROWOFF), so that the two rows of a pair are lanes lambda and lambda^4 of one warp.
 template <int N>
 CHS_DEV void col_pair_rows(int c, int& y0, int& y1) {      // rows holding v[2c], v[2c+1]
     constexpr int M = N / 2;
     if (2 * c < M) { y0 = 4 * c; y1 = 4 * c + 2; }
     else { y0 = 2 * (N - 1 - 2 * c) + 1; y1 = y0 - 2; }
 }
-
-// issues the asynchronous copies of a column tile; complete after chs_cp_async_wait_all() + barrier
+// row of line lambda of row tile r, relative to 8r: {0,4,3,7, 2,6,1,5}
+CHS_DEV int pair_rowoff(int lam) { return (int)((0x51627340u >> (4 * lam)) & 7u); }
+// and its inverse: the line that holds row 8r + y
+CHS_DEV int pair_lineof(int y) { return (int)((0x35712460u >> (4 * y)) & 7u); }
+// pair index c of (row tile r, pi)
 template <int N>
-CHS_DEV void col_tile_load_async(double2* scl, const double* __restrict__ g, int t) {
+CHS_DEV int pair_c(int r, int pi) { return (pi < 2) ? 2 * r + pi : (N / 2 - 1) - 2 * r - (pi - 2); }
+
+// row tile r of pair-major T <-> shared memory: piece (pi, slot s) = (T[y0][s], T[y1][s]) at point p = s/2,
+// line pi + 4 (s & 1).  A quarter-warp touches 4 x 32 contiguous bytes of HBM and one 128-byte wavefront.
+template <int N, bool STORE>
+CHS_DEV void row_tile_pairs_io(double2* sc, double* __restrict__ gT /* simulation base */, int r, int tid) {
     using G = Geo<N>;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int c = t + j * G::TPL;
-        int y0, y1;
-        col_pair_rows<N>(c, y0, y1);
-        double* d = reinterpret_cast<double*>(scl + G::idx(c));
-        chs_cp_async8(d, g + (size_t)y0 * N);
-        chs_cp_async8(d + 1, g + (size_t)y1 * N);
+    static_assert(G::LINES == 8 && !G::LINE_MAJOR && G::NT % 8 == 0, "pair-major T needs the 8-line point-major tile");
+    constexpr int M = G::M, CNT = 8 * M / G::NT;
+    const int lam = tid & 7, pi = lam & 3, h = lam >> 2;
+    double2* g2 = reinterpret_cast<double2*>(gT) + (size_t)pair_c<N>(r, pi) * 8 + h;
+#pragma unroll 8
+    for (int j = 0; j < CNT; ++j) {
+        const int p = (tid + j * G::NT) >> 3;
+        double2* g = g2 + (size_t)(p >> 2) * (M * 8) + 2 * (p & 3);
+        if (STORE) *g = sc[p * 8 + lam];
+        else chs_cp_async16(sc + p * 8 + lam, g);
     }
 }
 
-template <int N>
-CHS_DEV void col_tile_store(const double2* scl, double* __restrict__ g, int t) {
-    using G = Geo<N>;
-#pragma unroll 4
-    for (int j = 0; j < 16; ++j) {
-        const int c = t + j * G::TPL;
-        int y0, y1;
-        col_pair_rows<N>(c, y0, y1);
-        const double2 v = scl[G::idx(c)];
-        g[(size_t)y0 * N] = v.x;
-        g[(size_t)y1 * N] = v.y;
-    }
-}
-
-// row tile in slot order: one complex element = two adjacent slots = one 16-byte access
+// row tile in natural slot order (slab kernels): one complex element = two adjacent slots = one 16-byte access
 template <int N>
 CHS_DEV void row_tile_load_slots_async(double2* sc, const double* __restrict__ g, int tid) {
     using G = Geo<N>;
@@ -416,8 +421,9 @@ CHS_DEV void row_tile_store_slots(const double2* sc, double* __restrict__ g, int
     }
 }
 
-// row tile of a physical field (U): x -> Makhoul position (cold paths only)
-template <int N>
+// row tile of a physical field (U): x -> Makhoul position (cold paths only).  PAIRS: line l2 of the tile is
+// row pair_rowoff(l2) (batched kernels), else row l2 (slab kernels).
+template <int N, bool PAIRS = false>
 CHS_DEV void row_tile_load_phys(double* sm, const double* __restrict__ g, int tid) {
     using G = Geo<N>;
     constexpr int CNT = G::LINES * N / G::NT, UNR = 8;
@@ -427,7 +433,7 @@ CHS_DEV void row_tile_load_phys(double* sm, const double* __restrict__ g, int ti
 #pragma unroll
         for (int j = 0; j < UNR; ++j) {
             const int i = tid + (j0 + j) * G::NT;
-            v[j] = g[(size_t)(i / N) * N + (i % N)];
+            v[j] = g[(size_t)(PAIRS ? pair_rowoff(i / N) : i / N) * N + (i % N)];
         }
 #pragma unroll
         for (int j = 0; j < UNR; ++j) {
@@ -450,14 +456,14 @@ CHS_DEV void row_tile_load_phys_async(double* sm, const double* __restrict__ g, 
     }
 }
 
-template <int N>
+template <int N, bool PAIRS = false>
 CHS_DEV void row_tile_store_phys(const double* sm, double* __restrict__ g, int tid) {
     using G = Geo<N>;
     constexpr int CNT = G::LINES * N / G::NT;
 #pragma unroll 8
     for (int j = 0; j < CNT; ++j) {
         const int i = tid + j * G::NT;
-        g[(size_t)(i / N) * N + (i % N)] = sm[real_off<N>(mk_pos<N>(i % N)) + 2 * G::LOFF * (i / N)];
+        g[(size_t)(PAIRS ? pair_rowoff(i / N) : i / N) * N + (i % N)] = sm[real_off<N>(mk_pos<N>(i % N)) + 2 * G::LOFF * (i / N)];
     }
 }
 
@@ -523,14 +529,33 @@ CHS_DEV void store_block(double2* scl, int base, const double (&xr)[R], const do
     for (int c = 0; c < R; ++c) scl[Geo<N>::idx(base) + c * Geo<N>::LPC] = make_double2(xr[c], xi[c]);
 }
 
+// The same against a row tile in "piece" form (pair-major T, see Tile I/O): the element (p, line) of row
+// y_h of pair pi is the h-components of the two pieces at (p, pi) and (p, pi + 4) -- two 64-bit accesses.
+// Lanes lambda and lambda^4 read / write the same two pieces: loads and stores are separated by __syncwarp.
+template <int N, int R>
+CHS_DEV void load_block_x(const double2* sc, int lam, int base, double (&xr)[R], double (&xi)[R]) {
+    const double* q = reinterpret_cast<const double*>(sc + base * 8 + (lam & 3)) + (lam >> 2);
+#pragma unroll
+    for (int c = 0; c < R; ++c) { xr[c] = q[c * 16]; xi[c] = q[c * 16 + 8]; }
+}
+template <int N, int R>
+CHS_DEV void store_block_x(double2* sc, int lam, int base, const double (&xr)[R], const double (&xi)[R]) {
+    double* q = reinterpret_cast<double*>(sc + base * 8 + (lam & 3)) + (lam >> 2);
+#pragma unroll
+    for (int c = 0; c < R; ++c) { q[c * 16] = xr[c]; q[c * 16 + 8] = xi[c]; }
+}
+
 // One fused pass over the pairing units of thread t:
 //   [FWD: last forward FFT stage] -> items (post / update / pre in registers, functor f) -> [INV: first
 //   inverse FFT stage], in place in the tile.  Units are processed one after the other (2 * RL complex
 //   points live).
-template <int N, bool FWD, bool INV, class F>
+template <int N, bool FWD, bool INV, class F, bool XIN = false, bool XOUT = false>
 CHS_DEV void fused_units(double2* scl, int t, F& f) {
     using P = Pairing<N>;
     constexpr int M = N / 2, RL = P::RL;
+    // XIN / XOUT: the input / output side of the pass is in piece form (scl = tile base + line)
+    const int lam = (XIN || XOUT) ? (int)(threadIdx.x & 7) : 0;
+    double2* sc0 = scl - lam;
     f.begin(t);
 #pragma unroll 1
     for (int i = 0; i < P::NU; ++i) {
@@ -538,8 +563,14 @@ CHS_DEV void fused_units(double2* scl, int t, F& f) {
         const int rho_a = u, rho_b = (u == 0) ? P::Q / 2 : P::Q - u;
         const int base_a = freq_pos<M>(rho_a), base_b = freq_pos<M>(rho_b);
         double ar[RL], ai[RL], br[RL], bi[RL];
-        load_block<N, RL>(scl, base_a, ar, ai);
-        load_block<N, RL>(scl, base_b, br, bi);
+        if (XIN) {
+            load_block_x<N, RL>(sc0, lam, base_a, ar, ai);
+            load_block_x<N, RL>(sc0, lam, base_b, br, bi);
+        } else {
+            load_block<N, RL>(scl, base_a, ar, ai);
+            load_block<N, RL>(scl, base_b, br, bi);
+        }
+        if (XIN || XOUT) CHS_SYNCWARP();         // the partner lane has read the pieces this lane overwrites
         if (FWD) {
             dft<RL, false>(ar, ai);
             dft<RL, false>(br, bi);
@@ -549,8 +580,13 @@ CHS_DEV void fused_units(double2* scl, int t, F& f) {
             dft<RL, true>(ar, ai);
             dft<RL, true>(br, bi);
         }
-        store_block<N, RL>(scl, base_a, ar, ai);
-        store_block<N, RL>(scl, base_b, br, bi);
+        if (XOUT) {
+            store_block_x<N, RL>(sc0, lam, base_a, ar, ai);
+            store_block_x<N, RL>(sc0, lam, base_b, br, bi);
+        } else {
+            store_block<N, RL>(scl, base_a, ar, ai);
+            store_block<N, RL>(scl, base_b, br, bi);
+        }
     }
 }
 
@@ -674,7 +710,7 @@ struct ColMid {
 // one tile of the column kernel (out of line in the persistent build: the compiler then
 // allocates registers for the tile body alone)
 template <int N, int MODE>
-CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
+CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
     using G = Geo<N>;
     constexpr int M = G::M, LINES = G::LINES, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
@@ -686,11 +722,15 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
         const int sim = a.sim_index ? a.sim_index[si] : si;
         Sim* S = a.sims + sim;
         const size_t off = (size_t)sim * N * N;
-        // all global traffic of the tile prologue is issued before the first dependent use
-        // tile I/O keeps the 8 adjacent columns in adjacent lanes (64-byte segments) whatever the compute mapping
-        const int lio = G::WARP_LINES ? tid % LINES : l, tio = G::WARP_LINES ? tid / LINES : t;
-        double2* scio = sc + lio * G::LOFF;
-        if (MODE != COL_INV) col_tile_load_async<N>(scio, a.T + off + kx0 + lio, tio);
+        // the tile of T: one contiguous block in the shared-memory layout (pair-major T) -> bulk copies
+        double* gtile = a.T + off + (size_t)tile * (N * LINES);
+        void* bar = sm + G::OFF_FLAG + 1;
+        constexpr unsigned TILE_BYTES = G::TILE_DOUBLES * 8, CHUNK = TILE_BYTES >= 8192 ? 8192 : TILE_BYTES;
+        if (MODE != COL_INV && tid == 0) {
+            chs_mbar_expect_tx(bar, TILE_BYTES);
+            for (unsigned o = 0; o < TILE_BYTES; o += CHUNK)
+                chs_bulk_g2s(reinterpret_cast<char*>(sm) + o, reinterpret_cast<const char*>(gtile) + o, CHUNK, bar);
+        }
         if (MODE == COL_STEP) {
             // the hat_U tile is consumed in the middle of the tile's work: pull it into L2 now
             const double* hp = a.hatU + off + (size_t)tile * N * LINES;          // contiguous 8*N*LINES bytes
@@ -707,8 +747,7 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
             lamx = a.lam[kx];
             gxs = a.gsin[kx];
         }
-        chs_cp_async_wait_all();
-        __syncthreads();
+        if (MODE != COL_INV) chs_mbar_wait(bar, phase);
         if (!halted) {
             // -------- forward column DCT-II up to the last stage
             if (MODE != COL_INV) fft_fwd_range<N, 0, NST - 1, true>(scl, t, s_tw);
@@ -720,8 +759,8 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
             const bool nat = (MODE != COL_STEP) && a.natural;
             // (warp-line geometry: the lanes of a warp are consecutive frequencies of ONE line, so the tile
             // is stored line by line, [tile][LINES][ky], and a warp reads 128 contiguous bytes)
-            mid.hstride = nat ? N : (G::WARP_LINES ? 1 : LINES);
-            const size_t toff = nat ? off + col : off + (size_t)tile * N * LINES + (G::WARP_LINES ? (size_t)l * N : (size_t)l);
+            mid.hstride = nat ? N : LINES;
+            const size_t toff = nat ? off + col : off + (size_t)tile * N * LINES + (size_t)l;
             mid.hat = ((MODE == COL_FWD && a.dst) ? a.dst : a.hatU) + toff;
             mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + toff;
             mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
@@ -735,7 +774,6 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
                 line_barrier<N, true>();
                 // -------- remaining inverse stages
                 fft_inv_range<N, 0, NST - 1, true>(scl, t, s_tw);
-                if (G::WARP_LINES) __syncthreads();              // what follows crosses lines (edge terms, transposing store)
                 // -------- partial sums: spectral gradient energy + one-sided y-edge terms
                 if (MODE == COL_STEP && tid == 0) {
                     double v[1];
@@ -750,8 +788,14 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm) {
                     pp[P_GE * G::NTILES] = v[0];
                     pp[P_GYE * G::NTILES] = 0.75 * e;
                 }
-                // -------- store T tile
-                col_tile_store<N>(scio, a.T + off + kx0 + lio, tio);
+                // -------- store T tile: the last stage's barrier has passed; generic-proxy writes -> async proxy
+                chs_fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    for (unsigned o = 0; o < TILE_BYTES; o += CHUNK)
+                        chs_bulk_s2g(reinterpret_cast<char*>(gtile) + o, reinterpret_cast<const char*>(sm) + o, CHUNK);
+                    chs_bulk_commit_wait();
+                }
             }
         }
 }
@@ -761,11 +805,15 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
     using G = Geo<N>;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    if (threadIdx.x == 0) chs_mbar_init(sm + G::OFF_FLAG + 1, 1);
+    __syncthreads();
     CHS_PDL_TRIGGER();               // the next kernel of the stream may be scheduled from here on ...
     CHS_PDL_WAIT();                  // ... and this one touches global memory only after its predecessor is complete
     const int total = G::NTILES * a.nsims;
+    unsigned phase = 0;
     CHS_TILE_LOOP(w, total) {
-        k_col_tile<N, MODE>(a, w, sm);
+        k_col_tile<N, MODE>(a, w, sm, phase);
+        phase ^= 1;
         __syncthreads();                 // the tile buffer is reused by the next iteration
     }
     chs_cp_async_wait_all();
@@ -837,9 +885,9 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
         Sim* S = a.sims + sim;
         const size_t off = (size_t)sim * N * N;
         // tile prologue: every global access is issued before the first dependent use
-        if (MODE == ROW_STEP || MODE == ROW_INV) row_tile_load_slots_async<N>(sc, a.T + off + (size_t)row0 * N, tid);
+        if (MODE == ROW_STEP || MODE == ROW_INV) row_tile_pairs_io<N, false>(sc, a.T + off, tile, tid);
         if (control) stage_simk<G>(sm, S, tid);
-        const bool ra_line = sums && (row0 + l == ra_row);
+        const bool ra_line = sums && (row0 + pair_rowoff(l) == ra_row);     // line l of the tile is row row0 + pair_rowoff(l)
         const bool ra_tile = sums && (ra_row >= row0) && (ra_row < row0 + LINES);
         bool slow = false;                  // adaptive-dt column sums / jitter / prologue: unfused middle
         bool want_cols = false;
@@ -854,17 +902,18 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
         }
         if (MODE == ROW_FWD_U || MODE == ROW_FWD_MU) {
             const double* src = (MODE == ROW_FWD_U && a.src) ? a.src : a.U;
-            row_tile_load_phys<N>(sm, src + off + (size_t)row0 * N, tid);
+            row_tile_load_phys<N, true>(sm, src + off + (size_t)row0 * N, tid);
         }
         chs_cp_async_wait_all();
         __syncthreads();
         if (!halted) {
             // ============= inverse half: T rows (slot order) -> U rows (Makhoul order in smem)
             if (MODE == ROW_STEP || MODE == ROW_INV) {
-                if (ra_line && t == 0) ra_scr[0] = scl[G::idx(0)].x * sqrt(1.0 / N);   // row mean = C[0]/sqrt(N)
-                {   // fused: pre + first inverse stage
+                if (ra_line && t == 0)                                     // row mean = C[0]/sqrt(N); C[0] = slot 0 of the row's piece
+                    ra_scr[0] = reinterpret_cast<const double*>(sc + (l & 3))[l >> 2] * sqrt(1.0 / N);
+                {   // fused: 2x2 exchange out of the piece form + pre + first inverse stage
                     RowPre<N> pre{s_om};
-                    fused_units<N, false, true>(scl, t, pre);
+                    fused_units<N, false, true, RowPre<N>, true, false>(scl, t, pre);
                 }
                 line_barrier<N, true>();
                 fft_inv_range<N, 1, NST - 1, true>(scl, t, s_tw);
@@ -875,7 +924,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
             }
             if (MODE == ROW_INV) {
                 double* dstU = (a.dst ? a.dst : a.U) + off + (size_t)row0 * N;
-                row_tile_store_phys<N>(sm, dstU, tid);
+                row_tile_store_phys<N, true>(sm, dstU, tid);
             } else {
                 const double* K = sm + G::OFF_SIM;                 // SimK image (stage_simk)
                 // ============= jitter (solver.py:210-211): U += jitter*(2*noise - 1); U is state now
@@ -892,8 +941,8 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
 #pragma unroll
                         for (int j = 0; j < UNR; ++j) {
                             const int i = tid + (j0 + j) * NT;
-                            const int l2 = i / N, x = i % N;
-                            double* q = sm + real_off<N>(mk_pos<N>(x)) + 2 * G::LOFF * l2;
+                            const int y = i / N, x = i % N;                   // row y of the tile is line pair_lineof(y)
+                            double* q = sm + real_off<N>(mk_pos<N>(x)) + 2 * G::LOFF * pair_lineof(y);
                             const double u = *q + jv * (2.0 * z[j] - 1.0);
                             *q = u;
                             dstU[i] = u;
@@ -948,7 +997,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                         if (!slow) {
 #pragma unroll
                             for (int q = 1; q < R0; ++q) {
-                                const double2 wv = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : __ldg(s_tw + j * q);
+                                const double2 wv = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : tab_tw<N>(s_tw, j * q);
                                 const double x = xr[q], y = xi[q];
                                 xr[q] = x * wv.x + y * wv.y;               // conj twiddle, then inverse DFT
                                 xi[q] = y * wv.x - x * wv.y;
@@ -960,7 +1009,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                             dft<R0, false>(xr, xi);
 #pragma unroll
                             for (int q = 1; q < R0; ++q) {
-                                const double2 wv = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : __ldg(s_tw + j * q);   // (L1 hit)
+                                const double2 wv = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : tab_tw<N>(s_tw, j * q);   // (L1 hit)
                                 const double x = xr[q], y = xi[q];
                                 xr[q] = x * wv.x - y * wv.y;
                                 xi[q] = x * wv.y + y * wv.x;
@@ -1031,12 +1080,12 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                 }
                 // ============= forward half: remaining stages, fused last stage + post, store
                 fft_fwd_range<N, 1, NST - 1, true>(scl, t, s_tw);
-                {
+                {   // fused: last forward stage + post + 2x2 exchange into the piece form
                     RowPost<N> post{s_om};
-                    fused_units<N, true, false>(scl, t, post);
+                    fused_units<N, true, false, RowPost<N>, false, true>(scl, t, post);
                 }
                 __syncthreads();
-                row_tile_store_slots<N>(sc, ((MODE == ROW_FWD_U && a.dst) ? a.dst : a.T) + off + (size_t)row0 * N, tid);
+                row_tile_pairs_io<N, true>(sc, a.T + off, tile, tid);
                 // ============= control (with jitter k_diag finishes the iteration instead)
                 if (control && !jit) {
                     bool is_last;

@@ -48,6 +48,9 @@ template <int N, int MODE>
 CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs a) {
     CHS_PDL_TRIGGER();
     CHS_PDL_WAIT();               // programmatic dependent launch: nothing is read before the predecessor is complete
+    // device-side stop flag (energy stop, time limit, NaN): a stopped simulation is frozen -- U, H, A, B
+    // keep the state of the stopping step whatever the host still has queued (solver.py:199,247 break)
+    if ((MODE == S_STEP || MODE == S_YSTEP) && a.S->halted) return;
     using G = Geo<N>;
     constexpr int M = G::M, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
@@ -151,7 +154,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                     dft<R0, false>(xr, xi);
 #pragma unroll
                     for (int q = 1; q < R0; ++q) {
-                        const double2 w = G::STAGED_TABLES ? __ldg(a.tw + (q - 1) * ST0 + j) : __ldg(a.tw + j * q);
+                        const double2 w = G::STAGED_TABLES ? __ldg(a.tw + (q - 1) * ST0 + j) : tab_tw<N>(a.tw, j * q);
                         const double x = xr[q], y = xi[q];
                         xr[q] = x * w.x - y * w.y;
                         xi[q] = x * w.y + y * w.x;
@@ -352,6 +355,7 @@ CHS_KERNEL void k_slab_control(Sim* S, const double* vec, double* rows, long lon
     CHS_PDL_TRIGGER();
     CHS_PDL_WAIT();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (S->halted && post != 2) return;          // stopped: no further rows, no time accounting
     const chs_params& p = S->p;
     if (post == 2) {                     // Solver.prepare(): row 0 (solver.py:117-135)
         const double N2 = (double)N * (double)N, L2sq = p.L * p.L;

@@ -24,6 +24,33 @@ namespace chs {
 
 CHS_CX constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 
+// Twiddle tables tw (M entries) and om (N + N/4 entries) of the batched sizes N = 32 .. 1024 can live in
+// CONSTANT memory (-DCHS_CONST_TABLES=1): one 56 KB image for all sizes (N at double2 offset
+// 1.75 (N - 32): tw, then om), read with indexed LDC -- off the L1/LSU data pipe that the tile traffic
+// saturates.  Accessors tab_tw<N>/tab_om<N> fall back to the global tables (line-major sizes, host build).
+#ifndef CHS_CONST_TABLES
+#define CHS_CONST_TABLES 0
+#endif
+#define CHS_CTAB_ENTRIES 3584
+#if CHS_CONST_TABLES && !defined(CHS_EMU)
+__constant__ double2 c_tab[CHS_CTAB_ENTRIES];
+#endif
+CHS_CX constexpr int ctab_off(int N) { return 7 * (N - 32) / 4; }
+template <int N>
+CHS_DEV double2 tab_tw(const double2* __restrict__ tw, int i) {
+#if CHS_CONST_TABLES && !defined(CHS_EMU)
+    if constexpr (N <= 1024) return c_tab[ctab_off(N) + i];
+#endif
+    return __ldg(tw + i);
+}
+template <int N>
+CHS_DEV double2 tab_om(const double2* __restrict__ om, int i) {
+#if CHS_CONST_TABLES && !defined(CHS_EMU)
+    if constexpr (N <= 1024) return c_tab[ctab_off(N) + N / 2 + i];
+#endif
+    return __ldg(om + i);
+}
+
 #ifdef CHS_EMU
 static inline double chs_fmad(double a, double b, double c) { return std::fma(a, b, c); }
 #else
@@ -80,25 +107,19 @@ struct Geo {
     // are resident per SM and overlap each other's load / transform / store phases
     static constexpr int LINES = geo_lines(N);
     // Two tile layouts (complex point c of line l, in double2 units):
-    //   point-major (N <= 1024): c*LPC + l, the lines of a point adjacent (they are the lanes of
-    //     a warp), odd pitch for the transposing tile I/O;
+    //   point-major (N <= 1024): c*LINES + l, the lines of a point adjacent (they are the lanes of a
+    //     warp: a quarter-warp's 16-byte accesses are one contiguous 128-byte wavefront for any
+    //     butterfly stride); the tile is exactly 16*M*LINES bytes, which is also the layout of one
+    //     column tile of T in HBM (see "pair-major T" in chs_kernels.cuh): the column kernel moves its
+    //     tile with ONE bulk copy each way;
     //   line-major (N >= 2048): l*LOFF + c + pad(c), every warp works on ONE line so that its
     //     16-byte accesses are contiguous; pad() skews the 8-point blocks of the fused last stage
     //     (the blocks of 8 consecutive residues lie M/8, M/16, ... apart: the top digits of the
     //     position) over the banks.  pad is additive over the strides the stages use, see step().
-#ifndef CHS_WARP_LINES
-#define CHS_WARP_LINES 0
-#endif
-    // Optional geometry for N = 256 .. 1024 (batched kernels, -DCHS_WARP_LINES=1): line-major too, with
-    // the M/16 <= 32 threads of a line inside ONE warp -- the FFT stages of a line then need only
-    // __syncwarp, and the warps of a CTA drift apart instead of meeting at a block barrier after every
-    // stage.  Correct (parity suite, ThreadSanitizer on the host emulation) but measured SLOWER on
-    // B200 (195 k vs 224 k sim-steps/s): k_row gains 3 % (barrier stalls 9.4 -> 5.5 %), k_col loses
-    // 33 % -- with the lines of a point in adjacent lanes every twiddle / lambda / hat_U table load is
-    // one address per 8 lanes (a broadcast); with the points of a line in adjacent lanes each lane
-    // loads its own entry and the L1 pipe saturates (l1tex 70-84 %).  Off by default.
-    static constexpr bool WARP_LINES = CHS_WARP_LINES && (N >= 256) && (N <= 1024);
-    static constexpr bool LINE_MAJOR = (N >= 2048) || WARP_LINES;
+    // (A line-major geometry for N = 256 .. 1024 with the threads of a line inside one warp was measured
+    // in round 1: k_row +3 %, k_col -33 % because every table load stops being a warp broadcast.)
+    static constexpr bool WARP_LINES = false;
+    static constexpr bool LINE_MAJOR = (N >= 2048);
 #ifndef CHS_STAGED_TABLES
 #define CHS_STAGED_TABLES 0
 #endif
@@ -107,7 +128,7 @@ struct Geo {
     // point-major one (4 distinct entries per warp load) measured 216.5 k vs 222 k sim-steps/s at N=512,
     // batch 1024 (-DCHS_STAGED_TABLES=1), so the natural tables stay the default there
     static constexpr bool STAGED_TABLES = LINE_MAJOR || CHS_STAGED_TABLES;
-    static constexpr int LPC = LINE_MAJOR ? 1 : LINES + 1;     // point pitch
+    static constexpr int LPC = LINE_MAJOR ? 1 : LINES;         // point pitch
     // first radix 8: the top 3 position bits; 4: top 2 bits + the low bit of the next digit (x4);
     // 2: the low 2 bits of the second digit + the top bit (x4)
     static constexpr int LG = ilog2c(M), REM = LG % 3;
@@ -119,7 +140,7 @@ struct Geo {
     // idx(base + q*st) = idx(base) + q*step(st) for the points of one butterfly
     CHS_CX static constexpr int step(int st) { return LINE_MAJOR ? st + pad(st) : st * LPC; }
     static constexpr int LOFF_MIN = M + (M >> SH1) + W2 * (M >> SH2);
-    static constexpr int LOFF = LINE_MAJOR ? (WARP_LINES ? ((LOFF_MIN + 6) / 8) * 8 + 1 : LOFF_MIN) : 1;   // line offset (= 1 mod 8 when lines share a CTA)
+    static constexpr int LOFF = LINE_MAJOR ? LOFF_MIN : 1;    // line offset
     // every stage either strides by a multiple of a pad term's period or stays inside one period
     CHS_CX static constexpr bool pad_ok() {
         for (int s = 0; LINE_MAJOR && s < Rad<M>::nst; ++s) {
@@ -141,7 +162,10 @@ struct Geo {
     // processed one after the other instead of all loads first; latency is hidden by the 6 resident CTAs
     // per SM that 80 registers allow, not by the memory-level parallelism of one thread
     static constexpr bool SEQ = CHS_SEQ_STAGES && !LINE_MAJOR;
-    static constexpr int REGS = SEQ ? 80 : 128;
+#ifndef CHS_REGS
+#define CHS_REGS 128
+#endif
+    static constexpr int REGS = LINE_MAJOR ? 128 : CHS_REGS;
     static constexpr int MINB = (65536 / REGS) / NT > 16 ? 16 : ((65536 / REGS) / NT > 0 ? (65536 / REGS) / NT : 1);   // CTAs per SM
 #ifndef CHS_MINB_ROW
 #define CHS_MINB_ROW MINB
@@ -152,25 +176,21 @@ struct Geo {
     static constexpr int MINB_ROW = (NT == 128) ? CHS_MINB_ROW : MINB;   // N = 512: tuned on B200 (profiles/)
     static constexpr int MINB_COL = (NT == 128) ? CHS_MINB_COL : MINB;
     static constexpr int TILE_DOUBLES = LINE_MAJOR ? 2 * LINES * LOFF : 2 * M * LPC;
-    // fast_log table (CHS_LOG_N double2): in the point-major tile it lives in the PAD slot of the first
-    // CHS_LOG_N points (slot LINES of point c, never touched by the transforms), otherwise after the tile
-    static constexpr bool LOG_IN_PAD = !LINE_MAJOR && M >= CHS_LOG_N;
-    static constexpr int LOG_STRIDE = LOG_IN_PAD ? LPC : 1;    // in double2
-    // scratch after the tile (doubles): flag | x/y edge values | Ra | Sim image | fast_log table | reduction
-    static constexpr int OFF_FLAG = TILE_DOUBLES;
+    static constexpr int LOG_STRIDE = 1;                       // fast_log table entry pitch (double2)
+    // scratch after the tile (doubles): flag, mbarrier | x/y edge values | Ra | Sim image | fast_log table | reduction
+    static constexpr int OFF_FLAG = TILE_DOUBLES;              // int flag; OFF_FLAG + 1: the bulk-copy mbarrier
     static constexpr int OFF_EDGE = OFF_FLAG + 2;              // [LINES][4]
     static constexpr int OFF_RA = OFF_EDGE + 4 * LINES;        // mean, spare, then TPL partials
     static constexpr int OFF_SIM = OFF_RA + 2 + TPL + (TPL & 1);         // staged per-simulation constants (CHS_SIMK doubles)
-    static constexpr int OFF_LOGTAB = OFF_SIM + CHS_SIMK;      // (keeps double2 alignment)
-    static constexpr int OFF_RED = OFF_LOGTAB + (LOG_IN_PAD ? 0 : 2 * CHS_LOG_N);   // (NT/32)*4 + 4 doubles on the GPU; NT*8 in the host emulation
+    static constexpr int OFF_LOGTAB = OFF_SIM + CHS_SIMK;      // CHS_LOG_N double2 (keeps double2 alignment)
+    static constexpr int OFF_RED = OFF_LOGTAB + 2 * CHS_LOG_N; // (NT/32)*4 + 4 doubles on the GPU; NT*8 in the host emulation
     static constexpr int SMEM_BYTES = (OFF_RED + (NT / 32) * 4 + 4) * 8;
-    CHS_CX static constexpr int log_off() { return LOG_IN_PAD ? 2 * LINES : OFF_LOGTAB; }   // doubles from the tile base
+    CHS_CX static constexpr int log_off() { return OFF_LOGTAB; }          // doubles from the tile base
     static_assert(N >= 32 && (N & (N - 1)) == 0, "FFT path needs a power of two >= 32");
     static_assert((Rad<M>::RL == 8 || Rad<M>::RL == 4) && Rad<M>::nst >= 2, "plan must end with a radix-8 or radix-4 stage");
     static_assert((OFF_LOGTAB % 2) == 0 && (OFF_SIM % 2) == 0, "double2 alignment");
     static_assert(pad_ok(), "bank skew is not additive for this radix plan");
     static_assert(!LINE_MAJOR || (SH1 >= 3 && (W2 == 0 || SH2 >= 3)), "skew must be constant inside an 8-point block");
-    static_assert(!WARP_LINES || (32 % TPL == 0), "the threads of a line must share a warp");
 };
 
 // Makhoul reorder: physical index n -> position in v
@@ -278,7 +298,7 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
             if (st > 1) {
 #pragma unroll
                 for (int q = 1; q < r; ++q) {
-                    const double2 w = G::STAGED_TABLES ? __ldg(tw + Rad<M>::tws_off(S) + (q - 1) * st + j) : __ldg(tw + j * q * (M / Lb));
+                    const double2 w = G::STAGED_TABLES ? __ldg(tw + Rad<M>::tws_off(S) + (q - 1) * st + j) : tab_tw<N>(tw, j * q * (M / Lb));
                     const double a = xr[q], b = xi[q];
                     if (!INV) { xr[q] = a * w.x - b * w.y; xi[q] = a * w.y + b * w.x; }
                     else      { xr[q] = a * w.x + b * w.y; xi[q] = b * w.x - a * w.y; }     // conj(w)
@@ -310,7 +330,7 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
         if (st > 1) {
 #pragma unroll
             for (int p = 1; p < r; ++p) {
-                const double2 w = G::STAGED_TABLES ? __ldg(tw + Rad<M>::tws_off(S) + (p - 1) * st + j) : __ldg(tw + j * p * (M / Lb));
+                const double2 w = G::STAGED_TABLES ? __ldg(tw + Rad<M>::tws_off(S) + (p - 1) * st + j) : tab_tw<N>(tw, j * p * (M / Lb));
                 const double a = xr[i][p], b = xi[i][p];
                 if (!INV) { xr[i][p] = a * w.x - b * w.y; xi[i][p] = a * w.y + b * w.x; }
                 else      { xr[i][p] = a * w.x + b * w.y; xi[i][p] = b * w.x - a * w.y; }     // conj(w)
@@ -365,7 +385,7 @@ template <int N>
 CHS_DEV void post_pair(int k, const double2* __restrict__ om, double ar, double ai, double br, double bi,
                        double (&c)[4]) {
     constexpr int M = N / 2;
-    const double2 t = __ldg(om + N + k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    const double2 t = tab_om<N>(om, N + k), wk = tab_om<N>(om, k), wm = tab_om<N>(om, M - k);
     const double er = ar + br, ei = ai - bi;                  // 2E
     const double o_r = ai + bi, o_i = br - ar;                // 2O = -i (a - conj b)
     const double tr = t.x * o_r - t.y * o_i, ti = t.x * o_i + t.y * o_r;
@@ -382,7 +402,7 @@ CHS_DEV void post_special(const double2* __restrict__ om, double ar, double ai, 
                           double (&c)[4]) {
     constexpr int M = N / 2;
     const double rn = sqrt(1.0 / N);
-    const double2 w = __ldg(om + M / 2);       // sc * exp(-i pi/8), sc = s/2
+    const double2 w = tab_om<N>(om, M / 2);       // sc * exp(-i pi/8), sc = s/2
     c[0] = rn * (ar + ai);
     c[1] = rn * (ar - ai);
     c[2] = 2.0 * (w.x * hr + w.y * hi);        // s Re(w * conj(Zh))
@@ -393,7 +413,7 @@ template <int N>
 CHS_DEV void pre_pair(int k, const double2* __restrict__ om, const double (&c)[4], double& ar, double& ai,
                       double& br, double& bi) {
     constexpr int M = N / 2;
-    const double2 t = __ldg(om + N + k), wk = __ldg(om + k), wm = __ldg(om + (M - k));
+    const double2 t = tab_om<N>(om, N + k), wk = tab_om<N>(om, k), wm = tab_om<N>(om, M - k);
     const double vr = wk.x * c[0] - wk.y * c[1], vi = -wk.x * c[1] - wk.y * c[0];       // sc conj(wk)(c0 - i c1)
     const double v2r = wm.x * c[2] - wm.y * c[3], v2i = -wm.x * c[3] - wm.y * c[2];
     const double er = vr + v2r, ei = vi - v2i;                // E
@@ -408,7 +428,7 @@ CHS_DEV void pre_special(const double2* __restrict__ om, const double (&c)[4], d
                          double& hr, double& hi) {
     constexpr int M = N / 2;
     const double rn = sqrt(1.0 / N);
-    const double2 w = __ldg(om + M / 2);       // sc * exp(-i pi/8); 1/(s M) = 2 sc
+    const double2 w = tab_om<N>(om, M / 2);       // sc * exp(-i pi/8); 1/(s M) = 2 sc
     ar = rn * (c[0] + c[1]);
     ai = rn * (c[0] - c[1]);
     const double u = 2.0 * c[2], v = -2.0 * c[3];             // A/(sM) = (u + i v) * sc

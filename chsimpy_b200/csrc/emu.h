@@ -110,6 +110,15 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent
 static inline void chs_cp_async16(void* d, const void* s) { std::memcpy(d, s, 16); }
 static inline void chs_cp_async8(void* d, const void* s) { std::memcpy(d, s, 8); }
 static inline void chs_cp_async_wait_all() {}
+// bulk copies: synchronous memcpy in the host build (the mbarrier is a no-op)
+static inline void chs_mbar_init(void*, unsigned) {}
+static inline void chs_mbar_expect_tx(void*, unsigned) {}
+#define chs_mbar_wait(bar, parity) emu::g_bar->arrive_and_wait()      /* the copying thread arrives after its memcpy */
+static inline void chs_bulk_g2s(void* d, const void* s, unsigned n, void*) { std::memcpy(d, s, n); }
+static inline void chs_bulk_s2g(void* d, const void* s, unsigned n) { std::memcpy(d, s, n); }
+static inline void chs_fence_async_smem() {}
+static inline void chs_bulk_commit_wait() {}
+#define CHS_SYNCWARP() emu::t_wbar->arrive_and_wait()
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 3; return 0; }   // 3 "SMs": exercises the persistent loops
 template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 1; return 0; }

@@ -117,6 +117,27 @@ def test_slab_path_emulated(be):
     assert abs(sol.U.mean() - s.U_init.mean()) < 1e-14
 
 
+def test_slab_path_honours_stop_flag(be):
+    """A time limit hit at step ~10 while the host has 40 steps queued (full_sim, so no poll inside the
+    chunk): the slab kernels must freeze the state behind the device-side flag exactly like the batched
+    path -- computed_steps, row count, time_passed and U are those of the stopping step (oracle)."""
+    import ch_oracle as orc
+    kw = dict(N=64, seed=2023, kappa_tilde=3e-4, full_sim=True, time_max=0.3)
+    o = orc.run_default(nsteps=40, **kw)
+    assert o.stop_reason == "time-limit" and 5 < o.computed_steps < 30
+    for force in (False, True):
+        p = ch.Parameters()
+        p.N, p.no_gui, p.full_sim, p.kappa_tilde, p.ntmax, p.time_max = 64, True, True, 3e-4, 40, 0.3
+        s = ch.Solver(p, _backend=be, _force_slab=force)
+        s.prepare()
+        sol = s.solve_or_resume(40)
+        assert sol.stop_reason == "time-limit" and sol.computed_steps == o.computed_steps, (force, sol.computed_steps)
+        assert sol.timedata.data().shape == o.rows.shape
+        assert abs(s.time_passed - o.time_passed) <= 1e-12 * o.time_passed
+        assert sol.tau0 == o.tau0 and sol.t0 == o.t0
+        assert np.abs(sol.U - o.U).max() < 1e-13
+
+
 def test_gemm_path_emulated_vs_oracle(be):
     """DCT-as-GEMM path (chs_gemm.cuh) at a non-power-of-two N, in-kernel time loop with a
     re-entry, against the oracle (the tensor-core MMA is replaced by scalar dot products in

@@ -243,6 +243,23 @@ def test_slab_path_single_gpu(name, force):
     assert sol.computed_steps == m["computed_steps"]
 
 
+def test_slab_path_energy_stop():
+    """The slab path (default for N > 1024, where full_sim defaults to False) must honour the device-side
+    stop flag: the 8280-step run to the energy stop, 128 steps queued per host poll, forced onto the slab
+    kernels -- computed_steps, tau0, t0, the row count and U are those of the stopping step."""
+    import chsimpy_b200 as ch
+    z, m = load("n64_cinit089_stop")
+    p = make_params(m)
+    s = ch.Solver(p, _force_slab=True)
+    s.prepare()
+    sol = s.solve_or_resume(p.ntmax)
+    assert sol.stop_reason == "energy" and sol.computed_steps == m["computed_steps"] == 8280
+    assert sol.tau0 == m["tau0"] and abs(sol.t0 - m["t0"]) <= 1e-12 * m["t0"]
+    assert sol.timedata.data().shape[0] == z["rows"].shape[0]
+    check_rows(sol.timedata.data(), z["rows"], 64)
+    assert np.abs(sol.U - z["U"]).max() <= U_TOL
+
+
 def test_cli_and_simulator_chunked(tmp_path, monkeypatch):
     """`python -m chsimpy_b200`-style flow (reference __main__.py:8-25) and the chunked
     `update_every` path of Simulator.solve (simulator.py:56-87) incl. csv/yaml export."""
