@@ -128,9 +128,18 @@ struct KArgs {
 
 #ifdef CHS_EMU
 #define CHS_LDCG(p) (*(p))
+#define CHS_LDCS(p) (*(p))
 #define CHS_PREFETCH_L2(p) ((void)0)
 #else
 #define CHS_LDCG(p) __ldcg(p)
+#ifndef CHS_HAT_STREAM
+#define CHS_HAT_STREAM 0        /* measured: 242 k vs 248 k sim-steps/s with evict-first loads */
+#endif
+#if CHS_HAT_STREAM
+#define CHS_LDCS(p) __ldcs(p)        /* streaming (evict-first): hat_U has no reuse and must not push the tables out of L1 */
+#else
+#define CHS_LDCS(p) (*(p))
+#endif
 #define CHS_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 
@@ -379,20 +388,49 @@ template <int N>
 CHS_DEV int pair_c(int r, int pi) { return (pi < 2) ? 2 * r + pi : (N / 2 - 1) - 2 * r - (pi - 2); }
 
 // row tile r of pair-major T <-> shared memory: piece (pi, slot s) = (T[y0][s], T[y1][s]) at point p = s/2,
-// line pi + 4 (s & 1).  A quarter-warp touches 4 x 32 contiguous bytes of HBM and one 128-byte wavefront.
+// line pi + 4 ((s & 1) ^ piece_flip(p)).  A quarter-warp touches 4 x 32 contiguous bytes of HBM and one
+// 128-byte wavefront.  piece_flip: the four threads of a warp work on points M/radix(0) apart, i.e. in the
+// same 64-byte half of their 128-byte point rows -- flipping the halves with that bit of p spreads the
+// 64-bit accesses of the exchange passes over all banks.
+template <int N>
+CHS_DEV int piece_flip(int p) { return (p >> ilog2c((N / 2) / Rad<N / 2>::radix(0))) & 1; }
 template <int N, bool STORE>
 CHS_DEV void row_tile_pairs_io(double2* sc, double* __restrict__ gT /* simulation base */, int r, int tid) {
     using G = Geo<N>;
     static_assert(G::LINES == 8 && !G::LINE_MAJOR && G::NT % 8 == 0, "pair-major T needs the 8-line point-major tile");
-    constexpr int M = G::M, CNT = 8 * M / G::NT;
-    const int lam = tid & 7, pi = lam & 3, h = lam >> 2;
-    double2* g2 = reinterpret_cast<double2*>(gT) + (size_t)pair_c<N>(r, pi) * 8 + h;
-#pragma unroll 8
-    for (int j = 0; j < CNT; ++j) {
-        const int p = (tid + j * G::NT) >> 3;
-        double2* g = g2 + (size_t)(p >> 2) * (M * 8) + 2 * (p & 3);
-        if (STORE) *g = sc[p * 8 + lam];
-        else chs_cp_async16(sc + p * 8 + lam, g);
+    constexpr int M = G::M, TPL = G::TPL, CNT = 8 * M / G::NT;         // CNT = 16 pieces per thread
+    // thread -> (line lam, points p = p0 + j TPL): p & 3 and the line are fixed per thread, and piece_flip(p)
+    // is bit FB of j (p0 < TPL <= M/radix(0)): every address is base + compile-time offset
+    constexpr int FB = ilog2c((M / Rad<M>::radix(0)) / TPL);
+    static_assert((M / Rad<M>::radix(0)) % TPL == 0 && CNT == 16, "piece_flip must be a bit of j");
+    const int lam = tid & 7, pi = lam & 3, h = lam >> 2, p0 = tid >> 3;
+    double2* g0 = reinterpret_cast<double2*>(gT) + (size_t)pair_c<N>(r, pi) * 8 + (size_t)(p0 >> 2) * (M * 8) + 2 * (p0 & 3);
+    double2* s0 = sc + p0 * 8 + lam;
+    constexpr int GJ = (TPL >= 4) ? (TPL / 4) * (M * 8) : 0;           // global stride of j (TPL >= 4: p>>2 advances by TPL/4)
+    static_assert(TPL >= 4 || true, "");
+    if constexpr (TPL >= 4) {
+        if (STORE) {
+#pragma unroll
+            for (int j0 = 0; j0 < CNT; j0 += 8) {
+                double2 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = s0[(j0 + j) * TPL * 8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g0[(size_t)(j0 + j) * GJ + (h ^ (((j0 + j) >> FB) & 1))] = v[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CNT; ++j) chs_cp_async16(s0 + j * TPL * 8, g0 + (size_t)j * GJ + (h ^ ((j >> FB) & 1)));
+        }
+    } else {                                                           // tiny tiles (N = 32, 64): generic addressing
+        double2* g2 = reinterpret_cast<double2*>(gT) + (size_t)pair_c<N>(r, pi) * 8;
+#pragma unroll
+        for (int j = 0; j < CNT; ++j) {
+            const int p = p0 + j * TPL;
+            double2* g = g2 + (size_t)(p >> 2) * (M * 8) + 2 * (p & 3) + (h ^ piece_flip<N>(p));
+            if (STORE) *g = sc[p * 8 + lam];
+            else chs_cp_async16(sc + p * 8 + lam, g);
+        }
     }
 }
 
@@ -534,15 +572,17 @@ CHS_DEV void store_block(double2* scl, int base, const double (&xr)[R], const do
 // Lanes lambda and lambda^4 read / write the same two pieces: loads and stores are separated by __syncwarp.
 template <int N, int R>
 CHS_DEV void load_block_x(const double2* sc, int lam, int base, double (&xr)[R], double (&xi)[R]) {
+    const int f = 8 * piece_flip<N>(base);                 // constant over the block (R consecutive points)
     const double* q = reinterpret_cast<const double*>(sc + base * 8 + (lam & 3)) + (lam >> 2);
 #pragma unroll
-    for (int c = 0; c < R; ++c) { xr[c] = q[c * 16]; xi[c] = q[c * 16 + 8]; }
+    for (int c = 0; c < R; ++c) { xr[c] = q[c * 16 + f]; xi[c] = q[c * 16 + (8 - f)]; }
 }
 template <int N, int R>
 CHS_DEV void store_block_x(double2* sc, int lam, int base, const double (&xr)[R], const double (&xi)[R]) {
+    const int f = 8 * piece_flip<N>(base);
     double* q = reinterpret_cast<double*>(sc + base * 8 + (lam & 3)) + (lam >> 2);
 #pragma unroll
-    for (int c = 0; c < R; ++c) { q[c * 16] = xr[c]; q[c * 16 + 8] = xi[c]; }
+    for (int c = 0; c < R; ++c) { q[c * 16 + f] = xr[c]; q[c * 16 + (8 - f)] = xi[c]; }
 }
 
 // One fused pass over the pairing units of thread t:
@@ -638,6 +678,7 @@ struct ColMid {
     double ge;
     double* hat00;               // COL_FWD on the state: where C[0,0] is recorded (Sim::k.hat00), else null
     double hn[4];                // hat_U of the next item (prefetched one item ahead)
+    double2 tn[3];               // ... and its packed lambda / g table entry (COL_STEP)
     CHS_MEM void rows_of(int k, int (&idx)[4]) {
         constexpr int M = N / 2;
         idx[0] = k;
@@ -651,7 +692,11 @@ struct ColMid {
         rows_of(k, idx);
         const double* src = (MODE == COL_INV) ? hat_in : hat;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hn[j] = src[(size_t)idx[j] * hstride];
+        for (int j = 0; j < 4; ++j) hn[j] = CHS_LDCS(src + (size_t)idx[j] * hstride);
+        if (MODE == COL_STEP) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) tn[j] = __ldg(lamg + 3 * k + j);
+        }
     }
     CHS_MEM void begin(int k) { fetch(k); }
     // takes the prefetched hat_U of item k and immediately starts the loads of item kn, which
@@ -662,6 +707,7 @@ struct ColMid {
         double h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) h[j] = hn[j];
+        const double2 l01 = tn[0], l23 = tn[1], gg = tn[2];
         if (kn >= 0) fetch(kn);
         if (MODE == COL_FWD) {
 #pragma unroll
@@ -670,7 +716,6 @@ struct ColMid {
         } else if (MODE == COL_STEP) {
             // one packed table entry per item: lam of the four rows, and g[k] = sin^2(pi k/N) with
             // g[N-k] = g[k], g[M-k] = g[M+k] = 1 - g[k]  (k = 0: rows 0, M, M/2, 3M/2 -> 0, 1, 1/2, 1/2)
-            const double2 l01 = __ldg(lamg + 3 * k), l23 = __ldg(lamg + 3 * k + 1), gg = __ldg(lamg + 3 * k + 2);
             const double lm[4] = {l01.x, l01.y, l23.x, l23.y};
             const double gs[4] = {gg.x + gx, ((k == 0) ? 1.0 : gg.x) + gx, gg.y + gx, gg.y + gx};
 #pragma unroll
@@ -910,7 +955,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
             // ============= inverse half: T rows (slot order) -> U rows (Makhoul order in smem)
             if (MODE == ROW_STEP || MODE == ROW_INV) {
                 if (ra_line && t == 0)                                     // row mean = C[0]/sqrt(N); C[0] = slot 0 of the row's piece
-                    ra_scr[0] = reinterpret_cast<const double*>(sc + (l & 3))[l >> 2] * sqrt(1.0 / N);
+                    ra_scr[0] = reinterpret_cast<const double*>(sc + (l & 3))[l >> 2] * sqrt(1.0 / N);   // (piece_flip(0) = 0)
                 {   // fused: 2x2 exchange out of the piece form + pre + first inverse stage
                     RowPre<N> pre{s_om};
                     fused_units<N, false, true, RowPre<N>, true, false>(scl, t, pre);
@@ -994,10 +1039,15 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                             const double2 v = pj[q * G::step(ST0)];
                             xr[q] = v.x; xi[q] = v.y;
                         }
+#ifndef CHS_KEEP_TW0
+#define CHS_KEEP_TW0 1
+#endif
+                        double2 wk_[CHS_KEEP_TW0 ? R0 : 1];                  // stage-0 twiddles, used in both directions
                         if (!slow) {
 #pragma unroll
                             for (int q = 1; q < R0; ++q) {
                                 const double2 wv = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : tab_tw<N>(s_tw, j * q);
+                                if (CHS_KEEP_TW0) wk_[q] = wv;
                                 const double x = xr[q], y = xi[q];
                                 xr[q] = x * wv.x + y * wv.y;               // conj twiddle, then inverse DFT
                                 xi[q] = y * wv.x - x * wv.y;
@@ -1009,7 +1059,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                             dft<R0, false>(xr, xi);
 #pragma unroll
                             for (int q = 1; q < R0; ++q) {
-                                const double2 wv = G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : tab_tw<N>(s_tw, j * q);   // (L1 hit)
+                                const double2 wv = CHS_KEEP_TW0 ? wk_[q] : (G::STAGED_TABLES ? __ldg(s_tw + (q - 1) * ST0 + j) : tab_tw<N>(s_tw, j * q));
                                 const double x = xr[q], y = xi[q];
                                 xr[q] = x * wv.x - y * wv.y;
                                 xi[q] = x * wv.y + y * wv.x;

@@ -70,8 +70,10 @@ __device__ __forceinline__ void chs_bulk_s2g(void* dst, const void* src_smem, un
                  ::"l"(dst), "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void chs_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void chs_bulk_commit_wait() {      // complete (written), not only read
-    asm volatile("cp.async.bulk.commit_group;\ncp.async.bulk.wait_group 0;" ::: "memory");
+// (.read: the shared-memory source may be reused / the CTA may exit; the writes themselves complete before the
+// grid does -- the epilogue convention of TMA stores)
+__device__ __forceinline__ void chs_bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;\ncp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 #define CHS_SYNCWARP() __syncwarp()
 #endif

@@ -156,11 +156,13 @@ struct Geo {
     static constexpr int NT = LINES * TPL;                     // threads per CTA
     static constexpr int NTILES = N / LINES;
 #ifndef CHS_SEQ_STAGES
-#define CHS_SEQ_STAGES 1
+#define CHS_SEQ_STAGES 0
 #endif
-    // register-light stages for the batched geometry: the butterflies (and pairing units) of a thread are
-    // processed one after the other instead of all loads first; latency is hidden by the 6 resident CTAs
-    // per SM that 80 registers allow, not by the memory-level parallelism of one thread
+    // Register-light stages (-DCHS_SEQ_STAGES=1 -DCHS_REGS=80|96): the butterflies of a thread are processed
+    // one after the other instead of all loads first, which fits 5-6 CTAs per SM.  Measured on B200
+    // (profiles/r2_variants.md): 6 CTAs at 80 registers are SLOWER than 4 at 128 (the L1 data pipe, not
+    // latency, is the limiter: more resident warps only raise mio_throttle / L1 misses), so the default keeps
+    // the batched stages at 128 registers.
     static constexpr bool SEQ = CHS_SEQ_STAGES && !LINE_MAJOR;
 #ifndef CHS_REGS
 #define CHS_REGS 128

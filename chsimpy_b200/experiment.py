@@ -171,6 +171,27 @@ def initial_field(params):
     raise ValueError("generator not supported in ensembles: " + str(params.generator))
 
 
+def _noise_source(params, st):
+    """draw(n) -> the next n (N, N) uniform draws of the members' generator, positioned after the U_init draw.
+    PCG64: regenerated bit-exactly on the device (BatchStepper.pcg64_noise); Sobol: host draws."""
+    N = params.N
+    if params.generator == 'uniform':
+        rng = np.random.Generator(np.random.PCG64(params.seed))
+        rng.bit_generator.advance(N * N)                # U_init = the first (N, N) draw (solver.py:78-82)
+
+        def draw(n):
+            if hasattr(st, "pcg64_noise"):
+                dev = st.pcg64_noise(rng.bit_generator.state, n)
+                rng.bit_generator.advance(n * N * N)
+                return dev
+            return rng.random((n, N, N))
+        return draw
+    from scipy.stats import qmc
+    sob = qmc.Sobol(d=N, seed=params.seed)
+    sob.fast_forward(N)                                 # U_init = the first N points (solver.py:70-71)
+    return lambda n: np.stack([sob.random(N) for _ in range(n)])
+
+
 def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_init=None, host_procs=None,
                    batch_max=2048, poll_every=128, keep_fields=True, backend=None, device=None, timings=None,
                    pipeline_batch=256):
@@ -199,9 +220,15 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
         scal_iter = iter([_host_scalars(j) for j in jobs])
     scal = []
     t_host = 0.0
+    generated = U_init is None and init_params.Uinit_file is None
     if U_init is None:
         U_init = initial_field(init_params)
     assert U_init.shape == (init_params.N, init_params.N)
+    # jitter (reference solver.py:210-211): every member owns a generator with the SAME seed (quirk Q11), whose
+    # stream continues after the U_init draw -- so one noise stream serves all members of a batch
+    jitter_on = init_params.jitter is not None and 0.0 < init_params.jitter < 0.1
+    if jitter_on and (not generated or init_params.generator not in ('uniform', 'sobol')):
+        raise TypeError("'NoneType' object is not callable")      # create_rand is None (quirk Q7)
     out = []
     t_dev = 0.0
     for c0 in range(0, len(members), batch_max):
@@ -221,7 +248,8 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
         st.set_U(U_init)
         row0 = st.prepare()
         iters = max(init_params.ntmax, 0) - 1          # first solve_or_resume call: ntmax-1 iterations (Q3)
-        rows, _ = st.run(iters, poll_every=poll_every)
+        rows, _ = st.run(iters, draw_noise=_noise_source(init_params, st) if jitter_on else None,
+                         poll_every=min(poll_every, 64) if jitter_on else poll_every)
         fields = st.get_U() if keep_fields else None
         states = [st.get_state(j) for j in range(len(chunk))]
         t_dev += time.perf_counter() - td

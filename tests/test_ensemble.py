@@ -37,6 +37,46 @@ def test_factor_table_grid_and_sobol():
     assert n == 5 and rv.shape == (5, 2) and (rv >= 0.995).all() and (rv <= 1.005).all()
 
 
+def test_factor_tables_equal_the_reference_output():
+    """Every A-source against the tables the unmodified reference built (tests/golden/make_factor_tables.py)."""
+    z = np.load(os.path.join(HERE, "golden", "factor_tables.npz"))
+    cases = {"uniform_r7": (7, "uniform", 85972, False), "uniform_r7_indep": (7, "uniform", 85972, True),
+             "sobol_r5": (5, "sobol", 85972, False), "sobol_r6_indep": (6, "sobol", 11, True),
+             "grid_r10": (10, "grid", None, False), "grid_r17_indep": (17, "grid", None, True)}
+    for name, (runs, src, seed, indep) in cases.items():
+        ep = ex.ExperimentParams()
+        ep.runs, ep.A_source, ep.A_seed, ep.independent = runs, src, seed, indep
+        rv, A_list, n = ex.factor_table(ep)
+        assert A_list is None and n == int(z[name + "_n"]), name
+        assert rv.shape == z[name].shape and np.array_equal(rv, z[name]), name      # bit-identical
+
+
+def test_ensemble_jitter_uses_the_members_noise_stream():
+    """--jitter in an ensemble: every member continues the PCG64(seed) stream after the U_init draw
+    (reference solver.py:78-82,210-211; same seed for all members, Q11) -- so a one-member ensemble with
+    factors (1, 1) must equal the plain Solver run, and the noise must actually be applied."""
+    sys.path.insert(0, HERE)
+    from emu_lib import EmuBackend
+    be = EmuBackend()
+    p = _params()
+    p.jitter, p.ntmax = 0.004, 9
+    rv = np.ones((2, 2))
+    rv[1] = [1.003, 0.998]
+    res = ex.solve_ensemble(p, rv, None, host_procs=1, backend=be)
+    s = ch.Solver(p.deepcopy(), _backend=be)
+    s.prepare()
+    sol = s.solve_or_resume(p.ntmax)
+    got = res[0]["solution"]
+    assert got.computed_steps == sol.computed_steps == 9
+    assert np.array_equal(got.timedata.data(), sol.timedata.data())
+    assert np.array_equal(got.U, sol.U) and not np.array_equal(got.U, s.U_init)
+    assert not np.array_equal(res[1]["solution"].U, got.U)
+    p2 = _params()
+    p2.jitter, p2.generator = 0.004, "lcg"
+    with pytest.raises(TypeError):                      # create_rand is None for -g lcg (quirk Q7)
+        ex.solve_ensemble(p2, rv, None, host_procs=1, backend=be)
+
+
 def test_shard_covers_everything_once():
     for n in (1, 7, 8, 1024, 1025):
         for w in (1, 2, 3, 8):
