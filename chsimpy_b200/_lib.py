@@ -52,6 +52,7 @@ PROTOTYPES = {
     "chs_idctn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "chs_pcg64_fill": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64]),
     "chs_row_means": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "chs_lcg_fill": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "chs_debug_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "chs_launch_count": (C.c_int64, [C.c_void_p]),
     "chs_slab_supports_n": (C.c_int32, [C.c_int32]),
@@ -89,16 +90,33 @@ def _stale(lib_path):
 
 
 def build(force=False, verbose=False):
-    """Compiles csrc/chs_api.cu for sm_100a into chsimpy_b200/libchs_b200.so (in-tree)."""
+    """Compiles csrc/chs_api.cu for sm_100a into chsimpy_b200/libchs_b200.so (in-tree).  Safe under
+    torchrun: one process builds under an exclusive file lock into a temporary file that is renamed into
+    place; the others wait for the lock and find the library fresh."""
     if not force and not _stale(LIB_PATH):
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "chs_api.cu")]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libchs_b200.so:\n" + r.stdout + r.stderr)
+    import fcntl
+    import tempfile
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale(LIB_PATH):          # another rank built it while we waited
+                return LIB_PATH
+            nvcc = os.environ.get("NVCC", "nvcc")
+            fd, tmp = tempfile.mkstemp(prefix=".libchs_b200.", suffix=".so.tmp", dir=HERE)
+            os.close(fd)
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "chs_api.cu")]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libchs_b200.so:\n" + r.stdout + r.stderr)
+            os.chmod(tmp, 0o755)
+            os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -117,8 +135,17 @@ def load():
     """Returns the bound CUDA library, building it on first use.  Never falls back."""
     global _lib
     if _lib is None:
-        # CHS_B200_LIB: an alternative build of the SAME CUDA library (tuning experiments only)
-        path = os.environ.get("CHS_B200_LIB") or build()
+        # CHS_B200_LIB: an alternative nvcc build of the SAME CUDA library for tuning experiments
+        # (tools/build_variant.sh -> variants/*.so).  Only files inside this repository's chsimpy_b200/ or
+        # variants/ directories are accepted, and never the host-emulation test harness: no CPU fallback.
+        path = os.environ.get("CHS_B200_LIB")
+        if path:
+            real = os.path.realpath(path)
+            roots = (os.path.realpath(HERE), os.path.realpath(os.path.join(HERE, "..", "variants")))
+            if not any(real.startswith(r + os.sep) for r in roots) or "emu" in os.path.basename(real):
+                raise RuntimeError(f"CHS_B200_LIB={path}: only CUDA builds under chsimpy_b200/ or variants/ may be loaded")
+        else:
+            path = build()
         _lib = bind(C.CDLL(path))
         if _lib.chs_abi_version() != 1:
             raise RuntimeError("libchs_b200.so ABI mismatch")

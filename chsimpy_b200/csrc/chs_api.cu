@@ -1063,6 +1063,12 @@ extern "C" int chs_pcg64_fill(chs_solver* s, uint64_t state_hi, uint64_t state_l
     CHS_CUDA(cudaGetLastError());
     return 0;
 }
+extern "C" int chs_lcg_fill(double* out, int32_t n1, int32_t n2, double seed, void* stream) {
+    if (!out || n1 < 1 || n2 < 1) return fail("chs_lcg_fill: bad argument");
+    CHS_LAUNCH(k_lcg_fill, dim3(1), dim3(1), 0, (cudaStream_t)stream, out, (int)n1, (int)n2, seed);
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
 extern "C" int chs_row_means(chs_solver* s, const double* in, int64_t rows, int64_t cols, double* out) {
     if (!s || !in || !out || rows < 1 || cols < 1) return fail("chs_row_means: bad argument");
 #ifdef CHS_EMU

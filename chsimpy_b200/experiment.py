@@ -222,7 +222,12 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
     t_host = 0.0
     generated = U_init is None and init_params.Uinit_file is None
     if U_init is None:
-        U_init = initial_field(init_params)
+        if init_params.generator == 'lcg' and init_params.Uinit_file is None:
+            from .solver import _CudaBackend, lcg_sample      # the serial float64 LCG as a device kernel
+            be_ = backend if backend is not None else _CudaBackend(device)
+            U_init = init_params.XXX + init_params.XXX * 0.01 * lcg_sample(be_, init_params.N, init_params.N, init_params.seed)
+        else:
+            U_init = initial_field(init_params)
     assert U_init.shape == (init_params.N, init_params.N)
     # jitter (reference solver.py:210-211): every member owns a generator with the SAME seed (quirk Q11), whose
     # stream continues after the U_init draw -- so one noise stream serves all members of a batch

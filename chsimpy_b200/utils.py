@@ -131,6 +131,12 @@ def csv_import_matrix(fname):
     return np.loadtxt(fname, delimiter=',')
 
 
+def yaml_import(fname):
+    """reference utils.py:63-76: the object (Parameters or Solution) stored in a YAML file."""
+    from . import yamlio
+    return yamlio.load_object(fname)
+
+
 def vars_to_list(obj):
     out = []
     for name in dir(obj):

@@ -135,6 +135,10 @@ int chs_idctn(chs_solver*, const double* in, double* out);
 int chs_pcg64_fill(chs_solver*, uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
                    uint64_t offset, double* out, int64_t count);
 int chs_row_means(chs_solver*, const double* in, int64_t rows, int64_t cols, double* out);
+/* The reference's float64 LCG initial-condition generator (chsimpy/mport.py:8-32, pinned by the known-answer
+ * vector of reference tests/test.py:19-37): out[n1][n2] (row-major, device) = matlab_lcg_sample(n1, n2, seed).
+ * The recurrence is serial in float64 (the rounding of a*x is part of the specification): one device thread. */
+int chs_lcg_fill(double* out, int32_t n1, int32_t n2, double seed, void* stream);
 
 /* Self-test hook: y[i] = the device's table-driven natural log of x[i] (csrc/fastlog.cuh),
  * the routine that stands in for np.log at solver.py:173,220.  Device pointers. */

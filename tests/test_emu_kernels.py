@@ -262,3 +262,19 @@ def test_fast_log_accuracy(be):
     assert abs_err.max() <= 1e-18
     y = st.debug_log(np.array([0.0, -1.0, np.inf, np.nan, 5e-324]))
     assert y[0] == -np.inf and np.isnan(y[1]) and y[2] == np.inf and np.isnan(y[3]) and abs(y[4] - np.log(5e-324)) < 1e-12
+
+
+def test_device_lcg_is_the_reference_generator(be):
+    """k_lcg_fill against the reference's only golden vector (reference tests/test.py:25-37: 5 x 4, seed 2023)
+    and bit for bit against the host restatement at the size of `-g lcg -N 64`."""
+    from chsimpy_b200 import mport
+    from chsimpy_b200.solver import lcg_sample
+    known = [[0.5475444293336684, 0.29257702841077793, 0.3117376865408093, 0.9844947126621821],
+             [0.8031704429551821, 0.03775238992541674, 0.37862920778739695, 0.5387215616827465],
+             [0.7217314246677474, 0.7984879318617694, 0.8011069301520972, 0.8502945903922872],
+             [0.5455620291389348, 0.34767496602035824, 0.8863348965003783, 0.8019890788951838],
+             [0.9676096443867356, 0.12967026239711338, 0.008214473728190397, 0.4722352030092083]]
+    got = lcg_sample(be, 5, 4, 2023)
+    assert np.allclose(got, known, rtol=0, atol=1e-15)
+    assert np.array_equal(got, mport.matlab_lcg_sample(5, 4, 2023))
+    assert np.array_equal(lcg_sample(be, 64, 64, 2023), mport.matlab_lcg_sample(64, 64, 2023))

@@ -443,3 +443,14 @@ def test_fast_log_accuracy_on_device():
     assert ulp_err[big].max() <= 1.25 and abs_err[~big].max() <= 1e-18
     y = st.debug_log(np.array([0.0, -1.0, np.nan]))
     assert y[0] == -np.inf and np.isnan(y[1]) and np.isnan(y[2])
+
+
+def test_device_lcg_n512_bitexact():
+    """k_lcg_fill (one device thread, float64 recurrence) == the host restatement of reference mport.py:8-32,
+    bit for bit, at the size of `-g lcg -N 512` (and the reference's 5 x 4 known-answer vector)."""
+    from chsimpy_b200 import mport
+    from chsimpy_b200.solver import _CudaBackend, lcg_sample
+    be = _CudaBackend()
+    assert np.array_equal(lcg_sample(be, 512, 512, 2023), mport.matlab_lcg_sample(512, 512, 2023))
+    known0 = [0.5475444293336684, 0.29257702841077793, 0.3117376865408093, 0.9844947126621821]
+    assert np.allclose(lcg_sample(be, 5, 4, 2023)[0], known0, rtol=0, atol=1e-15)

@@ -113,3 +113,47 @@ def test_solver_needs_cuda_no_fallback():
     p.N, p.kappa_tilde = 64, 3e-4
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ch.Solver(p)
+
+
+# ---- the reference's own YAML / CSV unit tests (reference tests/test.py:40-118), ported -------------
+def test_ref_dump_parameters_scalars_roundtrip(tmp_path):
+    f = str(tmp_path / "test-dump-parameters.yaml")
+    p1 = ch.Parameters()
+    p1.func_A0 = lambda temp: 1+2*temp  # is ignored as it is non-scalar
+    p1.yaml_export_scalars(f)
+    p2 = ch.utils.yaml_import(f)
+    assert isinstance(p2, ch.Parameters) and p1.is_scalarwise_equal_with(p2)
+
+
+def test_ref_dump_parameters_roundtrip_mismatch(tmp_path):
+    f = str(tmp_path / "test-dump-parameters.yaml")
+    p1 = ch.Parameters()
+    p1.N = 512
+    p1.yaml_export_scalars(f)
+    p2 = ch.utils.yaml_import(f)
+    p1.N = 256
+    assert p1 != p2 and p2.N == 512 and p1.N == 256
+
+
+def test_ref_dump_solution_scalars_roundtrip(tmp_path):
+    f = str(tmp_path / "test-dump-solution.yaml")
+    params = ch.Parameters()
+    params.kappa_tilde = 2.989112919661156e-4          # (skips the 0.5 s sympy solve; any Parameters works)
+    s1 = ch.Solution(params)
+    s1.tau0, s1.t0, s1.computed_steps, s1.stop_reason = 1674, 2934.2, 1674, 'energy'
+    s1.yaml_export_scalars(f)
+    s2 = ch.utils.yaml_import(f)
+    assert isinstance(s2, ch.Solution) and s1.is_scalarwise_equal_with(s2)
+    assert s2.params.N == 512 and s2.tau0 == 1674 and s2.stop_reason == 'energy' and s2.A0 == s1.A0
+
+
+def test_ref_dump_csv_roundtrip_and_compress(tmp_path):
+    from chsimpy_b200 import mport
+    f = str(tmp_path / "test-dump-lcg_matrix.csv")
+    m = mport.matlab_lcg_sample(55, 34, 2023)
+    ch.utils.csv_export_matrix(m, fname=f)
+    assert np.allclose(m, ch.utils.csv_import_matrix(f))
+    fz = str(tmp_path / "test-matrix.csv.bz2")
+    r = np.random.default_rng(3).random((54, 33))
+    ch.utils.csv_export_matrix(r, fz)
+    assert np.allclose(r, ch.utils.csv_import_matrix(fz))
