@@ -81,38 +81,60 @@ def cpu_baseline(sample_steps=300):
     """Oracle port, one core, default config (BASELINE config 1 shape), bounded sample."""
     dt = _oracle_member((1.0, 1.0, 2.989112919661156e-4, 20, sample_steps))
     return {"value": round(sample_steps / dt, 2), "unit": "sim-steps/s", "cores": 1, "kind": "port",
+            "port_over_reference": port_over_reference(),
             "sample": f"oracle/ch_oracle.py (numpy+scipy.fftpack restatement of solver.py), 1 sim N={N_GRID}, "
                       f"{sample_steps} steps after 20 warm-up, single thread"}
+
+
+def port_over_reference():
+    """Speed of the oracle port relative to the unmodified reference, measured in the build container where
+    both run (tools/port_vs_reference.py -> profiles/port_over_reference.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "port_over_reference.json")))["port_over_reference"]
+    except Exception:
+        return None
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure
     Python and cannot travel to the GPU box) on all physical host cores, experiment.py-style
-    process pool, one member per core, `sample` CH steps per bench step."""
+    process pool (experiment.py:197-211), TWO members per core, `sample` CH steps per member
+    per bench step."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = physical_cores()
-    sample = 2                                   # CH steps per member per bench step
-    fac, kap = member_scalars(cores)
-    jobs = [(fac[i, 0], fac[i, 1], kap[i], args.warmup * sample, args.steps * sample) for i in range(cores)]
+    members = 2 * cores
+    sample = 1                                   # CH steps per member per bench step
+    fac, kap = member_scalars(members)
+    jobs = [(fac[i, 0], fac[i, 1], kap[i], args.warmup * sample, args.steps * sample) for i in range(members)]
     t0 = time.perf_counter()
     with mp.get_context("forkserver").Pool(cores) as pool:
-        secs = pool.map(_oracle_member, jobs)
-    wall = max(secs)
-    value = cores * args.steps * sample / wall
+        tw = time.perf_counter()
+        secs = pool.map(_oracle_member, jobs, chunksize=1)
+        wall_pool = time.perf_counter() - tw
+    # `cores` workers run concurrently, each its members back to back: the job's stepping time is the workers'
+    # busy time (the pool's wall time also holds every member's set-up and warm-up, which the GPU arm does not
+    # time either -- it is reported as pool_wall_s)
+    wall = sum(secs) / cores
+    value = members * args.steps * sample / wall
+    por = port_over_reference()
     line = {"impl": "reference", "metric": "ch_steps_per_sec_n512", "value": round(value, 2), "unit": "sim-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(wall / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_text(cores) + f" [CPU arm: one member per physical host core, "
-                                   f"{sample} CH steps per bench step]", "members_per_gpu": cores, "N": N_GRID},
+            "config": {"workload": workload_text(members) + f" [CPU arm: two members per physical host core, "
+                                   f"{sample} CH step per member per bench step]", "members_per_gpu": members, "N": N_GRID},
             "cpu_baseline": {"value": round(value, 2), "unit": "sim-steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{cores} members x {args.steps * sample} steps, mp.Pool({cores}), "
-                                       f"BLAS/FFT single-threaded per process as in the reference"},
+                             "port_over_reference": por,
+                             "sample": f"{members} members x {args.steps * sample} steps, mp.Pool({cores}), "
+                                       f"BLAS/FFT single-threaded per process as in the reference; "
+                                       f"port_over_reference = oracle port speed / unmodified reference speed on one "
+                                       f"core (profiles/port_over_reference.json, build container)",
+                             "pool_wall_s": round(wall_pool, 2)},
             "e2e": {"value": round(value, 2), "unit": "sim-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "setup_s": round(time.perf_counter() - t0 - wall, 2)}
+            "gpu_launches": 0, "setup_s": round(time.perf_counter() - t0 - wall_pool, 2)}
     print(json.dumps(line), flush=True)
 
 
@@ -276,32 +298,52 @@ def run_b200(args):
                 "k_col_gbs_own_32N2": round(32 * N_GRID ** 2 * B / (col_us * 1e-6) / 1e9, 1),
                 "k_row_gbs_own_16N2": round(16 * N_GRID ** 2 * B / (row_us * 1e-6) / 1e9, 1)}
 
-    # ---- e2e: public API from host buffers, copies inside the timed region
-    hostU = torch.from_numpy(U0).pin_memory()
+    # ---- e2e: public API from host buffers, copies inside the timed region.  The members run as G groups:
+    # while group g+1 steps, the TimeData rows and final fields of group g drain to pinned host memory on a
+    # copy stream (double buffering in time); the pinned buffers are allocated NUMA-local to the GPU.
+    del st
+    torch.cuda.empty_cache()
+    G = 4 if B % 4 == 0 and B >= 64 else 1
+    Bg = B // G
+    numa = bind_to_gpu_numa(local)
     rows_host = torch.empty((B, K, 9), dtype=torch.float64).pin_memory()
     U_host = torch.empty((B, N_GRID, N_GRID), dtype=torch.float64).pin_memory()
+    groups = [BatchStepper(N_GRID, structs[g * Bg:(g + 1) * Bg], rows_cap=K + 8) for g in range(G)]
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
     barrier()
     te0 = time.perf_counter()
-    st.U.copy_(hostU.to("cuda", non_blocking=True).expand(B, N_GRID, N_GRID))      # H2D (members share the field)
-    st._meanU = np.full(B, float(U0.mean()))
-    st.prepare()
-    st.begin()
-    st.steps(K, last=True)
-    st.poll()
-    rows_host.copy_(st.rows[:, :K, :], non_blocking=True)                            # D2H TimeData
-    st.end()
-    U_host.copy_(st.U, non_blocking=True)                                            # D2H final fields
+    for g, sg in enumerate(groups):
+        sg.set_U(U0)                                        # H2D: the members share one initial field (quirk Q11)
+        sg.prepare()
+        sg.begin()
+        sg.steps(K, last=True)
+        sg.end()                                            # materialises U = idctn(hat_U); returns when the group is done
+        copy_stream.wait_stream(main_stream)
+        with torch.cuda.stream(copy_stream):
+            rows_host[g * Bg:(g + 1) * Bg].copy_(sg.rows[:, :K, :], non_blocking=True)     # D2H TimeData
+            U_host[g * Bg:(g + 1) * Bg].copy_(sg.U, non_blocking=True)                       # D2H final fields
+    copy_stream.synchronize()
     barrier()
     te = time.perf_counter() - te0
     if world > 1:
         tt = torch.tensor([te], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-    assert np.isfinite(rows_host.numpy()).all()
+    assert np.isfinite(rows_host.numpy()).all() and abs(float(U_host[B - 1].mean()) - float(U0.mean())) < 1e-9
     e2e = {"value": round(world * B * K / te, 1), "unit": "sim-steps/s",
-           "h2d_bytes_per_step": int((hostU.numel() * 8 + B * 136) / K),
+           "h2d_bytes_per_step": int((G * U0.size * 8 + B * 136) / K),
            "d2h_bytes_per_step": int((rows_host.numel() + U_host.numel()) * 8 / K),
-           "what": "BatchStepper from pinned host U_init -> prepare -> K steps -> TimeData rows + final U on host"}
+           "what": f"BatchStepper.set_U (host U_init) -> prepare -> K steps -> TimeData rows + final U in pinned host memory; "
+                   f"{G} member groups, the D2H of a group overlaps the steps of the next (copy stream)",
+           "groups": G, "pinned_numa_node": numa}
+    del groups, rows_host, U_host
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: one large domain on the row-slab path over ALL ranks of this run (collective)
+    large = None
+    if not args.no_cpu:
+        large = large_domain_suite(ch, rank, world)
 
     if rank == 0:
         line = {"metric": "ch_steps_per_sec_n512", "value": round(value, 1), "unit": "sim-steps/s",
@@ -312,12 +354,13 @@ def run_b200(args):
                            "(inputs larger than L2, no flush needed)" if B * 6 > 252 else "L2-resident batch"},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "sims_per_s_at_1674_steps": round(value / 1673.0, 2)}
+        if large is not None:
+            line["large_domain"] = large
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
             line["single_sim"] = single_sim_probe(ch)
             line["ensemble_to_stop"] = ensemble_to_stop_probe(ch)
             line["jitter_adaptive"] = jitter_adaptive_probe(ch)
-            line["large_domain"] = large_domain_probe(ch)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -401,25 +444,104 @@ def jitter_adaptive_probe(ch):
             "wall_s": round(dt, 3), "delt_last": float(sol.delt[-1]), "note": "noise = numpy PCG64 stream reproduced bit-exactly on the device (k_pcg64_fill); diagnostics via k_diag"}
 
 
-def large_domain_probe(ch, N=8192, steps=20):
-    """BASELINE configs[4] on ONE GPU: a single N=8192 domain on the row-slab path (the multi-GPU runs
-    of the same path are tools/slab_check.py under torchrun; profiles/r1d_slab_results.md)."""
+def bind_to_gpu_numa(index):
+    """Pins this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers it
+    allocates next are node-local (8 ranks sharing one host otherwise halve each other's D2H rate)."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True).strip().lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def large_domain_suite(ch, rank, world):
+    """BASELINE configs[4] on the ranks of this run: the n8192_k4 fixture of the unmodified reference is
+    replayed on this world size first (parity), then N=8192 and N=16384 are timed on the slab path."""
     import torch
+    W = (rank, world) if world > 1 else None
+    out = {"n_gpus": world, "path": "row slabs + peer-memory transposes over NVLink (symmetric memory), one exchange launch "
+                                    "per pass, sums gathered peer-to-peer" if world > 1 else "row slabs on one GPU"}
+    z = np.load(os.path.join(ROOT, "tests", "golden", "n8192_k4.npz"))
+    m = json.loads(str(z["meta"]))
+    p = ch.Parameters()
+    p.no_gui = True
+    for k, v in m["params"].items():
+        setattr(p, k, v)
+    s = ch.Solver(p, _world=W)
+    s.prepare()
+    sol = s.solve_or_resume(p.ntmax)
+    rows, ref = sol.timedata.data(), z["rows"]
+    rel = np.abs(rows - ref) / np.maximum(np.abs(ref), 1e-300)
+    rel[ref == 0] = np.abs(rows[ref == 0])
+    st_ = p.N // 64
+    du = float(np.abs(sol.U[::st_, ::st_] - z["U_sample"]).max())
+    assert rel.max() < 1e-9 and du < 1e-11, ("large-domain parity", float(rel.max()), du)
+    out["parity_n8192_k4"] = {"rows_max_rel": float(rel.max()), "U_max_abs": du, "fixture": "tests/golden/n8192_k4.npz (unmodified reference)"}
+    del s, sol
+    torch.cuda.empty_cache()
+    for N, steps in ((8192, 30), (16384, 12)):
+        out[f"N{N}"] = large_domain_probe(ch, N, steps, rank, world)
+    return out
+
+
+def large_domain_probe(ch, N, steps, rank=0, world=1):
+    """One N x N domain, `steps` CH steps on the slab path over `world` ranks; device-timed (CUDA events, max
+    over ranks); the exchange share is measured with events around the transposes in a second run."""
+    import torch
+    import torch.distributed as dist
     p = ch.Parameters()
     p.no_gui, p.full_sim, p.N = True, True, N
     p.kappa_tilde = 2.989112919661156e-4
-    s = ch.Solver(p)
+    s = ch.Solver(p, _world=(rank, world) if world > 1 else None)
     s.prepare()
     eng = s._stepper
     eng.run(3)
-    torch.cuda.synchronize()
-    t = time.perf_counter()
-    eng.run(steps)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t
-    out = {"workload": f"configs[4] on one GPU: N={N} single domain, {steps} steps (slab path: 4 kernels per step)",
-           "ms_per_step": round(dt / steps * 1e3, 3), "steps_per_s": round(steps / dt, 1),
-           "algorithmic_gbs_32N2": round(32.0 * N * N * steps / dt / 1e9, 1), "launches": eng.launch_count()}
+
+    def timed(profile):
+        eng._prof = [] if profile else None
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.begin()
+        e0.record()
+        for i in range(steps):
+            eng._step(last=(i == steps - 1))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        x = sum(a.elapsed_time(b) for a, b in eng._prof) if profile else 0.0
+        eng._prof = None
+        if world > 1:
+            tt = torch.tensor([ms, x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms, x = float(tt[0]), float(tt[1])
+        return ms, x
+    l0 = eng.launch_count()
+    ms, _ = timed(False)
+    launches = eng.launch_count() - l0
+    ms2, xms = timed(True)
+    st = eng.get_state(0)
+    out = {"workload": f"configs[4]: N={N} single domain, {steps} steps, {world} GPU(s)",
+           "ms_per_step": round(ms / steps, 4), "steps_per_s": round(steps / (ms * 1e-3), 1),
+           "algorithmic_gbs_32N2": round(32.0 * N * N * steps / (ms * 1e-3) / 1e9, 1),
+           "exchange_share": round(xms / ms2, 3), "exchange_ms_per_step": round(xms / steps, 4),
+           "nvlink_bytes_per_step_per_gpu": int(2 * 8 * N * N // world * (world - 1) // world),
+           "launches_per_step": round(launches / steps, 1), "computed_steps": int(st.computed_steps)}
     del s, eng
     torch.cuda.empty_cache()
     return out

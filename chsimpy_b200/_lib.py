@@ -63,6 +63,9 @@ PROTOTYPES = {
     "chs_slab_destroy": (None, [C.c_void_p]),
     "chs_slab_row": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double]),
     "chs_slab_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "chs_slab_transpose_peers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "chs_slab_sums_peers": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "chs_slab_control_gathered": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "chs_slab_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "chs_slab_yedge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "chs_slab_clear_yedge": (C.c_int, [C.c_void_p]),

@@ -932,6 +932,20 @@ extern "C" int chs_slab_transpose(chs_slab* s, const double* in, double* out, in
     return 0;
 }
 
+// One launch for the blocks of all P ranks: dst[p] = peer-mapped destination base for rank p (already offset
+// to this rank's column range); the block for rank p is in[:, p*C .. p*C + C).
+extern "C" int chs_slab_transpose_peers(chs_slab* s, const double* in, const uint64_t* dst, int32_t R, int32_t C,
+                                        int32_t in_ld, int32_t out_ld) {
+    if (!s || !in || !dst || s->world < 1 || s->world > 8) return fail("chs_slab_transpose_peers: bad argument (at most 8 ranks)");
+    PeerPtrs pp;
+    for (int i = 0; i < 8; ++i) pp.p[i] = (i < s->world) ? (double*)(uintptr_t)dst[i] : nullptr;
+    CHS_LAUNCH_PDL(k_slab_transpose_peers, dim3((C + 31) / 32, (R + 31) / 32, s->world), dim3(256), 32 * 33 * sizeof(double),
+                   s->stream, pp, in, (int)R, (int)C, (int)in_ld, (int)out_ld, s->rank, s->world);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // The whole y pass of a step on `rows` local x-slot rows (global slot index slot_base + r), B holding
 // the transposed x-transformed mu (physical y along the row) on entry:
 //   H = (H + Seig*rowDCT(B))/CHeig ;  B = rowIDCT(H)      (one kernel, one read of B and H, one write of each)
@@ -969,17 +983,27 @@ extern "C" int chs_slab_reduce(chs_slab* s, int32_t rows, int32_t with_update) {
 
 // the sums of one step in a single launch: per-tile partials + spectral gradient energy + the y-edge
 // terms of the stored field (top_edge: this rank holds rows 0/1 of the domain, bottom_edge: rows N-2/N-1)
-extern "C" int chs_slab_sums(chs_slab* s, int32_t top_edge, int32_t bottom_edge) {
-    if (!s) return fail("chs_slab_sums: null handle");
+static int slab_sums(chs_slab* s, int32_t top_edge, int32_t bottom_edge, const uint64_t* peer_slots) {
     const size_t n = (size_t)s->N;
     const double* t0 = top_edge ? s->U : nullptr;
     const double* b0 = bottom_edge ? s->U + (size_t)(s->rows - 2) * n : nullptr;
+    PeerPtrs pp;
+    for (int i = 0; i < 8; ++i) pp.p[i] = (peer_slots && i < s->world) ? (double*)(uintptr_t)peer_slots[i] : nullptr;
     CHS_LAUNCH_PDL(k_slab_sums, dim3(1), dim3(128 * (R_NVAL + 1)), 128 * (R_NVAL + 1) * sizeof(double), s->stream,
                (const double*)s->part, (int)(s->rows / slab_lines(s->N)), (const double*)s->part_ge, s->upd_used,
-               t0, t0 ? t0 + n : nullptr, b0, b0 ? b0 + n : nullptr, s->N, s->vec);
+               t0, t0 ? t0 + n : nullptr, b0, b0 ? b0 + n : nullptr, s->N, s->vec, pp, peer_slots ? s->world : 0);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());
     return 0;
+}
+extern "C" int chs_slab_sums(chs_slab* s, int32_t top_edge, int32_t bottom_edge) {
+    if (!s) return fail("chs_slab_sums: null handle");
+    return slab_sums(s, top_edge, bottom_edge, nullptr);
+}
+// the same, and the 7 sums are also stored into peer_slots[r] (8 doubles in rank r's gather buffer, peer-mapped)
+extern "C" int chs_slab_sums_peers(chs_slab* s, int32_t top_edge, int32_t bottom_edge, const uint64_t* peer_slots) {
+    if (!s || !peer_slots || s->world > 8) return fail("chs_slab_sums_peers: bad argument");
+    return slab_sums(s, top_edge, bottom_edge, peer_slots);
 }
 
 extern "C" int chs_slab_prepare(chs_slab* s, const double* U_halo, double mean_u) {
@@ -998,13 +1022,21 @@ extern "C" int chs_slab_prepare(chs_slab* s, const double* U_halo, double mean_u
 }
 
 // post: 0 prologue (only ||mu||^2 + pre part), 1 end of an iteration, 2 prepare (row 0)
-extern "C" int chs_slab_control(chs_slab* s, int32_t last, int32_t post) {
-    if (!s) return fail("chs_slab_control: null handle");
-    CHS_LAUNCH_PDL(k_slab_control, dim3(1), dim3(32), 0, s->stream, s->sim, (const double*)s->vec, s->rowsbuf, s->rows_cap, s->N,
-               (int)last, (int)post);
+static int slab_control(chs_slab* s, int32_t last, int32_t post, const double* allvec) {
+    CHS_LAUNCH_PDL(k_slab_control, dim3(1), dim3(32), 0, s->stream, s->sim, s->vec, s->rowsbuf, s->rows_cap, s->N,
+               (int)last, (int)post, allvec, s->world);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());
     return 0;
+}
+extern "C" int chs_slab_control(chs_slab* s, int32_t last, int32_t post) {
+    if (!s) return fail("chs_slab_control: null handle");
+    return slab_control(s, last, post, nullptr);
+}
+// the rank sums come from the gather buffer allvec[world][8] (filled by every rank's chs_slab_sums_peers)
+extern "C" int chs_slab_control_gathered(chs_slab* s, int32_t last, int32_t post, const double* allvec) {
+    if (!s || !allvec) return fail("chs_slab_control_gathered: bad argument");
+    return slab_control(s, last, post, allvec);
 }
 
 extern "C" int chs_slab_begin(chs_slab* s) {

@@ -225,6 +225,27 @@ CHS_KERNEL void k_slab_transpose(const double* in, double* out, int R, int C, in
         if (bx + k < C && by + tx < R) out[(size_t)(bx + k) * out_ld + by + tx] = tile[tx * 33 + k];
 }
 
+// The exchange of one pass as ONE launch over all peers: blockIdx.z = i handles the block for rank
+// p = (rank + i) % P (local block first, link load spread): out_p[c][r] = in[r][p*C + c], written straight
+// into rank p's buffer over NVLink (dst.p[p] = peer-mapped destination, offset to this rank's columns).
+struct PeerPtrs { double* p[8]; };
+CHS_KERNEL void k_slab_transpose_peers(PeerPtrs dst, const double* in, int R, int C, int in_ld, int out_ld, int rank, int P) {
+    CHS_PDL_TRIGGER();
+    CHS_PDL_WAIT();
+    CHS_SMEM_DECL
+    double* tile = reinterpret_cast<double*>(CHS_SMEM_PTR);       // 32*33 doubles
+    const int peer = (rank + (int)blockIdx.z) % P;
+    const double* src = in + (size_t)peer * C;
+    double* out = dst.p[peer];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;       // 256 threads: 32 x 8
+    for (int k = ty; k < 32; k += 8)
+        if (by + k < R && bx + tx < C) tile[k * 33 + tx] = src[(size_t)(by + k) * in_ld + bx + tx];
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8)
+        if (bx + k < C && by + tx < R) out[(size_t)(bx + k) * out_ld + by + tx] = tile[tx * 33 + k];
+}
+
 // y-edge terms of the gradient energy from two stored rows of U: 3/4 * sum_x (U[r1][x]-U[r0][x])^2
 CHS_KERNEL void k_slab_yedge(const double* r0, const double* r1, int N, double* out, int accumulate) {
     CHS_SMEM_DECL
@@ -321,7 +342,8 @@ CHS_KERNEL void k_slab_reduce(const double* part, int ntiles, const double* part
 // lanes sum the per-tile partials (lane-strided, fixed order), the last 128 threads the y-edge
 // terms of the stored field (top: rows 0/1 of the domain, bottom: rows N-2/N-1; null = not mine).
 CHS_KERNEL void k_slab_sums(const double* part, int ntiles, const double* part_ge, int nge, const double* top0,
-                            const double* top1, const double* bot0, const double* bot1, int N, double* vec) {
+                            const double* top1, const double* bot0, const double* bot1, int N, double* vec,
+                            PeerPtrs peers, int P) {
     CHS_PDL_TRIGGER();
     CHS_PDL_WAIT();
     CHS_SMEM_DECL
@@ -346,16 +368,27 @@ CHS_KERNEL void k_slab_sums(const double* part, int ntiles, const double* part_g
             t += 0.75 * e;
         }
         vec[v] = t;
+        // P > 0: this rank's sums also go to slot [rank] of every rank's gather buffer (peer-mapped stores);
+        // k_slab_control adds the P slots in rank order after the exchange barrier -- no all-reduce launch
+        for (int r = 0; r < P; ++r) peers.p[r][v] = t;
     }
 }
 
 // step_control() of the tile path, fed with the rank-reduced sums (one thread; every rank runs
 // it on identical inputs and so keeps an identical Sim image).  post = 0: prologue.
-CHS_KERNEL void k_slab_control(Sim* S, const double* vec, double* rows, long long rows_cap, int N, int last, int post) {
+CHS_KERNEL void k_slab_control(Sim* S, double* vec, double* rows, long long rows_cap, int N, int last, int post,
+                               const double* allvec, int P) {
     CHS_PDL_TRIGGER();
     CHS_PDL_WAIT();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (S->halted && post != 2) return;          // stopped: no further rows, no time accounting
+    if (allvec) {                                // sums of all ranks, gathered by k_slab_sums: fixed order -> identical on every rank
+        for (int v = 0; v < R_NVAL; ++v) {
+            double t = 0;
+            for (int r = 0; r < P; ++r) t += allvec[r * 8 + v];
+            vec[v] = t;
+        }
+    }
     const chs_params& p = S->p;
     if (post == 2) {                     // Solver.prepare(): row 0 (solver.py:117-135)
         const double N2 = (double)N * (double)N, L2sq = p.L * p.L;

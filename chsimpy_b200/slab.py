@@ -30,7 +30,7 @@ from . import _lib, utils
 class SlabEngine:
     S_FWD, S_MU, S_INV, S_STEP, S_YFWD = 0, 1, 2, 3, 4
 
-    def __init__(self, N, param_struct, rows_cap=1024, backend=None, device=None, world=None):
+    def __init__(self, N, param_struct, rows_cap=1024, backend=None, device=None, world=None, _selfpeer=False):
         from .solver import _CudaBackend
         self.be = backend if backend is not None else _CudaBackend(device)
         lib = self.lib = self.be.lib
@@ -54,6 +54,15 @@ class SlabEngine:
         self._main = self._side = None
         if self.P > 1 and self.be.name == "cuda" and os.environ.get("CHS_SLAB_P2P", "1") != "0":
             self._setup_peer_buffers()
+        elif self.P == 1 and _selfpeer:
+            # test hook: the peer-memory route with this rank as its own (only) peer -- exercises the one-launch
+            # exchange, the gathered sums and the gathered control kernel without a second GPU
+            RN = R * n
+            flat = self.be.empty((2 * RN + 16,))
+            self._ab, self._hdl = flat, type("NoBarrier", (), {"barrier": staticmethod(lambda: None)})()
+            self.A, self.B = flat[:RN].reshape(R, n), flat[RN:2 * RN].reshape(R, n)
+            self._gather = flat[2 * RN:].reshape(2, 1, 8)
+            self._peer, self._ab_base, self._parity = [self.be.ptr(flat)], self.be.ptr(flat), 0
         if self._peer is None:
             self.A = self.be.empty((R, n))
             self.B = self.be.empty((R, n))
@@ -75,6 +84,7 @@ class SlabEngine:
         self._vec = self._tensor(self.work[off:off + 56]).view(self._torch().float64)
         self._full = None
         self._mean = 0.0
+        self._prof = None                                # bench.py: list of (start, end) CUDA events around the exchanges
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -89,16 +99,21 @@ class SlabEngine:
             import torch
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
-            ab = symm.empty((2, self.R, self.N), dtype=torch.float64, device=self.U.device)
-            hdl = symm.rendezvous(ab, dist.group.WORLD)
+            # one symmetric allocation: A | B | gather buffer of the diagnostic sums [2 (step parity)][P][8]
+            RN = self.R * self.N
+            flat = symm.empty((2 * RN + 16 * self.P,), dtype=torch.float64, device=self.U.device)
+            hdl = symm.rendezvous(flat, dist.group.WORLD)
             peers = [int(x) for x in hdl.buffer_ptrs]
             if len(peers) != self.P or int(hdl.rank) != self.rank:
                 raise RuntimeError("unexpected symmetric-memory group")
             off = int(getattr(hdl, "offset", 0) or 0)
-            self._ab, self._hdl = ab, hdl
-            self.A, self.B = ab[0], ab[1]
+            self._ab, self._hdl = flat, hdl
+            self.A, self.B = flat[:RN].view(self.R, self.N), flat[RN:2 * RN].view(self.R, self.N)
+            self._gather = flat[2 * RN:].view(2, self.P, 8)
+            self._gather.zero_()
             self._peer = [x + off for x in peers]
-            self._ab_base = self.be.ptr(ab)
+            self._ab_base = self.be.ptr(flat)
+            self._parity = 0
             hdl.barrier()
             n = int(os.environ.get("CHS_SLAB_CHUNKS", "1"))   # measured on 2 GPUs, N=8192: 1.59 / 1.67 / 1.66 ms for 1 / 2 / 4
             gran = self.lib.chs_slab_row_granularity(self.N)
@@ -137,24 +152,32 @@ class SlabEngine:
             dist.all_reduce(self._vec)                  # 7 doubles, NCCL; identical on every rank
 
     def _transpose(self, src, dst, r0=0, rc=None, sync=True):
+        if self._prof is None:
+            return self._transpose_impl(src, dst, r0, rc, sync)
+        torch = self._torch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._transpose_impl(src, dst, r0, rc, sync)
+        e1.record()
+        self._prof.append((e0, e1))
+
+    def _transpose_impl(self, src, dst, r0=0, rc=None, sync=True):
         """dst[c_local][r_global] = src[r_local][c_global] for the local rows r0 .. r0+rc (works in
         both directions).  P > 1: the block for rank p is written into p's buffer; with `sync` a
         cross-rank barrier follows (all writes have landed, all reads of the old dst are over)."""
         lib, h, be, R, N, P = self.lib, self._h, self.be, self.R, self.N, self.P
         rc = R if rc is None else rc
         esz = 8
-        if P == 1:
+        if P == 1 and self._peer is None:
             self._ck(lib.chs_slab_transpose(h, be.ptr(src) + r0 * N * esz, be.ptr(dst) + r0 * esz, rc, N, N, N),
                      "chs_slab_transpose")
             return
         if self._peer is not None:
-            # out_p[c_local][rank*R + r_local] = src[r_local][p*R + c_local], over NVLink into rank p's dst
+            # out_p[c_local][rank*R + r_local] = src[r_local][p*R + c_local], over NVLink into rank p's dst:
+            # ONE launch, blockIdx.z = peer (the local block first, the link load spread)
             doff = be.ptr(dst) - self._ab_base
-            for i in range(P):
-                p = (self.rank + i) % P                  # start with the local block, spread the link load
-                self._ck(lib.chs_slab_transpose(h, be.ptr(src) + (r0 * N + p * R) * esz,
-                                                self._peer[p] + doff + (self.rank * R + r0) * esz, rc, R, N, N),
-                         "chs_slab_transpose")
+            dsts = (C.c_uint64 * P)(*[self._peer[p] + doff + (self.rank * R + r0) * esz for p in range(P)])
+            self._ck(lib.chs_slab_transpose_peers(h, be.ptr(src) + r0 * N * esz, dsts, rc, R, N, N), "chs_slab_transpose_peers")
             if sync:
                 self._hdl.barrier()
             return
@@ -249,6 +272,21 @@ class SlabEngine:
                                       self.row_base + r0, 1, float(self._mean)), "chs_slab_row")
 
         self._pass(y_pass, self.B, self.A)
+        if self._peer is not None and self._nchunks == 1:
+            # peer-memory route: x pass, its exchange and the 7 sums (stored into every rank's gather buffer by
+            # the sums kernel) share ONE device-side barrier; the control kernel adds the ranks' sums in rank
+            # order -- 8 launches per step, no collective
+            x_pass(0, R)
+            self._transpose(self.A, self.B, sync=False)
+            par = self._parity
+            self._parity ^= 1
+            goff = be.ptr(self._gather) - self._ab_base + (par * self.P + self.rank) * 64
+            slots = (C.c_uint64 * self.P)(*[self._peer[p] + goff for p in range(self.P)])
+            self._ck(lib.chs_slab_sums_peers(h, int(self.rank == 0), int(self.rank == self.P - 1), slots), "chs_slab_sums_peers")
+            self._hdl.barrier()
+            self._ck(lib.chs_slab_control_gathered(h, int(bool(last)), 1, be.ptr(self._gather) + par * self.P * 64),
+                     "chs_slab_control_gathered")
+            return
         self._pass(x_pass, self.A, self.B)               # B for the next step (its barrier also covers the sums)
         # per-tile partials + y-edge terms of the stored field -> the 7 local sums, one launch
         self._ck(lib.chs_slab_sums(h, int(self.rank == 0), int(self.rank == self.P - 1)), "chs_slab_sums")

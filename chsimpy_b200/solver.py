@@ -39,6 +39,11 @@ class _CudaBackend:
     def upload(self, t, arr):
         t.copy_(self.torch.from_numpy(np.require(arr, dtype=np.float64, requirements=['C', 'W'])))
 
+    def upload_broadcast(self, t, arr2d):
+        """t[b] = arr2d for every b: ONE host->device copy of the shared field, replicated on the device."""
+        one = self.torch.from_numpy(np.require(arr2d, dtype=np.float64, requirements=['C', 'W'])).to(self.device, non_blocking=True)
+        t.copy_(one.expand_as(t))
+
     def to_device(self, arr):
         return self.torch.from_numpy(np.require(arr, requirements=['C', 'W'])).to(self.device)
 
@@ -107,8 +112,14 @@ class BatchStepper:
     # -- fields ---------------------------------------------------------------------------
     def set_U(self, U):
         U = np.asarray(U, dtype=np.float64)
-        if U.ndim == 2:
-            U = np.broadcast_to(U, (self.batch,) + U.shape)
+        if U.ndim == 2:                                   # one field shared by all members (the ensemble, quirk Q11)
+            assert U.shape == (self.N, self.N)
+            if hasattr(self.be, "upload_broadcast"):
+                self.be.upload_broadcast(self.U, U)
+            else:
+                self.be.upload(self.U, np.broadcast_to(U, (self.batch,) + U.shape))
+            self._meanU = np.full(self.batch, U.mean())
+            return
         assert U.shape == (self.batch, self.N, self.N)
         self.be.upload(self.U, U)
         self._meanU = np.ascontiguousarray(U.reshape(self.batch, -1).mean(axis=1)) if U.strides[0] else \
@@ -241,7 +252,7 @@ class Solver:
     """Cahn-Hilliard integrator (DCT, Flory-Huggins energy) -- API of reference
     chsimpy/solver.py:45-252."""
 
-    def __init__(self, params=None, U_init=None, _backend=None, _world=None, _force_slab=False):
+    def __init__(self, params=None, U_init=None, _backend=None, _world=None, _force_slab=False, _selfpeer=False):
         self.params = params
         self.solution = Solution(self.params)
         N = params.N
@@ -284,7 +295,7 @@ class Solver:
             self._stepper = BatchStepper(N, [ps], backend=be)
         else:
             from .slab import SlabEngine
-            self._stepper = SlabEngine(N, ps, backend=be, world=_world)
+            self._stepper = SlabEngine(N, ps, backend=be, world=_world, _selfpeer=_selfpeer)
 
     def _draw_sobol(self, n):
         self._sobol_drawn += n

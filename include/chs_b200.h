@@ -175,6 +175,10 @@ void chs_slab_destroy(chs_slab*);
 int chs_slab_row(chs_slab*, int32_t mode, const double* src, double* dst, int32_t rows, int32_t row_base,
                  int32_t diag, double mean_u);
 int chs_slab_transpose(chs_slab*, const double* in, double* out, int32_t R, int32_t C, int32_t in_ld, int32_t out_ld);
+/* the exchange of one pass in ONE launch (world <= 8): block p of `in` (columns p*C .. p*C+C) is transposed
+ * straight into dst[p], the peer-mapped destination in rank p's buffer */
+int chs_slab_transpose_peers(chs_slab*, const double* in, const uint64_t* dst /*[world] device addresses*/, int32_t R, int32_t C,
+                             int32_t in_ld, int32_t out_ld);
 /* the y pass of one step in one kernel: H = (H + Seig*rowDCT(B))/CHeig; B = rowIDCT(H)  (solver.py:201-208) */
 int chs_slab_update(chs_slab*, double* H, double* B, int32_t rows, int32_t slot_base);
 int chs_slab_yedge(chs_slab*, const double* row_a, const double* row_b, int32_t accumulate);
@@ -183,9 +187,13 @@ int chs_slab_reduce(chs_slab*, int32_t rows, int32_t with_update);    /* local s
 /* reduce + both yedge calls of one step in a single launch (top_edge / bottom_edge: this rank holds rows
  * 0,1 / N-2,N-1 of the domain) */
 int chs_slab_sums(chs_slab*, int32_t top_edge, int32_t bottom_edge);
+/* ... and stores the 7 sums into peer_slots[r] (8 doubles of rank r's gather buffer) for every rank r: the
+ * cross-rank reduction then needs no collective, chs_slab_control_gathered adds the slots in rank order */
+int chs_slab_sums_peers(chs_slab*, int32_t top_edge, int32_t bottom_edge, const uint64_t* peer_slots /*[world]*/);
 double* chs_slab_vec(chs_slab*);                                      /* device pointer, 7 doubles */
 int chs_slab_prepare(chs_slab*, const double* U_with_halo /*[rows+2][N]*/, double mean_u);   /* solver.py:84-127 */
 int chs_slab_control(chs_slab*, int32_t last, int32_t post);          /* solver.py:195-199, 230-249 */
+int chs_slab_control_gathered(chs_slab*, int32_t last, int32_t post, const double* allvec /*[world][8]*/);
 int chs_slab_begin(chs_slab*);
 int chs_slab_rewind_rows(chs_slab*);
 int chs_slab_get_state(chs_slab*, chs_state*, int64_t* rows_written, int32_t* halted);

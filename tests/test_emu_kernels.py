@@ -117,6 +117,25 @@ def test_slab_path_emulated(be):
     assert abs(sol.U.mean() - s.U_init.mean()) < 1e-14
 
 
+def test_slab_peer_route_single_rank(be):
+    """The peer-memory route of the slab path (one exchange launch over all peers, sums stored into the ranks'
+    gather buffers, gathered control kernel) with the rank as its own peer, against the reference fixture."""
+    z = np.load(os.path.join(GOLD, "n64_k200.npz"))
+    m = json.loads(str(z["meta"]))
+    p = ch.Parameters()
+    p.no_gui = True
+    for k, v in m["params"].items():
+        setattr(p, k, v)
+    s = ch.Solver(p, _backend=be, _force_slab=True, _selfpeer=True)
+    assert s._stepper._peer is not None
+    s.prepare()
+    sol = s.solve_or_resume(9)
+    rows, ref = sol.timedata.data(), z["rows"][:9]
+    rel = np.abs(rows - ref) / np.maximum(np.abs(ref), 1e-300)
+    rel[ref == 0] = np.abs(rows[ref == 0])
+    assert sol.computed_steps == 9 and rel.max() < 1e-11, rel.max(axis=0)
+
+
 def test_slab_path_honours_stop_flag(be):
     """A time limit hit at step ~10 while the host has 40 steps queued (full_sim, so no poll inside the
     chunk): the slab kernels must freeze the state behind the device-side flag exactly like the batched
