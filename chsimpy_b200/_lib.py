@@ -66,6 +66,12 @@ PROTOTYPES = {
     "chs_slab_transpose_peers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "chs_slab_sums_peers": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "chs_slab_control_gathered": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "chs_slab_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chs_slab_control_dyn": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "chs_slab_step_x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
+    "chs_slab_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chs_slab_pcg64_fill": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64]),
+    "chs_slab_row_means": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "chs_slab_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "chs_slab_yedge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "chs_slab_clear_yedge": (C.c_int, [C.c_void_p]),

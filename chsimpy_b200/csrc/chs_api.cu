@@ -878,7 +878,7 @@ extern "C" int chs_slab_set_stream(chs_slab* s, void* stream) {
 
 template <int N>
 static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int rows, int row_base, int diag, double mean_u,
-                    double* H = nullptr) {
+                    double* H = nullptr, const double* noise = nullptr, const double* noise_mean = nullptr) {
     using G = Geo<N>;
     SlabArgs a;
     // a launch may cover a sub-range of the rank's rows (pipelined exchange): row_base is global
@@ -887,6 +887,7 @@ static int slab_row(chs_slab* s, int mode, const double* src, double* dst, int r
     a.src = src; a.dst = dst; a.Uout = s->U + (size_t)local0 * N; a.rows = rows; a.row_base = row_base; a.diag = diag; a.mean_u = mean_u;
     a.tile0 = local0 / G::LINES; a.tiles_total = s->rows / G::LINES;
     a.part = s->part; a.S = s->sim; a.tw = s->tw; a.om = s->om; a.logtab = s->logtab;
+    a.noise = noise ? noise + (size_t)local0 * N : nullptr; a.noise_mean = noise_mean;
     a.H = H; a.part_ge = s->part_ge; a.lam = s->lam; a.gsin = s->gsin; a.kof = s->kof; a.lamg = s->lamg;
     const int ntiles = rows / G::LINES;
 #ifdef CHS_EMU
@@ -920,6 +921,87 @@ extern "C" int chs_slab_row(chs_slab* s, int32_t mode, const double* src, double
 #define CALL(NN) if (slab_row<NN>(s, mode, src, dst, rows, row_base, diag, mean_u, mode == S_YFWD ? dst : nullptr)) return -1;
     CHS_FOR_SLAB_N(s->N, CALL)
 #undef CALL
+    return 0;
+}
+
+// The x pass of a step (mode S_STEP) with the per-step jitter of solver.py:210-211: `noise` = this step's uniform
+// draws for the rank's rows ([rows of the rank][N], device), `noise_mean` = device scalar, mean of the whole
+// N x N draw (both NULL without jitter).
+extern "C" int chs_slab_step_x(chs_slab* s, const double* src, double* dst, int32_t rows, int32_t row_base, double mean_u,
+                               const double* noise, const double* noise_mean) {
+    if (!s || !src || !dst || rows < 1 || rows % slab_lines(s->N)) return fail("chs_slab_step_x: bad argument");
+    if ((noise == nullptr) != (noise_mean == nullptr)) return fail("chs_slab_step_x: noise and noise_mean go together");
+#define CALL(NN) if (slab_row<NN>(s, S_STEP, src, dst, rows, row_base, 1, mean_u, nullptr, noise, noise_mean)) return -1;
+    CHS_FOR_SLAB_N(s->N, CALL)
+#undef CALL
+    return 0;
+}
+
+// adaptive dt: colsum[x] = sum over this rank's rows of delt_max/sqrt(1 + 62.5 mu(U[y][x])^2) (solver.py:182-183);
+// scratch: at least 16*N doubles.  The caller adds the ranks' vectors (all-reduce) and hands the result to
+// chs_slab_control*_dyn.
+extern "C" int chs_slab_colsum(chs_slab* s, double* colsum, double* scratch) {
+    if (!s || !colsum || !scratch) return fail("chs_slab_colsum: bad argument");
+    const int nch = s->rows >= 16 ? 16 : 1;
+#ifdef CHS_EMU
+    const int nt = 32;
+#else
+    const int nt = 128;
+#endif
+    CHS_LAUNCH(k_slab_colsum, dim3((s->N + nt - 1) / nt, nch), dim3(nt), 0, s->stream, (const double*)s->U, s->rows, s->N,
+               (const Sim*)s->sim, (const double2*)s->logtab, scratch);
+    CHS_LAUNCH(k_slab_colsum_final, dim3((s->N + nt - 1) / nt), dim3(nt), 0, s->stream, (const double*)scratch, nch, s->N, colsum);
+    s->launches += 2;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// jitter: stencil gradient energy of the stored field; top / bot = boundary rows of the neighbouring ranks
+// (device, N doubles each; ignored at the domain edges but must be valid pointers).  The partial sums replace the
+// spectral ones of the y pass in the following chs_slab_sums* call.
+extern "C" int chs_slab_grad(chs_slab* s, const double* top, const double* bot) {
+    if (!s || !top || !bot) return fail("chs_slab_grad: bad argument");
+#ifdef CHS_EMU
+    const int nb = 2, nt = 64;
+#else
+    const int nb = SLAB_UPD_BLOCKS, nt = 256;
+#endif
+    CHS_LAUNCH(k_slab_grad, dim3(nb), dim3(nt), nt * sizeof(double), s->stream, (const double*)s->U, top, bot, s->rows, s->row_base,
+               s->N, s->part_ge);
+    s->upd_used = nb;
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// numpy PCG64 draws into `out` on the slab handle's stream (see chs_pcg64_fill), and row means
+extern "C" int chs_slab_pcg64_fill(chs_slab* s, uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
+                                   uint64_t offset, double* out, int64_t count) {
+    if (!s || !out || count < 0) return fail("chs_slab_pcg64_fill: bad argument");
+    if (count == 0) return 0;
+    const long long threads = (count + PCG_RUN - 1) / PCG_RUN;
+#ifdef CHS_EMU
+    const int nt = 32;
+#else
+    const int nt = 128;
+#endif
+    CHS_LAUNCH(k_pcg64_fill, dim3((unsigned)((threads + nt - 1) / nt)), dim3(nt), 0, s->stream, out, (long long)count,
+               (unsigned long long)state_hi, (unsigned long long)state_lo, (unsigned long long)inc_hi,
+               (unsigned long long)inc_lo, (unsigned long long)offset);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int chs_slab_row_means(chs_slab* s, const double* in, int64_t rows, int64_t cols, double* out) {
+    if (!s || !in || !out || rows < 1 || cols < 1) return fail("chs_slab_row_means: bad argument");
+#ifdef CHS_EMU
+    const int nt = 32;
+#else
+    const int nt = 256;
+#endif
+    CHS_LAUNCH(k_row_means, dim3((unsigned)rows), dim3(nt), nt * sizeof(double), s->stream, in, (long long)cols, out);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -1022,21 +1104,27 @@ extern "C" int chs_slab_prepare(chs_slab* s, const double* U_halo, double mean_u
 }
 
 // post: 0 prologue (only ||mu||^2 + pre part), 1 end of an iteration, 2 prepare (row 0)
-static int slab_control(chs_slab* s, int32_t last, int32_t post, const double* allvec) {
+static int slab_control(chs_slab* s, int32_t last, int32_t post, const double* allvec, const double* colsum) {
     CHS_LAUNCH_PDL(k_slab_control, dim3(1), dim3(32), 0, s->stream, s->sim, s->vec, s->rowsbuf, s->rows_cap, s->N,
-               (int)last, (int)post, allvec, s->world);
+               (int)last, (int)post, allvec, s->world, colsum);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());
     return 0;
 }
 extern "C" int chs_slab_control(chs_slab* s, int32_t last, int32_t post) {
     if (!s) return fail("chs_slab_control: null handle");
-    return slab_control(s, last, post, nullptr);
+    return slab_control(s, last, post, nullptr, nullptr);
 }
 // the rank sums come from the gather buffer allvec[world][8] (filled by every rank's chs_slab_sums_peers)
 extern "C" int chs_slab_control_gathered(chs_slab* s, int32_t last, int32_t post, const double* allvec) {
     if (!s || !allvec) return fail("chs_slab_control_gathered: bad argument");
-    return slab_control(s, last, post, allvec);
+    return slab_control(s, last, post, allvec, nullptr);
+}
+// adaptive dt: colsum = the all-rank column sums of chs_slab_colsum (N doubles, device) when this control step
+// is followed by an iteration that updates delt (solver.py:177-181), else NULL; allvec may be NULL
+extern "C" int chs_slab_control_dyn(chs_slab* s, int32_t last, int32_t post, const double* allvec, const double* colsum) {
+    if (!s) return fail("chs_slab_control_dyn: null handle");
+    return slab_control(s, last, post, allvec, colsum);
 }
 
 extern "C" int chs_slab_begin(chs_slab* s) {

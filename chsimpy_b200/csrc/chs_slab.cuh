@@ -39,6 +39,8 @@ struct SlabArgs {
     const double2* lamg;        // packed per-item lambda / g table (KArgs::lamg)
     const int* kof;
     Sim* S;
+    const double* noise;        // S_STEP with jitter: uniform draws of this step for the launch's rows [rows][N], else null
+    const double* noise_mean;   // ... and the mean of the WHOLE N x N draw (device scalar)
     const double2* tw;          // natural table (point-major geometry), or the per-stage tables (line-major)
     const double2* om;
     const double2* logtab;
@@ -128,6 +130,38 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
         if (MODE == S_INV) {
             row_tile_store_phys<N>(sm, a.dst + goff, tid);
         } else {
+            const bool jit = (MODE == S_STEP) && (a.noise != nullptr);
+            if (jit) {
+                // jitter (solver.py:210-211): U += jitter*(2*noise - 1) on the field in shared memory; the jittered
+                // field is what gets stored, diagnosed and fed to mu (hat_U' is NOT touched, quirk Q2)
+                const double jv = a.S->p.jitter;
+                const double* nz = a.noise + goff;
+                constexpr int CNT = LINES * N / NT;
+#pragma unroll 4
+                for (int j = 0; j < CNT; ++j) {
+                    const int i = tid + j * NT;
+                    double* q = sm + real_off<N>(mk_pos<N>(i % N)) + 2 * G::LOFF * (i / N);
+                    *q += jv * (2.0 * nz[i] - 1.0);
+                }
+                __syncthreads();
+                if (ra_tile) {                                          // mean of the jittered Ra row
+                    if (ra_line) {
+                        double sj = 0;
+                        for (int i = 0; i < 16; ++i) {
+                            const double2 v = scl[G::idx(t + i * TPL)];
+                            sj += v.x + v.y;
+                        }
+                        ra_scr[2 + t] = sj;
+                    }
+                    __syncthreads();
+                    if (ra_line && t == 0) {
+                        double sj = 0;
+                        for (int jj = 0; jj < TPL; ++jj) sj += ra_scr[2 + jj];
+                        ra_scr[0] = sj / (double)N;
+                    }
+                    __syncthreads();
+                }
+            }
             if (MODE == S_STEP) {
                 row_tile_store_phys<N>(sm, a.Uout + goff, tid);  // reads only; no barrier needed before the in-place physics
                 __syncthreads();
@@ -136,7 +170,9 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                 const chs_params p = a.S->p;
                 PhysK pk;
                 pk.th.RT = p.RT; pk.th.mBRT = -p.BRT; pk.th.A0 = p.A0; pk.th.A1 = p.A1; pk.th.m2A1 = -2.0 * p.A1; pk.th.B = p.B;
-                pk.threshold = p.threshold; pk.meanU = a.mean_u;
+                pk.threshold = p.threshold;
+                // conserved mean (Q4); the jitter shifts it by jitter*(2*mean(noise) - 1)
+                pk.meanU = a.mean_u + (jit ? p.jitter * (2.0 * a.noise_mean[0] - 1.0) : 0.0);
                 const double ra_mean = ra_line ? ra_scr[0] : 0.0;
                 RowAcc acc = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
@@ -183,7 +219,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB) k_slab_row(SlabArgs 
                         }
                     }
                     pp[R_GE * nt_all] = 0;
-                    pp[R_EDGE * nt_all] = 0.75 * e;
+                    pp[R_EDGE * nt_all] = jit ? 0.0 : 0.75 * e;        // with jitter the gradient energy is the stencil sum of k_slab_grad
                     pp[R_F * nt_all] = s4[0];
                     pp[R_ABS * nt_all] = s4[1];
                     pp[R_MU2 * nt_all] = s4[2];
@@ -258,6 +294,62 @@ CHS_KERNEL void k_slab_yedge(const double* r0, const double* r1, int N, double* 
         double t = 0;
         for (unsigned j = 0; j < blockDim.x; ++j) t += red[j];
         out[0] = (accumulate ? out[0] : 0.0) + 0.75 * t;
+    }
+}
+
+// adaptive dt (solver.py:182-183): per-column sums of delt_max/sqrt(1 + 62.5 mu(U)^2) over this rank's rows,
+// in two fixed-order levels (gridDim.y row chunks -> part[chunk][N], then k_slab_colsum_final): deterministic
+CHS_KERNEL void k_slab_colsum(const double* U, int rows, int N, const Sim* S, const double2* logtab, double* part) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= N) return;
+    const chs_params p = S->p;
+    ThermoK k;
+    k.RT = p.RT; k.mBRT = -p.BRT; k.A0 = p.A0; k.A1 = p.A1; k.m2A1 = -2.0 * p.A1; k.B = p.B;
+    const int per = (rows + gridDim.y - 1) / gridDim.y;
+    const int y0 = blockIdx.y * per, y1 = (y0 + per < rows) ? y0 + per : rows;
+    double s = 0, fa = 0, fb = 0, fp = 0;
+    for (int y = y0; y < y1; ++y) {
+        const double mu = thermo_acc<1, true>(U[(size_t)y * N + x], k, logtab, fa, fb, fp);
+        s += p.delt_max / sqrt(1.0 + 62.5 * (mu * mu));
+    }
+    part[(size_t)blockIdx.y * N + x] = s;
+}
+CHS_KERNEL void k_slab_colsum_final(const double* part, int nchunks, int N, double* colsum) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= N) return;
+    double s = 0;
+    for (int c = 0; c < nchunks; ++c) s += part[(size_t)c * N + x];
+    colsum[x] = s;
+}
+
+// gradient energy of the stored (jittered) field by np.gradient's stencils (solver.py:213-217): raw sum of
+// (gy^2 + gx^2) h^2 over this rank's rows; top / bot = the neighbouring ranks' boundary rows (ignored at the
+// domain edges); per-block partial sums in part[gridDim.x]
+CHS_KERNEL void k_slab_grad(const double* U, const double* top, const double* bot, int rows, int row_base, int N, double* part) {
+    CHS_SMEM_DECL
+    double* red = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    double v = 0;
+    const size_t total = (size_t)rows * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / N), x = (int)(i % N);
+        const int gy_ = row_base + y;
+        const double c = U[i];
+        const double up = (y > 0) ? U[i - N] : top[x], dn = (y < rows - 1) ? U[i + N] : bot[x];
+        double gy, gx;
+        if (gy_ == 0) gy = dn - c;
+        else if (gy_ == N - 1) gy = c - up;
+        else gy = 0.5 * (dn - up);
+        if (x == 0) gx = U[i + 1] - c;
+        else if (x == N - 1) gx = c - U[i - 1];
+        else gx = 0.5 * (U[i + 1] - U[i - 1]);
+        v += gy * gy + gx * gx;
+    }
+    red[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (unsigned j = 0; j < blockDim.x; ++j) t += red[j];
+        part[blockIdx.x] = t;
     }
 }
 
@@ -377,7 +469,7 @@ CHS_KERNEL void k_slab_sums(const double* part, int ntiles, const double* part_g
 // step_control() of the tile path, fed with the rank-reduced sums (one thread; every rank runs
 // it on identical inputs and so keeps an identical Sim image).  post = 0: prologue.
 CHS_KERNEL void k_slab_control(Sim* S, double* vec, double* rows, long long rows_cap, int N, int last, int post,
-                               const double* allvec, int P) {
+                               const double* allvec, int P, const double* colsum) {
     CHS_PDL_TRIGGER();
     CHS_PDL_WAIT();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -443,6 +535,20 @@ CHS_KERNEL void k_slab_control(Sim* S, double* vec, double* rows, long long rows
         S->mu2_pending = vec[R_MU2];
     }
     if (last) return;
+    // ---- "pre" part of the next iteration: adaptive dt (solver.py:177-193) from the all-rank column sums
+    const long long cs_next = S->computed_steps;
+    if (colsum && p.adaptive_time && cs_next > 500 && (cs_next % 2) == 0) {
+        double m = colsum[0];
+        for (int x = 1; x < N; ++x) {
+            const double v = colsum[x];
+            if (v != v) m = v; else if (m == m && v < m) m = v;      // NaN propagates like np.min
+        }
+        const double dnew = (m > p.delt) ? m : p.delt;               // Python max(params.delt, dyn): NaN loses
+        if (dnew / S->delt > 1.15) S->delt = 0.75 * S->delt + 0.25 * dnew;
+        else S->delt = dnew;
+        S->delt_coef = S->delt;
+        sim_derive_lam(*S);
+    }
     S->time_delta_sum += S->delt;
     S->time_passed = S->time_delta_sum / p.M_tilde;
     if (p.time_limit_s > 0.0 && S->time_passed > p.time_limit_s) { S->stop_reason = CHS_STOP_TIME; S->halted = 1; }

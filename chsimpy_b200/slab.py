@@ -85,6 +85,8 @@ class SlabEngine:
         self._full = None
         self._mean = 0.0
         self._prof = None                                # bench.py: list of (start, end) CUDA events around the exchanges
+        self._cols = self._cols_scr = self._halo = None  # adaptive dt: all-rank column sums; jitter: neighbours' rows
+        self._cs = 1                                     # host mirror of computed_steps (which iterations update delt)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -246,6 +248,14 @@ class SlabEngine:
 
     def begin(self):
         lib, h = self.lib, self._h
+        # the conserved mean (Q4) is that of the field hat_U is recomputed from (solver.py:159): after a jittered
+        # call that is the jittered field (quirk Q2), not U_init
+        m = self._tensor(self.U).sum(dtype=self._torch().float64)
+        if self.P > 1:
+            import torch.distributed as dist
+            m = m.reshape(1).clone()
+            dist.all_reduce(m)
+        self._mean = float(m) / (self.N * self.N)
         self._ck(lib.chs_slab_begin(h), "chs_slab_begin")
         self._row(self.S_FWD, self.U, self.A)            # x-transform of U
         self._transpose(self.A, self.B)
@@ -254,44 +264,105 @@ class SlabEngine:
         self._ck(lib.chs_slab_clear_yedge(h), "chs_slab_clear_yedge")
         self._ck(lib.chs_slab_reduce(h, self.R, 0), "chs_slab_reduce")
         self._allreduce_vec()
-        self._ck(lib.chs_slab_control(h, 0, 0), "chs_slab_control")
+        cols = None
+        if self._ps.adaptive_time:
+            if self._want_cols(self._cs, False):         # re-entry: the first iteration may already update delt
+                self._colsum()
+            elif self._cols is None:
+                self._cols = self.be.empty((self.N,))
+                self._cols_scr = self.be.empty((16 * self.N,))
+            cols = self.be.ptr(self._cols)
+        self._ck(lib.chs_slab_control_dyn(h, 0, 0, None, cols), "chs_slab_control_dyn")
         if self._peer is not None:
             self._hdl.barrier()                          # every rank is done reading B before it is rewritten
         self._transpose(self.A, self.B)                  # every step starts from B = transpose(A)
 
-    def _step(self, last):
+    def _want_cols(self, cs_next, last):
+        """Will the iteration that follows update delt (solver.py:177-181)?  cs_next = computed_steps it starts with."""
+        return bool(self._ps.adaptive_time) and not last and cs_next > 500 and cs_next % 2 == 0
+
+    def _colsum(self):
+        """All-rank column sums of delt_max/sqrt(1+62.5 mu(U)^2) -> self._cols (adaptive dt, solver.py:182-183)."""
+        if self._cols is None:
+            self._cols = self.be.empty((self.N,))
+            self._cols_scr = self.be.empty((16 * self.N,))
+        self._ck(self.lib.chs_slab_colsum(self._h, self.be.ptr(self._cols), self.be.ptr(self._cols_scr)), "chs_slab_colsum")
+        if self.P > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._tensor(self._cols))    # sum over the row slabs; identical bits on every rank
+
+    def _halo_rows(self):
+        """Device pointers to the boundary rows of the neighbouring slabs (own rows at the domain edges)."""
+        be, R, N = self.be, self.R, self.N
+        if self.P == 1:
+            return be.ptr(self.U), be.ptr(self.U)
+        import torch
+        import torch.distributed as dist
+        U = self._tensor(self.U)
+        mine = torch.stack([U[0], U[R - 1]]).contiguous()
+        allb = [torch.empty_like(mine) for _ in range(self.P)]
+        dist.all_gather(allb, mine)
+        self._halo = allb                                # keep alive until the kernel has run
+        top = allb[self.rank - 1][1] if self.rank > 0 else U[0]
+        bot = allb[self.rank + 1][0] if self.rank < self.P - 1 else U[R - 1]
+        return top.data_ptr(), bot.data_ptr()
+
+    def _step(self, last, noise=None, noise_mean=None):
+        """One CH step.  noise / noise_mean: device pointers to this step's draws for the rank's rows and to the
+        mean of the whole draw (jitter), or None."""
         lib, h, be, R, N = self.lib, self._h, self.be, self.R, self.N
         esz = 8 * N
+        jit = noise is not None
+        adaptive = bool(self._ps.adaptive_time)
 
         def y_pass(r0, rc):      # hat_mu' = DCT(B); H = (H + Seig*hat_mu')/CHeig; B = IDCT(H): one kernel
             self._ck(lib.chs_slab_update(h, be.ptr(self.H) + r0 * esz, be.ptr(self.B) + r0 * esz, rc,
                                          self.row_base + r0), "chs_slab_update")
 
-        def x_pass(r0, rc):      # U_new stored, diagnostics, mu, x-transform
-            self._ck(lib.chs_slab_row(h, self.S_STEP, be.ptr(self.A) + r0 * esz, be.ptr(self.A) + r0 * esz, rc,
-                                      self.row_base + r0, 1, float(self._mean)), "chs_slab_row")
+        def x_pass(r0, rc):      # (jitter,) U_new stored, diagnostics, mu, x-transform
+            self._ck(lib.chs_slab_step_x(h, be.ptr(self.A) + r0 * esz, be.ptr(self.A) + r0 * esz, rc, self.row_base + r0,
+                                         float(self._mean), noise, noise_mean), "chs_slab_step_x")
 
+        def after_x():           # what needs the complete stored field of this step
+            if jit:              # stencil gradient energy of the jittered field (1-row halo from the neighbours)
+                top, bot = self._halo_rows()
+                self._ck(lib.chs_slab_grad(h, top, bot), "chs_slab_grad")
+            if self._want_cols(self._cs + 1, last):
+                self._colsum()
+
+        cols = be.ptr(self._cols) if (adaptive and self._cols is not None) else None
+        edges = (0, 0) if jit else (int(self.rank == 0), int(self.rank == self.P - 1))
         self._pass(y_pass, self.B, self.A)
         if self._peer is not None and self._nchunks == 1:
             # peer-memory route: x pass, its exchange and the 7 sums (stored into every rank's gather buffer by
             # the sums kernel) share ONE device-side barrier; the control kernel adds the ranks' sums in rank
             # order -- 8 launches per step, no collective
             x_pass(0, R)
+            after_x()
+            cols = be.ptr(self._cols) if (adaptive and self._cols is not None) else None
             self._transpose(self.A, self.B, sync=False)
             par = self._parity
             self._parity ^= 1
             goff = be.ptr(self._gather) - self._ab_base + (par * self.P + self.rank) * 64
             slots = (C.c_uint64 * self.P)(*[self._peer[p] + goff for p in range(self.P)])
-            self._ck(lib.chs_slab_sums_peers(h, int(self.rank == 0), int(self.rank == self.P - 1), slots), "chs_slab_sums_peers")
+            self._ck(lib.chs_slab_sums_peers(h, edges[0], edges[1], slots), "chs_slab_sums_peers")
             self._hdl.barrier()
-            self._ck(lib.chs_slab_control_gathered(h, int(bool(last)), 1, be.ptr(self._gather) + par * self.P * 64),
-                     "chs_slab_control_gathered")
+            self._ck(lib.chs_slab_control_dyn(h, int(bool(last)), 1, be.ptr(self._gather) + par * self.P * 64, cols),
+                     "chs_slab_control_dyn")
+            self._cs += 1
             return
-        self._pass(x_pass, self.A, self.B)               # B for the next step (its barrier also covers the sums)
+        if jit or adaptive:      # the whole field of the step must be stored before the stencil / column sums
+            x_pass(0, R)
+            after_x()
+            cols = be.ptr(self._cols) if (adaptive and self._cols is not None) else None
+            self._transpose(self.A, self.B)
+        else:
+            self._pass(x_pass, self.A, self.B)           # B for the next step (its barrier also covers the sums)
         # per-tile partials + y-edge terms of the stored field -> the 7 local sums, one launch
-        self._ck(lib.chs_slab_sums(h, int(self.rank == 0), int(self.rank == self.P - 1)), "chs_slab_sums")
+        self._ck(lib.chs_slab_sums(h, edges[0], edges[1]), "chs_slab_sums")
         self._allreduce_vec()
-        self._ck(lib.chs_slab_control(h, int(bool(last)), 1), "chs_slab_control")
+        self._ck(lib.chs_slab_control_dyn(h, int(bool(last)), 1, None, cols), "chs_slab_control_dyn")
+        self._cs += 1
 
     def get_state(self, sim=0):
         st = _lib.State()
@@ -303,23 +374,54 @@ class SlabEngine:
     def set_state(self, sim, st):
         self._ck(self.lib.chs_slab_set_state(self._h, C.byref(st)), "chs_slab_set_state")
 
+    def pcg64_noise(self, bit_generator_state, n):
+        """(noise [n][R][N] for this rank's rows, global per-step means [n]) on the device: the next n*N*N doubles of
+        a numpy PCG64 generator, bit-identical to rng.random((N, N)) per step (each rank generates only its rows)."""
+        st = bit_generator_state["state"]
+        s128, i128 = int(st["state"]), int(st["inc"])
+        m64 = (1 << 64) - 1
+        R, N = self.R, self.N
+        noise = self.be.empty((n, R, N))
+        mean = self.be.empty((n,))
+        for i in range(n):
+            self._ck(self.lib.chs_slab_pcg64_fill(self._h, s128 >> 64, s128 & m64, i128 >> 64, i128 & m64,
+                                                  i * N * N + self.row_base * N, self.be.ptr(noise) + i * R * N * 8, R * N),
+                     "chs_slab_pcg64_fill")
+        self._ck(self.lib.chs_slab_row_means(self._h, self.be.ptr(noise), n, R * N, self.be.ptr(mean)), "chs_slab_row_means")
+        if self.P > 1:
+            import torch.distributed as dist
+            mt = self._tensor(mean)
+            dist.all_reduce(mt)
+            mt /= self.P
+        return noise, mean
+
     def run(self, iters, draw_noise=None, poll_every=None):
-        if draw_noise is not None:
-            raise NotImplementedError("jitter is not available on the slab path yet")
-        if self._ps.adaptive_time:
-            raise NotImplementedError("adaptive time stepping is not available on the slab path yet")
         done = np.zeros(1, np.int64)
         if iters <= 0:
             return [np.empty((0, 9))], done
         chunk = self.rows_cap if poll_every is None else min(self.rows_cap, int(poll_every))
+        if draw_noise is not None:                       # noise of a whole chunk is resident: bound it to ~1 GiB
+            chunk = max(1, min(chunk, (1 << 30) // (self.R * self.N * 8)))
         out = []
+        self._cs = int(self.get_state(0).computed_steps)
         self.begin()
         n_done = 0
         self.get_state(0)
         while n_done < iters and not self._halted:
             n = min(chunk, iters - n_done)
+            noise = nmean = None
+            if draw_noise is not None:
+                drawn = draw_noise(n)
+                if isinstance(drawn, tuple):              # generated on the device (PCG64 kernel), this rank's rows
+                    noise, nmean = drawn
+                else:                                     # host draws (Sobol): this rank's rows are uploaded
+                    r0 = self.row_base
+                    noise = self.be.to_device(np.ascontiguousarray(drawn[:, r0:r0 + self.R, :]))
+                    nmean = self.be.to_device(drawn.reshape(n, -1).mean(axis=1))
             for i in range(n):
-                self._step(last=(n_done + i + 1 == iters))
+                self._step(last=(n_done + i + 1 == iters),
+                           noise=None if noise is None else self.be.ptr(noise) + i * self.R * self.N * 8,
+                           noise_mean=None if nmean is None else self.be.ptr(nmean) + i * 8)
             self.get_state(0)
             if self._rw:
                 out.append(self.be.download(self.rows[:self._rw, :]))

@@ -194,6 +194,20 @@ double* chs_slab_vec(chs_slab*);                                      /* device 
 int chs_slab_prepare(chs_slab*, const double* U_with_halo /*[rows+2][N]*/, double mean_u);   /* solver.py:84-127 */
 int chs_slab_control(chs_slab*, int32_t last, int32_t post);          /* solver.py:195-199, 230-249 */
 int chs_slab_control_gathered(chs_slab*, int32_t last, int32_t post, const double* allvec /*[world][8]*/);
+/* --adaptive-time and --jitter on the slab path (solver.py:177-193, 210-211):
+ *   chs_slab_colsum       per-column sums of delt_max/sqrt(1+62.5 mu^2) over the rank's rows -> colsum[N] (scratch >= 16 N)
+ *   chs_slab_control_dyn  control step that also applies the adaptive-dt update from the all-rank colsum (or NULL)
+ *   chs_slab_step_x       x pass with this step's noise rows + the mean of the whole draw (device scalar)
+ *   chs_slab_grad         np.gradient stencil energy of the stored jittered field (neighbour boundary rows given)
+ *   chs_slab_pcg64_fill / chs_slab_row_means   numpy PCG64 draws / row means on the slab handle's stream */
+int chs_slab_colsum(chs_slab*, double* colsum, double* scratch);
+int chs_slab_control_dyn(chs_slab*, int32_t last, int32_t post, const double* allvec, const double* colsum);
+int chs_slab_step_x(chs_slab*, const double* src, double* dst, int32_t rows, int32_t row_base, double mean_u,
+                    const double* noise, const double* noise_mean);
+int chs_slab_grad(chs_slab*, const double* top, const double* bot);
+int chs_slab_pcg64_fill(chs_slab*, uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
+                        uint64_t offset, double* out, int64_t count);
+int chs_slab_row_means(chs_slab*, const double* in, int64_t rows, int64_t cols, double* out);
 int chs_slab_begin(chs_slab*);
 int chs_slab_rewind_rows(chs_slab*);
 int chs_slab_get_state(chs_slab*, chs_state*, int64_t* rows_written, int32_t* halted);

@@ -56,6 +56,9 @@ CASES = {
     # BASELINE config 5 sizes (the reference needs about 6.5 s and 8 GiB per step at N=8192)
     "n4096_k6": dict(p=dict(N=4096, ntmax=6, full_sim=True), keep_U=False),
     "n8192_k4": dict(p=dict(N=8192, ntmax=4, full_sim=True), keep_U=False),
+    # jitter + adaptive dt on the slab path (N > 1024); delt_max scaled with 512/N (the column SUM makes delt_dyn ~ N, Q6)
+    "n2048_jitter_adaptive": dict(p=dict(N=2048, ntmax=530, full_sim=True, adaptive_time=True, delt_max=5e-11, jitter=0.005),
+                                  keep_U=False),
     "n100_k100": dict(p=dict(N=100, ntmax=100, full_sim=True), keep_U=True),     # benchmark.py -N 100 smoke size
     # other generators / user-supplied field
     "n64_lcg_k100": dict(p=dict(N=64, ntmax=100, full_sim=True, generator="lcg"), keep_U=True, keep_Uinit=True),

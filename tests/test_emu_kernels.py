@@ -136,6 +136,35 @@ def test_slab_peer_route_single_rank(be):
     assert sol.computed_steps == 9 and rel.max() < 1e-11, rel.max(axis=0)
 
 
+@pytest.mark.parametrize("kw,steps,selfpeer", [(dict(jitter=0.004), 14, False),
+                                               (dict(jitter=0.003, adaptive_time=True, delt_max=3e-9), 508, True)])
+def test_slab_jitter_and_adaptive_vs_oracle(be, kw, steps, selfpeer):
+    """--jitter / --adaptive-time on the slab path (reference solver.py:177-193, 210-211): the rank's rows of the
+    PCG64 noise stream, stencil gradient energy with halo rows, all-rank column sums -> delt; against the oracle,
+    with a re-entry in the middle (quirks Q2/Q3; adaptive: the multipliers revert to params.delt on re-entry)."""
+    import ch_oracle as orc
+    p = ch.Parameters()
+    p.N, p.no_gui, p.full_sim, p.kappa_tilde, p.seed, p.ntmax = 64, True, True, 2.7e-4, 5, steps
+    for k, v in kw.items():
+        setattr(p, k, v)
+    s = ch.Solver(p, _backend=be, _force_slab=True, _selfpeer=selfpeer)
+    s.prepare()
+    first = steps - 5
+    s.solve_or_resume(first)
+    sol = s.solve_or_resume(5)
+    o = orc.run_default(N=64, nsteps=first, seed=5, kappa_tilde=2.7e-4, full_sim=True, **kw)
+    o.run(5)
+    assert sol.computed_steps == o.computed_steps == steps
+    rows, ref = sol.timedata.data(), o.rows
+    rel = np.abs(rows - ref) / np.maximum(np.abs(ref), 1e-300)
+    rel[ref == 0] = np.abs(rows[ref == 0])
+    assert rel.max() < 1e-9, rel.max(axis=0)
+    assert np.abs(sol.U - o.U).max() < 1e-11
+    assert abs(s.delt - o.delt) <= 1e-12 * o.delt
+    if "adaptive_time" in kw:
+        assert o.delt > p.delt                   # the adaptive branch really ran
+
+
 def test_slab_path_honours_stop_flag(be):
     """A time limit hit at step ~10 while the host has 40 steps queued (full_sim, so no poll inside the
     chunk): the slab kernels must freeze the state behind the device-side flag exactly like the batched

@@ -243,6 +243,44 @@ def test_slab_path_single_gpu(name, force):
     assert sol.computed_steps == m["computed_steps"]
 
 
+def test_slab_jitter_adaptive_n2048_golden():
+    """--jitter + --adaptive-time on the slab path (N > 1024) against the unmodified reference's run
+    (tests/golden/n2048_jitter_adaptive.npz): rows, the delt sequence, and the field."""
+    import chsimpy_b200 as ch
+    z, m = load("n2048_jitter_adaptive")
+    p = make_params(m)
+    s = ch.Solver(p)
+    s.prepare()
+    sol = s.solve_or_resume(p.ntmax)
+    assert sol.computed_steps == m["computed_steps"]
+    check_rows(sol.timedata.data(), z["rows"], p.N)
+    assert float(sol.delt[-1]) > p.delt and abs(s.delt - m["delt_final"]) <= 1e-12 * m["delt_final"]
+    st = p.N // 64
+    assert np.abs(sol.U[::st, ::st] - z["U_sample"]).max() <= U_TOL
+
+
+@pytest.mark.parametrize("kw,steps", [(dict(jitter=0.004), 40), (dict(adaptive_time=True, delt_max=1.2e-9), 560),
+                                      (dict(jitter=0.003, adaptive_time=True, delt_max=1.2e-9), 530)])
+def test_slab_jitter_adaptive_forced_vs_oracle(kw, steps):
+    """The same features on the forced slab path at N=128 against the oracle, with a re-entry."""
+    import ch_oracle as orc
+    import chsimpy_b200 as ch
+    p = ch.Parameters()
+    p.N, p.no_gui, p.full_sim, p.kappa_tilde, p.seed, p.ntmax = 128, True, True, 2.7e-4, 5, steps
+    for k, v in kw.items():
+        setattr(p, k, v)
+    s = ch.Solver(p, _force_slab=True)
+    s.prepare()
+    s.solve_or_resume(steps - 7)
+    sol = s.solve_or_resume(7)
+    o = orc.run_default(N=128, nsteps=steps - 7, seed=5, kappa_tilde=2.7e-4, full_sim=True, **kw)
+    o.run(7)
+    assert sol.computed_steps == o.computed_steps == steps
+    check_rows(sol.timedata.data(), o.rows, 128)
+    assert np.abs(sol.U - o.U).max() <= U_TOL
+    assert abs(s.delt - o.delt) <= 1e-12 * o.delt
+
+
 def test_slab_path_energy_stop():
     """The slab path (default for N > 1024, where full_sim defaults to False) must honour the device-side
     stop flag: the 8280-step run to the energy stop, 128 steps queued per host poll, forced onto the slab

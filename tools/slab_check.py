@@ -12,7 +12,7 @@ if world > 1:
 W = (rank, world) if world > 1 else None
 gold = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-for case in ("n2048_k10", "n8192_k4"):       # frozen outputs of the reference (tests/golden/make_golden.py)
+for case in ("n2048_k10", "n8192_k4") + (("n2048_jitter_adaptive",) if "--jitter" in sys.argv else ()):       # frozen outputs of the reference (tests/golden/make_golden.py)
     z = np.load(os.path.join(gold, case + ".npz")); m = json.loads(str(z["meta"]))
     p = ch.Parameters(); p.no_gui = True
     for k, v in m["params"].items(): setattr(p, k, v)
@@ -26,8 +26,9 @@ for case in ("n2048_k10", "n8192_k4"):       # frozen outputs of the reference (
     assert rel.max() < 1e-9 and du < 1e-11
     del s
 
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+N = int(argv[0]) if len(argv) > 0 else 8192
+steps = int(argv[1]) if len(argv) > 1 else 20
 p = ch.Parameters(); p.no_gui = True; p.N = N; p.full_sim = True; p.kappa_tilde = 2.989112919661156e-4
 t = time.perf_counter(); s = ch.Solver(p, _world=W); s.prepare(); torch.cuda.synchronize()
 if rank == 0: print(f"[slab] N={N} setup+prepare {time.perf_counter()-t:.1f}s", flush=True)
