@@ -311,6 +311,7 @@ def run_b200(args):
     groups = [BatchStepper(N_GRID, structs[g * Bg:(g + 1) * Bg], rows_cap=K + 8) for g in range(G)]
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
+    cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(G)]
     barrier()
     te0 = time.perf_counter()
     for g, sg in enumerate(groups):
@@ -321,8 +322,10 @@ def run_b200(args):
         sg.end()                                            # materialises U = idctn(hat_U); returns when the group is done
         copy_stream.wait_stream(main_stream)
         with torch.cuda.stream(copy_stream):
+            cev[g][0].record()
             rows_host[g * Bg:(g + 1) * Bg].copy_(sg.rows[:, :K, :], non_blocking=True)     # D2H TimeData
             U_host[g * Bg:(g + 1) * Bg].copy_(sg.U, non_blocking=True)                       # D2H final fields
+            cev[g][1].record()
     copy_stream.synchronize()
     barrier()
     te = time.perf_counter() - te0
@@ -336,7 +339,8 @@ def run_b200(args):
            "d2h_bytes_per_step": int((rows_host.numel() + U_host.numel()) * 8 / K),
            "what": f"BatchStepper.set_U (host U_init) -> prepare -> K steps -> TimeData rows + final U in pinned host memory; "
                    f"{G} member groups, the D2H of a group overlaps the steps of the next (copy stream)",
-           "groups": G, "pinned_numa_node": numa}
+           "groups": G, "pinned_numa_node": numa,
+           "d2h_gbs_this_rank": round((rows_host.numel() + U_host.numel()) * 8 / 1e6 / sum(a.elapsed_time(b) for a, b in cev), 1)}
     del groups, rows_host, U_host
     torch.cuda.empty_cache()
 
@@ -446,25 +450,29 @@ def jitter_adaptive_probe(ch):
 
 def bind_to_gpu_numa(index):
     """Pins this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers it
-    allocates next are node-local (8 ranks sharing one host otherwise halve each other's D2H rate)."""
+    allocates next are node-local (8 ranks sharing one host otherwise halve each other's D2H rate).
+    Returns the node, or a short reason why no binding was made."""
     try:
-        bus = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                      text=True).strip().lower()
-        if len(bus.split(":")[0]) == 8:
-            bus = bus[4:]
-        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        path = f"/sys/bus/pci/devices/{bus}/numa_node"
+        if not os.path.exists(path):
+            return f"no {path}"
+        node = int(open(path).read())
         if node < 0:
-            return None
+            return "numa_node=-1 (single node or not exposed)"
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.update(range(int(lo), int(hi or lo) + 1))
         cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
+        if not cpus:
+            return f"node {node}: none of its CPUs is in this process's affinity mask"
+        os.sched_setaffinity(0, cpus)
         return node
-    except Exception:
-        return None
+    except Exception as e:                               # noqa: BLE001 -- best effort
+        return f"{type(e).__name__}: {e}"
 
 
 def large_domain_suite(ch, rank, world):
