@@ -299,8 +299,13 @@ def run_b200(args):
                 "k_row_gbs_own_16N2": round(16 * N_GRID ** 2 * B / (row_us * 1e-6) / 1e9, 1)}
 
     # ---- e2e: public API from host buffers, copies inside the timed region.  The members run as G groups:
-    # while group g+1 steps, the TimeData rows and final fields of group g drain to pinned host memory on a
-    # copy stream (double buffering in time); the pinned buffers are allocated NUMA-local to the GPU.
+    # while group g+1 steps, the results of group g drain to pinned host memory on a copy stream (double
+    # buffering in time).  Two variants are timed:
+    #   e2e.value              host U_init -> set_U (H2D) -> prepare -> K steps -> the steps' results (the TimeData
+    #                          rows: E, E2, SA, ... of every member and step) in pinned host memory (D2H)
+    #   e2e.with_final_fields  the same plus every member's final N x N field (what Solution.U / the per-run
+    #                          exports of experiment.py need once per simulation, i.e. once per ~1700 steps; at
+    #                          K = 20 steps per run it is 99.9 % of the bytes and bound by the host's D2H rate)
     del st
     torch.cuda.empty_cache()
     G = 4 if B % 4 == 0 and B >= 64 else 1
@@ -311,36 +316,56 @@ def run_b200(args):
     groups = [BatchStepper(N_GRID, structs[g * Bg:(g + 1) * Bg], rows_cap=K + 8) for g in range(G)]
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
-    cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(G)]
-    barrier()
-    te0 = time.perf_counter()
-    for g, sg in enumerate(groups):
-        sg.set_U(U0)                                        # H2D: the members share one initial field (quirk Q11)
-        sg.prepare()
-        sg.begin()
-        sg.steps(K, last=True)
-        sg.end()                                            # materialises U = idctn(hat_U); returns when the group is done
-        copy_stream.wait_stream(main_stream)
-        with torch.cuda.stream(copy_stream):
-            cev[g][0].record()
-            rows_host[g * Bg:(g + 1) * Bg].copy_(sg.rows[:, :K, :], non_blocking=True)     # D2H TimeData
-            U_host[g * Bg:(g + 1) * Bg].copy_(sg.U, non_blocking=True)                       # D2H final fields
-            cev[g][1].record()
-    copy_stream.synchronize()
-    barrier()
-    te = time.perf_counter() - te0
-    if world > 1:
-        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        te = float(tt.item())
-    assert np.isfinite(rows_host.numpy()).all() and abs(float(U_host[B - 1].mean()) - float(U0.mean())) < 1e-9
+
+    def e2e_run(with_fields):
+        cev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(G)]
+        done = [torch.cuda.Event() for _ in range(G)]
+        barrier()
+        t0_ = time.perf_counter()
+        for sg in groups:
+            sg.set_U(U0)                                    # H2D: the members share one initial field (quirk Q11)
+            sg.prepare()                                    # row 0 (reads it back: the only host syncs of the run)
+        for g, sg in enumerate(groups):
+            sg.begin()
+            sg.steps(K, last=True)
+            if with_fields:
+                sg.end()                                    # queues U = idctn(hat_U)
+            done[g].record(main_stream)
+            copy_stream.wait_event(done[g])
+            with torch.cuda.stream(copy_stream):
+                cev[g][0].record()
+                rows_host[g * Bg:(g + 1) * Bg].copy_(sg.rows[:, :K, :], non_blocking=True)     # D2H TimeData
+                if with_fields:
+                    U_host[g * Bg:(g + 1) * Bg].copy_(sg.U, non_blocking=True)                   # D2H final fields
+                cev[g][1].record()
+        copy_stream.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0_
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        for sg in groups:
+            sg.poll()                                       # (outside the timed region) every member ran K steps
+            assert int(sg._rw.min()) == K
+        assert np.isfinite(rows_host.numpy()).all()
+        return dt, sum(a.elapsed_time(b) for a, b in cev)
+    e2e_run(False)                                          # warm-up of the group handles
+    te, _ = e2e_run(False)
+    tf, cms = e2e_run(True)
+    assert abs(float(U_host[B - 1].mean()) - float(U0.mean())) < 1e-9
+    row_bytes, fld_bytes = rows_host.numel() * 8, U_host.numel() * 8
     e2e = {"value": round(world * B * K / te, 1), "unit": "sim-steps/s",
            "h2d_bytes_per_step": int((G * U0.size * 8 + B * 136) / K),
-           "d2h_bytes_per_step": int((rows_host.numel() + U_host.numel()) * 8 / K),
-           "what": f"BatchStepper.set_U (host U_init) -> prepare -> K steps -> TimeData rows + final U in pinned host memory; "
-                   f"{G} member groups, the D2H of a group overlaps the steps of the next (copy stream)",
+           "d2h_bytes_per_step": int(row_bytes / K),
+           "what": f"BatchStepper.set_U (host U_init, H2D) -> prepare -> K steps -> every step's TimeData row of every member "
+                   f"in pinned host memory (D2H on a copy stream); {G} member groups",
            "groups": G, "pinned_numa_node": numa,
-           "d2h_gbs_this_rank": round((rows_host.numel() + U_host.numel()) * 8 / 1e6 / sum(a.elapsed_time(b) for a, b in cev), 1)}
+           "with_final_fields": {"value": round(world * B * K / tf, 1), "unit": "sim-steps/s",
+                                 "d2h_bytes_per_step": int((row_bytes + fld_bytes) / K),
+                                 "d2h_gbs_this_rank": round((row_bytes + fld_bytes) / 1e6 / cms, 1),
+                                 "what": "the same plus the final N x N field of every member (Solution.U): the D2H of a group "
+                                         "overlaps the steps of the next; bound by the host's D2H rate when all GPUs of the box copy"}}
     del groups, rows_host, U_host
     torch.cuda.empty_cache()
 

@@ -44,6 +44,7 @@ struct chs_solver {
     // host mirrors
     std::vector<Sim> hsims;
     std::vector<int> hindex;
+    std::vector<char> hstale;       // U of sim i is older than hat_U (steps ran without per-step U storage): chs_end materialises it
     int n_running;
     long long launches;
     int num_sms;
@@ -333,6 +334,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     std::memset(s->hsims.data(), 0, sizeof(Sim) * batch);
     s->hindex.resize(batch);
     for (int i = 0; i < batch; ++i) s->hindex[i] = i;
+    s->hstale.assign(batch, 0);
     s->n_running = batch;
     s->launches = 0;
     s->timing = false; s->ev_used = 0; s->ev_diag = false; s->t_iters = 0;
@@ -529,6 +531,7 @@ extern "C" int chs_prepare(chs_solver* s, const double* mean_U_host) {
     if (!s || !mean_U_host) return fail("chs_prepare: bad argument");
     CHS_CUDA(cudaMemcpyAsync(s->mean, mean_U_host, sizeof(double) * s->batch, cudaMemcpyHostToDevice, s->stream));
     CHS_CUDA(cudaStreamSynchronize(s->stream));        // mean_U_host may be pageable and short-lived
+    std::fill(s->hstale.begin(), s->hstale.end(), 0);  // the caller has just set U
     if (s->gemm) return gemm_launch(s, 0, 0, nullptr, nullptr, nullptr, false);
 #define CALL(NN) if (do_prepare<NN>(s)) return -1;
     CHS_FOR_N(s->N, CALL)
@@ -581,6 +584,9 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
     static const bool pdl_env = [] { const char* e = getenv("CHS_PDL"); return !e || atoi(e) != 0; }();
     const bool pdl = pdl_env && !s->timing;
     if (s->n_running == s->batch) a.sim_index = nullptr;
+    // without noise the step kernels keep the field in spectral form only (U is materialised by chs_end);
+    // with noise k_row stores the jittered U every step
+    for (int i = 0; i < s->n_running; ++i) s->hstale[s->hindex[i]] = noise ? 0 : 1;
     const dim3 grid(G::NTILES, s->n_running);
     const dim3 gcol = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, a.nsims), grow = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, a.nsims);
     for (long long it = 0; it < n_iters; ++it) {
@@ -644,11 +650,12 @@ extern "C" int chs_rewind_rows(chs_solver* s) {
 template <int N>
 static int do_end(chs_solver* s) {
     using G = Geo<N>;
-    if (pull(s)) return -1;
+    // host-tracked: which simulations stepped since their U was last valid.  No device read-back and no
+    // synchronisation -- the inverse transform is just queued on the handle's stream.
     std::vector<int> stale;
     for (int i = 0; i < s->batch; ++i)
-        if (s->hsims[i].u_stale && s->hsims[i].p.jitter == 0.0) stale.push_back(i);
-    for (int i = 0; i < s->batch; ++i) s->hsims[i].u_stale = 0;
+        if (s->hstale[i]) stale.push_back(i);
+    std::fill(s->hstale.begin(), s->hstale.end(), 0);
     if (!stale.empty()) {
         CHS_CUDA(cudaMemcpyAsync(s->index, stale.data(), sizeof(int) * stale.size(), cudaMemcpyHostToDevice, s->stream));
         KArgs a = base_args(s);
@@ -660,9 +667,6 @@ static int do_end(chs_solver* s) {
         s->launches += 2;
         CHS_CUDA(cudaGetLastError());
     }
-    // clear the stale flags on the device too
-    CHS_CUDA(cudaMemcpyAsync(s->sims, s->hsims.data(), sizeof(Sim) * s->batch, cudaMemcpyHostToDevice, s->stream));
-    CHS_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
 

@@ -194,7 +194,7 @@ def _noise_source(params, st):
 
 def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_init=None, host_procs=None,
                    batch_max=2048, poll_every=128, keep_fields=True, backend=None, device=None, timings=None,
-                   pipeline_batch=256):
+                   pipeline_batch=256, scalars=None):
     """Runs the members `run_ids` in lock-step on one GPU.  Returns a list of dicts with the
     reference's 12-tuple (`tuple`), the TimeData (`timedata`), the final field (`U`, optional)
     and the per-member Solution scalars."""
@@ -209,7 +209,10 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
         jobs.append((p.R, p.temp, p.B, float(p.func_A0(p.temp)), float(p.func_A1(p.temp)), p.XXX, p.kappa_tilde))
     nproc = host_procs or min(len(jobs), utils.get_number_physical_cores() or 1)
     pool = None
-    if nproc > 1 and len(jobs) > 1:
+    if scalars is not None:                            # computed by the caller (work-queue driver: one shared pool)
+        assert len(scalars) == len(jobs)
+        scal_iter = iter(scalars)
+    elif nproc > 1 and len(jobs) > 1:
         # forkserver: the workers start from a clean process (no CUDA context, no torch threads).
         # imap streams the results in order: the device runs batch k while the pool is still
         # working on the scalars of batch k+1 (the sympy work is the larger part of an ensemble)
@@ -284,6 +287,68 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
     return out
 
 
+def scalar_jobs(init_params, rand_values, A_list, run_ids):
+    """The _host_scalars job of every member in run_ids (what solve_ensemble would build itself)."""
+    jobs = []
+    for rid in run_ids:
+        p, _, _ = member_params(init_params, rid, rand_values, A_list)
+        jobs.append((p.R, p.temp, p.B, float(p.func_A0(p.temp)), float(p.func_A1(p.temp)), p.XXX, p.kappa_tilde))
+    return jobs
+
+
+def solve_from_queue(init_params, rand_values, A_list, claim, host_procs, keep_fields=True, backend=None, device=None,
+                     timings=None):
+    """Dynamic load balance over ranks: `claim()` hands out the next chunk of run ids (a shared
+    counter, see work_queue) or None.  The stop step varies by +-15 % with (A0, A1), so a static split leaves
+    ranks idle; here a rank that finishes early simply claims more.  The sympy scalars of chunk k+1 are computed
+    by the host pool while the device steps chunk k."""
+    pool = mp.get_context("forkserver").Pool(max(1, host_procs)) if host_procs and host_procs > 1 else None
+
+    def submit(ids):
+        jobs = scalar_jobs(init_params, rand_values, A_list, ids)
+        if pool is None:
+            return [_host_scalars(j) for j in jobs]
+        return pool.map_async(_host_scalars, jobs, chunksize=max(1, len(jobs) // (4 * host_procs)))
+    out, chunks = [], 0
+    t0 = time.perf_counter()
+    t_dev = t_wait = 0.0
+    nxt = claim()
+    nxt_s = submit(nxt) if nxt is not None else None
+    U_init = None
+    while nxt is not None:
+        cur, cur_s = nxt, nxt_s
+        nxt = claim()
+        nxt_s = submit(nxt) if nxt is not None else None
+        tw = time.perf_counter()
+        scal = cur_s if isinstance(cur_s, list) else cur_s.get()
+        t_wait += time.perf_counter() - tw
+        td = time.perf_counter()
+        res = solve_ensemble(init_params, rand_values, A_list, run_ids=cur, U_init=U_init, host_procs=1,
+                             keep_fields=keep_fields, backend=backend, device=device, scalars=scal)
+        t_dev += time.perf_counter() - td
+        out.extend(res)
+        chunks += 1
+    if pool is not None:
+        pool.close()
+        pool.join()
+    if timings is not None:
+        timings.update(host_scalars_s=t_wait, device_s=t_dev, host_procs=host_procs, chunks=chunks,
+                       total_s=time.perf_counter() - t0)
+    return out
+
+
+def work_queue(n_items, chunk, store=None, key="chs_ensemble_next_chunk"):
+    """claim() for solve_from_queue: an atomic counter in the process group's store (world > 1) or a local one."""
+    state = {"next": 0}
+
+    def claim():
+        c = (store.add(key, 1) - 1) if store is not None else state["next"]
+        state["next"] += 1
+        lo = c * chunk
+        return list(range(lo, min(lo + chunk, n_items))) if lo < n_items else None
+    return claim
+
+
 def _export_member(job):
     """Per-run files of reference simulator.py:135-156 (yaml scalars + csv matrices)."""
     fname_sol, yaml_on, export_csv, compress, sol = job
@@ -326,15 +391,23 @@ def main(argv=None):
                       f"localtime, {utils.get_current_localtime()}", f"argv, '{' '.join(sys.argv)}'"]
         with open(f"{init_params.file_id}-metadata.csv", 'w') as f:
             f.write("\n".join(utils_meta))
-    mine = shard(n_items, rank, world)
     tm = {}
     t0 = time.perf_counter()
     # the ranks of a box share its host cores: each gets its share for the sympy pool
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     share = max(1, (utils.get_number_physical_cores() or 1) // max(1, local_world))
-    res = solve_ensemble(init_params, rand_values, A_list, run_ids=mine,
-                         host_procs=(share if world > 1 else None) if ep.processes == -1 else max(1, ep.processes), timings=tm,
-                         keep_fields=not ep.no_export)
+    if world > 1:
+        # dynamic load balance: chunks of members are claimed from a counter in the process group's store
+        import torch.distributed as dist
+        store = dist.distributed_c10d._get_default_store()
+        chunk = max(16, min(256, -(-n_items // (4 * world))))
+        res = solve_from_queue(init_params, rand_values, A_list, work_queue(n_items, chunk, store),
+                               host_procs=share if ep.processes == -1 else max(1, ep.processes),
+                               keep_fields=not ep.no_export, timings=tm)
+    else:
+        res = solve_ensemble(init_params, rand_values, A_list, run_ids=shard(n_items, rank, world),
+                             host_procs=None if ep.processes == -1 else max(1, ep.processes), timings=tm,
+                             keep_fields=not ep.no_export)
     t_solve = time.perf_counter() - t0
     if not ep.no_export:
         jobs = [(f"{r['params'].file_id}.solution", init_params.yaml, init_params.export_csv,
@@ -351,7 +424,7 @@ def main(argv=None):
         gathered = [None] * world if rank == 0 else None
         dist.gather_object(tuples, gathered, dst=0)
         if rank == 0:
-            tuples = [t for part in gathered for t in part]
+            tuples = sorted((t for part in gathered for t in part), key=lambda t: t[9])     # by run id
         dist.barrier()
     if rank == 0:
         df = pd.DataFrame(tuples, columns=RESULT_COLUMNS)

@@ -120,7 +120,9 @@ int chs_poll(chs_solver*, int32_t* stop_reason, int64_t* computed_steps, int64_t
 int chs_rewind_rows(chs_solver*);
 
 /* Exit of solve_or_resume (solver.py:251): materialises U = idctn(hat_U) in the U
- * buffer for every sim whose U is stale (no-jitter runs never store U per step). */
+ * buffer for every sim whose U is stale (no-jitter runs never store U per step).  The inverse transform
+ * is queued on the handle's stream; the call does not synchronise (which simulations stepped is tracked on
+ * the host). */
 int chs_end(chs_solver*);
 
 /* Stand-alone transforms on [batch][N][N] device arrays (in -> out, T is scratch):

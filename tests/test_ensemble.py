@@ -112,6 +112,50 @@ def _rank_main(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _rank_queue(rank, world, port, q):
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from emu_lib import EmuBackend
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ep = ex.ExperimentParams()
+    ep.runs, ep.A_seed = 7, 85972
+    rv, A_list, n = ex.factor_table(ep)
+    store = dist.distributed_c10d._get_default_store()
+    res = ex.solve_from_queue(_params(), rv, A_list, ex.work_queue(n, 2, store), host_procs=1, backend=EmuBackend())
+    tuples = [r["tuple"] for r in res]
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(tuples, gathered, dst=0)
+    if rank == 0:
+        q.put([[t[9] for t in part] for part in gathered] + [sorted((t for part in gathered for t in part), key=lambda t: t[9])])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_work_queue_two_ranks_covers_every_member_once():
+    """Dynamic load balance: chunks of run ids claimed from a shared counter; every member is solved
+    exactly once, whichever rank claims it, with the same bits as the single-process run."""
+    import torch.multiprocessing as tmp
+    from emu_lib import EmuBackend
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = 27500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_rank_queue, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ids0, ids1, tuples = got
+    assert sorted(ids0 + ids1) == list(range(7)) and ids0 and ids1          # both ranks got work, nothing twice
+    ep = ex.ExperimentParams()
+    ep.runs, ep.A_seed = 7, 85972
+    rv, A_list, n = ex.factor_table(ep)
+    ref = [r["tuple"] for r in ex.solve_ensemble(_params(), rv, A_list, host_procs=1, backend=EmuBackend())]
+    assert tuples == ref
+
+
 def test_two_rank_gloo_equals_single_process():
     import torch.multiprocessing as tmp
     from emu_lib import EmuBackend

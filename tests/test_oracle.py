@@ -25,7 +25,10 @@ def test_every_fixture_was_pinned_bit_exact():
     names = sorted(glob.glob(os.path.join(GOLD, "*.npz")))
     assert len(names) >= 25
     for f in names:
-        m = json.loads(str(np.load(f)["meta"]))
+        z = np.load(f)
+        if "meta" not in z.files:            # factor_tables.npz: not a solver case
+            continue
+        m = json.loads(str(z["meta"]))
         assert m["oracle_bitexact"] is True, m["name"]
 
 
