@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libchs_b200.so")
-SOURCES = ("chs_api.cu", "chs_kernels.cuh", "chs_slab.cuh", "chs_gemm.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
+SOURCES = ("chs_api.cu", "chs_kernels.cuh", "chs_slab.cuh", "chs_big.cuh", "chs_gemm.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
 # (no -split-compile: it builds 2x faster but the kernels measured 6 % slower on B200)
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -72,6 +72,12 @@ PROTOTYPES = {
     "chs_slab_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "chs_slab_pcg64_fill": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64]),
     "chs_slab_row_means": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "chs_big_supports_n": (C.c_int32, [C.c_int32]),
+    "chs_big_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "chs_big_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "chs_big_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    "chs_big_phys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "chs_big_sums": (C.c_int, [C.c_void_p]),
     "chs_slab_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "chs_slab_yedge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "chs_slab_clear_yedge": (C.c_int, [C.c_void_p]),

@@ -733,6 +733,7 @@ extern "C" int64_t chs_launch_count(const chs_solver* s) { return s ? s->launche
 //  Slab path (large single domain; see chs_slab.cuh and chsimpy_b200/slab.py)
 // =======================================================================================
 #include "chs_slab.cuh"
+#include "chs_big.cuh"
 
 struct chs_slab {
     int device, N, rows, row_base, world, rank;
@@ -754,7 +755,12 @@ struct chs_slab {
 };
 static const int SLAB_UPD_BLOCKS = 1184, SLAB_PREP_BLOCKS = 1184;
 
-static int slab_lines(int N) { return geo_lines(N); }
+// sizes the FFT kernels do not take run on the GEMM-based arbitrary-N path (chs_big.cuh): one rank, any row count
+static bool fft_slab_supports(int N) {
+    return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || N == 8192 || N == 16384;
+}
+static bool big_mode(int N) { return !fft_slab_supports(N) && N >= 8 && N <= 2048; }
+static int slab_lines(int N) { return big_mode(N) ? 1 : geo_lines(N); }
 
 struct SlabLayout { size_t sim, part, part_ge, yedge, vec, tw, om, lam, gsin, lamg, kof, logtab, total; };
 static SlabLayout slab_layout(int N, int rows) {
@@ -777,12 +783,11 @@ static SlabLayout slab_layout(int N, int rows) {
     return L;
 }
 
-extern "C" int32_t chs_slab_supports_n(int32_t N) {
-    return (N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || N == 8192 || N == 16384) ? 1 : 0;
-}
+extern "C" int32_t chs_slab_supports_n(int32_t N) { return fft_slab_supports(N) ? 1 : 0; }
+extern "C" int32_t chs_big_supports_n(int32_t N) { return big_mode(N) ? 1 : 0; }
 extern "C" int32_t chs_slab_row_granularity(int32_t N) { return chs_slab_supports_n(N) ? slab_lines(N) : -1; }
 extern "C" int64_t chs_slab_workspace_bytes(int32_t N, int32_t rows) {
-    if (!chs_slab_supports_n(N) || rows < 1 || rows % slab_lines(N)) return -1;
+    if ((!chs_slab_supports_n(N) && !big_mode(N)) || rows < 1 || rows % slab_lines(N)) return -1;
     return (int64_t)slab_layout(N, rows).total;
 }
 
@@ -815,7 +820,9 @@ static int slab_set_attrs() {
 extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, int32_t row_base, int32_t world, int32_t rank,
                                      const chs_params* p, double* U, double* rowsbuf, int64_t rows_cap,
                                      void* workspace, int64_t workspace_bytes, const double* lambda_host, void* stream) {
-    if (!chs_slab_supports_n(N) || rows < 1 || rows % slab_lines(N) || !p) { fail("chs_slab_create: bad N/rows"); return nullptr; }
+    const bool big = big_mode(N);
+    if ((!chs_slab_supports_n(N) && !big) || rows < 1 || rows % slab_lines(N) || !p) { fail("chs_slab_create: bad N/rows"); return nullptr; }
+    if (big && (world != 1 || rows != N)) { fail("chs_slab_create: the arbitrary-N path runs on one rank"); return nullptr; }
     const SlabLayout L = slab_layout(N, rows);
     if (workspace_bytes < (int64_t)L.total) { fail("chs_slab_create: workspace too small"); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { fail("chs_slab_create: cudaSetDevice failed"); return nullptr; }
@@ -837,10 +844,12 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     std::vector<double> gs(N);
     std::vector<int> kof(N);
     const long double pi = 3.14159265358979323846264338327950288L;
-    fill_twiddles(N, tw);
-    fill_om(N, om);
+    if (!big) {                                     // FFT tables (powers of two only)
+        fill_twiddles(N, tw);
+        fill_om(N, om);
+        fill_kof(N, kof);
+    }
     for (int k = 0; k < N; ++k) { const long double sn = sinl(pi * k / N); gs[k] = (double)(sn * sn); }
-    fill_kof(N, kof);
     for (int i = 0; i < LOG_TABLE_N; ++i) {
         const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << 45), b1 = LOG_OFF + ((unsigned long long)(i + 1) << 45);
         double z0, z1; std::memcpy(&z0, &b0, 8); std::memcpy(&z1, &b1, 8);
@@ -854,15 +863,17 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     ok &= cudaMemcpyAsync(s->kof, kof.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->logtab, lt.data(), sizeof(double2) * LOG_TABLE_N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaMemcpyAsync(s->lam, lambda_host, sizeof(double) * N, cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
-    ok &= upload_const_tables(N, tw, om, s->stream) == 0;
     std::vector<double2> lamg;
-    fill_lamg(N, lambda_host, gs, lamg);
-    ok &= cudaMemcpyAsync(s->lamg, lamg.data(), sizeof(double2) * lamg.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    if (!big) {
+        ok &= upload_const_tables(N, tw, om, s->stream) == 0;
+        fill_lamg(N, lambda_host, gs, lamg);
+        ok &= cudaMemcpyAsync(s->lamg, lamg.data(), sizeof(double2) * lamg.size(), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
+    }
     ok &= cudaMemcpyAsync(s->sim, &s->hsim, sizeof(Sim), cudaMemcpyHostToDevice, s->stream) == cudaSuccess;
     ok &= cudaStreamSynchronize(s->stream) == cudaSuccess;
     int rc = 0;
 #define CALL(NN) rc = slab_set_attrs<NN>();
-    switch (N) {
+    if (!big) switch (N) {
         case 64: CALL(64) break; case 128: CALL(128) break; case 256: CALL(256) break; case 512: CALL(512) break;
         case 1024: CALL(1024) break; case 2048: CALL(2048) break; case 4096: CALL(4096) break;
         case 8192: CALL(8192) break; case 16384: CALL(16384) break;
@@ -1170,6 +1181,65 @@ extern "C" int chs_slab_set_state(chs_slab* s, const chs_state* st) {
 }
 
 // ---- device-side numpy PCG64 stream (jitter noise) -------------------------------------------
+// ---- arbitrary-N path (chs_big.cuh): stage-level calls on a slab handle created for a size the FFT kernels do
+// not take; every matrix operand is n8 x n8 (N rounded up to a multiple of 8), row-major with pitch ld, zero padded
+static int big_blocks(const chs_slab* s) {
+#ifdef CHS_EMU
+    return 2;
+#else
+    return s->N < 592 ? s->N : 592;
+#endif
+}
+extern "C" int chs_big_gemm(chs_slab* s, const double* A, const double* B, double* D, int32_t n8, int32_t ld) {
+    if (!s || !A || !B || !D || n8 < 8 || n8 % 8 || ld < n8) return fail("chs_big_gemm: bad argument");
+    const int nb = (n8 + BIG_TILE - 1) / BIG_TILE;
+    CHS_LAUNCH(k_big_gemm, dim3(nb, nb), dim3(128), 2 * BIG_TILE * (BIG_KS + 1) * sizeof(double), s->stream, A, B, D, (int)n8, (int)ld);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int chs_big_update(chs_slab* s, double* H, const double* Mh, int32_t ld) {
+    if (!s || !H || !Mh) return fail("chs_big_update: bad argument");
+    CHS_LAUNCH(k_big_update, dim3(big_blocks(s)), dim3(256), 0, s->stream, H, Mh, (const double*)s->lam, (const Sim*)s->sim, s->N, (int)ld);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int chs_big_copy(chs_slab* s, const double* src, int32_t sld, double* dst, int32_t dld, int32_t respect_halt) {
+    if (!s || !src || !dst) return fail("chs_big_copy: bad argument");
+    CHS_LAUNCH(k_big_copy, dim3(big_blocks(s)), dim3(256), 0, s->stream, src, (int)sld, dst, (int)dld, s->N, (const Sim*)s->sim, (int)respect_halt);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+// physics of the new field (Up, pitch ld; or the stored U when from_U): [jitter ->] U, diagnostics partials, mu -> A
+extern "C" int chs_big_phys(chs_slab* s, const double* Up, double* A, int32_t ld, double mean_u, const double* noise,
+                            const double* noise_mean, int32_t diag, int32_t from_U) {
+    if (!s || !A || (!Up && !from_U)) return fail("chs_big_phys: bad argument");
+#ifdef CHS_EMU
+    const int nt = 32;
+#else
+    const int nt = 256;
+#endif
+    CHS_LAUNCH(k_big_phys, dim3(big_blocks(s)), dim3(nt), 5 * nt * sizeof(double), s->stream, Up, s->U, A, s->N, (int)ld, s->sim,
+               (const double2*)s->logtab, mean_u, noise, noise_mean, (int)diag, (int)from_U, s->part);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+// the 7 sums of a step from the k_big_phys partials (+ the stencil gradient partials of chs_slab_grad)
+extern "C" int chs_big_sums(chs_slab* s) {
+    if (!s) return fail("chs_big_sums: null handle");
+    PeerPtrs pp;
+    for (int i = 0; i < 8; ++i) pp.p[i] = nullptr;
+    CHS_LAUNCH(k_slab_sums, dim3(1), dim3(128 * (R_NVAL + 1)), 128 * (R_NVAL + 1) * sizeof(double), s->stream,
+               (const double*)s->part, big_blocks(s), (const double*)s->part_ge, s->upd_used,
+               (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, (const double*)nullptr, s->N, s->vec, pp, 0);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int chs_pcg64_fill(chs_solver* s, uint64_t state_hi, uint64_t state_lo, uint64_t inc_hi, uint64_t inc_lo,
                               uint64_t offset, double* out, int64_t count) {
     if (!s || !out || count < 0) return fail("chs_pcg64_fill: bad argument");

@@ -271,15 +271,26 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
         }
         __syncthreads();
     }
-    if (tid != 0) return;
-    const chs_params& p = S->p;
-    if (post) {
-        double acc[P_NSLOT];
+    // the per-tile partial sums of all P_NSLOT slots, added by the whole CTA: every thread takes a strided share
+    // (all loads of the CTA are in flight together -- one L2 latency instead of 7*NTILES dependent ones, which
+    // was half of a single simulation's step time), then the fixed-order block reduction (deterministic)
+    double acc[P_NSLOT];
+    {
+        double v[P_NSLOT];
+#pragma unroll
         for (int s = 0; s < P_NSLOT; ++s) {
             double a = 0;
-            for (int tl = 0; tl < NTILES; ++tl) a += CHS_LDCG(part + s * NTILES + tl);
-            acc[s] = a;
+            if (post || s == P_MU2)
+                for (int tl = tid; tl < NTILES; tl += nthreads) a += CHS_LDCG(part + s * NTILES + tl);
+            v[s] = a;
         }
+        reduce_stage<P_NSLOT>(v, scratch, tid);
+        __syncthreads();
+        if (tid != 0) return;
+        reduce_final<P_NSLOT>(acc, scratch, nthreads);
+    }
+    const chs_params& p = S->p;
+    if (post) {
         const double N2 = (double)N * (double)N;
         const double L2sq = p.L * p.L;
         const double grad2 = (acc[P_GE] + acc[P_GYE] + acc[P_GXE]) / (p.delx * p.delx);
@@ -322,9 +333,7 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
             S->skip_check = 1;
         }
     } else {                                          // prologue (chs_begin): only ||mu||^2 is new
-        double a2 = 0;
-        for (int tl = 0; tl < NTILES; ++tl) a2 += CHS_LDCG(part + P_MU2 * NTILES + tl);
-        S->mu2_pending = a2;
+        S->mu2_pending = acc[P_MU2];
     }
     if (last) return;
     // ---- "pre" part of the next iteration --------------------------------------------

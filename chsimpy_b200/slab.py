@@ -443,3 +443,99 @@ class SlabEngine:
 
     def launch_count(self):
         return int(self.lib.chs_slab_launch_count(self._h))
+
+
+class BigEngine(SlabEngine):
+    """Arbitrary N (the reference accepts any N): sizes that are neither a power of two (FFT kernels) nor <= 104
+    (one-CTA GEMM kernel).  One simulation on one GPU; the 2-D DCT-II / DCT-III are FP64 tensor-core GEMMs
+    C.X.C^T / C^T.Y.C over global memory (csrc/chs_big.cuh), the rest is the slab path's elementwise, reduction
+    and control machinery.  Same interface as SlabEngine / BatchStepper."""
+
+    def __init__(self, N, param_struct, rows_cap=1024, backend=None, device=None):
+        from .solver import _CudaBackend
+        self.be = backend if backend is not None else _CudaBackend(device)
+        lib = self.lib = self.be.lib
+        self.N = n = int(N)
+        if not lib.chs_big_supports_n(n):
+            raise ValueError(f"N={N} is not supported by the arbitrary-N path (8..2048)")
+        self.rank, self.P, self.R, self.row_base = 0, 1, n, 0
+        self.batch, self.rows_cap = 1, int(rows_cap)
+        self.n8 = n8 = (n + 7) // 8 * 8
+        self.ld = n8
+        self.U = self.be.empty((n, n))
+        self.rows = self.be.empty((self.rows_cap, 9))
+        # Cm | Ct | H (hat_U) | A (mu) | T | M (hat_mu, then the new field): zero-padded n8 x ld operands
+        self.mats = self.be.empty((6, n8, self.ld))
+        if self.be.name == "cuda":
+            self.mats.zero_()
+        else:
+            self.mats[...] = 0.0
+        k = np.arange(n, dtype=np.longdouble)[:, None]
+        x = np.arange(n, dtype=np.longdouble)[None, :]
+        Cm = np.sqrt(np.longdouble(2) / n) * np.cos(np.pi * k * (2 * x + 1) / (2 * np.longdouble(n)))
+        Cm[0, :] = np.sqrt(np.longdouble(1) / n)
+        pad = np.zeros((2, n8, self.ld))
+        pad[0, :n, :n] = Cm.astype(np.float64)               # orthonormal DCT-II matrix (scipy.fftpack.dctn norm='ortho')
+        pad[1, :n, :n] = Cm.T.astype(np.float64)
+        self.be.upload(self.mats[:2], pad)
+        self._peer = None
+        self._nchunks = 1
+        self._main = self._side = None
+        wbytes = lib.chs_slab_workspace_bytes(n, n)
+        self.work = self.be.empty((wbytes,), "u1")
+        lam = np.ascontiguousarray(utils.laplace_spectrum_1d(n), dtype=np.float64)
+        self._ps = param_struct
+        self._h = _lib.check(lib, lib.chs_slab_create(self.be.device_index(), n, n, 0, 1, 0, C.byref(param_struct),
+                                                       self.be.ptr(self.U), self.be.ptr(self.rows), self.rows_cap,
+                                                       self.be.ptr(self.work), wbytes, lam.ctypes.data,
+                                                       self.be.stream_handle()), "chs_slab_create")
+        self._full = None
+        self._mean = 0.0
+        self._prof = None
+        self._cols = self._cols_scr = self._halo = None
+        self._cs = 1
+
+    def _m(self, i):
+        return self.be.ptr(self.mats) + i * self.n8 * self.ld * 8
+
+    def _gemm(self, a, b, d):
+        self._ck(self.lib.chs_big_gemm(self._h, self._m(a), self._m(b), self._m(d), self.n8, self.ld), "chs_big_gemm")
+
+    CM, CT, H_, A_, T_, M_ = range(6)
+
+    def begin(self):
+        lib, h, be = self.lib, self._h, self.be
+        m = self._tensor(self.U).sum(dtype=self._torch().float64)
+        self._mean = float(m) / (self.N * self.N)            # conserved mean of the field hat_U is recomputed from (Q2, Q4)
+        self._ck(lib.chs_slab_begin(h), "chs_slab_begin")
+        self._ck(lib.chs_big_copy(h, be.ptr(self.U), self.N, self._m(self.M_), self.ld, 0), "chs_big_copy")
+        self._gemm(self.CM, self.M_, self.T_)                # hat_U = C . U . C^T          (solver.py:159)
+        self._gemm(self.T_, self.CT, self.H_)
+        self._ck(lib.chs_big_phys(h, None, self._m(self.A_), self.ld, float(self._mean), None, None, 0, 1), "chs_big_phys")
+        self._ck(lib.chs_big_sums(h), "chs_big_sums")
+        cols = None
+        if self._ps.adaptive_time:
+            if self._want_cols(self._cs, False):
+                self._colsum()
+            elif self._cols is None:
+                self._cols = self.be.empty((self.N,))
+                self._cols_scr = self.be.empty((16 * self.N,))
+            cols = be.ptr(self._cols)
+        self._ck(lib.chs_slab_control_dyn(h, 0, 0, None, cols), "chs_slab_control_dyn")
+
+    def _step(self, last, noise=None, noise_mean=None):
+        lib, h, be = self.lib, self._h, self.be
+        self._gemm(self.A_, self.CT, self.T_)                # hat_mu = C . mu . C^T        (solver.py:201)
+        self._gemm(self.CM, self.T_, self.M_)
+        self._ck(lib.chs_big_update(h, self._m(self.H_), self._m(self.M_), self.ld), "chs_big_update")
+        self._gemm(self.H_, self.CM, self.T_)                # U = C^T . hat_U . C          (solver.py:208)
+        self._gemm(self.CT, self.T_, self.M_)
+        self._ck(lib.chs_big_phys(h, self._m(self.M_), self._m(self.A_), self.ld, float(self._mean), noise, noise_mean,
+                                  1, 0), "chs_big_phys")
+        self._ck(lib.chs_slab_grad(h, be.ptr(self.U), be.ptr(self.U)), "chs_slab_grad")     # np.gradient energy (one rank: no halo)
+        if self._want_cols(self._cs + 1, last):
+            self._colsum()
+        cols = be.ptr(self._cols) if (self._ps.adaptive_time and self._cols is not None) else None
+        self._ck(lib.chs_big_sums(h), "chs_big_sums")
+        self._ck(lib.chs_slab_control_dyn(h, int(bool(last)), 1, None, cols), "chs_slab_control_dyn")
+        self._cs += 1

@@ -293,9 +293,15 @@ class Solver:
         be = _backend if _backend is not None else _CudaBackend()
         if _world is None and not _force_slab and be.lib.chs_supports_n(N):
             self._stepper = BatchStepper(N, [ps], backend=be)
-        else:
+        elif be.lib.chs_slab_supports_n(N):
             from .slab import SlabEngine
             self._stepper = SlabEngine(N, ps, backend=be, world=_world, _selfpeer=_selfpeer)
+        elif _world is None and be.lib.chs_big_supports_n(N):
+            from .slab import BigEngine              # any other N up to 2048: the transforms as tensor-core GEMMs
+            self._stepper = BigEngine(N, ps, backend=be)
+        else:
+            raise ValueError(f"N={N}: supported are powers of two 32..16384 (FFT kernels; 64..16384 over several GPUs) "
+                             f"and any N from 8 to 2048 on one GPU (GEMM kernels)")
 
     def _draw_sobol(self, n):
         self._sobol_drawn += n

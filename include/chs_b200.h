@@ -203,6 +203,17 @@ int chs_slab_control_gathered(chs_slab*, int32_t last, int32_t post, const doubl
  *   chs_slab_grad         np.gradient stencil energy of the stored jittered field (neighbour boundary rows given)
  *   chs_slab_pcg64_fill / chs_slab_row_means   numpy PCG64 draws / row means on the slab handle's stream */
 int chs_slab_colsum(chs_slab*, double* colsum, double* scratch);
+/* Arbitrary-N path (the reference accepts any N, cli_parser.py:27): for sizes neither a power of two nor <= 104,
+ * chs_slab_create builds a one-rank handle whose transforms are FP64 tensor-core GEMMs C.X.C^T / C^T.Y.C
+ * (csrc/chs_big.cuh); chsimpy_b200/slab.py (BigEngine) sequences the stage calls.  Operands are n8 x n8 matrices
+ * (N rounded up to a multiple of 8, zero padded), row-major with pitch ld. */
+int32_t chs_big_supports_n(int32_t N);
+int chs_big_gemm(chs_slab*, const double* A, const double* B, double* D, int32_t n8, int32_t ld);
+int chs_big_update(chs_slab*, double* H, const double* Mh, int32_t ld);                 /* solver.py:201-206 */
+int chs_big_copy(chs_slab*, const double* src, int32_t sld, double* dst, int32_t dld, int32_t respect_halt);
+int chs_big_phys(chs_slab*, const double* Up, double* A, int32_t ld, double mean_u, const double* noise,
+                 const double* noise_mean, int32_t diag, int32_t from_U);               /* solver.py:166-175, 210-228 */
+int chs_big_sums(chs_slab*);
 int chs_slab_control_dyn(chs_slab*, int32_t last, int32_t post, const double* allvec, const double* colsum);
 int chs_slab_step_x(chs_slab*, const double* src, double* dst, int32_t rows, int32_t row_base, double mean_u,
                     const double* noise, const double* noise_mean);

@@ -326,3 +326,30 @@ def test_device_lcg_is_the_reference_generator(be):
     assert np.allclose(got, known, rtol=0, atol=1e-15)
     assert np.array_equal(got, mport.matlab_lcg_sample(5, 4, 2023))
     assert np.array_equal(lcg_sample(be, 64, 64, 2023), mport.matlab_lcg_sample(64, 64, 2023))
+
+
+@pytest.mark.parametrize("kw,steps", [(dict(), 12), (dict(jitter=0.004), 8)])
+def test_arbitrary_n_path_vs_oracle(be, kw, steps):
+    """N = 120 (neither a power of two nor <= 104): BigEngine -- the transforms as tiled GEMMs (scalar dot products in
+    the host build), np.gradient stencil energy, the slab path's reduction / control kernels -- against the oracle,
+    with a re-entry."""
+    import ch_oracle as orc
+    from chsimpy_b200.slab import BigEngine
+    assert be.lib.chs_supports_n(120) == 0 and be.lib.chs_slab_supports_n(120) == 0 and be.lib.chs_big_supports_n(120) == 1
+    p = ch.Parameters()
+    p.N, p.no_gui, p.full_sim, p.kappa_tilde, p.seed, p.ntmax = 120, True, True, 2.7e-4, 5, steps
+    for k, v in kw.items():
+        setattr(p, k, v)
+    s = ch.Solver(p, _backend=be)
+    assert isinstance(s._stepper, BigEngine)
+    s.prepare()
+    s.solve_or_resume(steps - 4)
+    sol = s.solve_or_resume(4)
+    o = orc.run_default(N=120, nsteps=steps - 4, seed=5, kappa_tilde=2.7e-4, full_sim=True, **kw)
+    o.run(4)
+    assert sol.computed_steps == o.computed_steps == steps
+    rows, ref = sol.timedata.data(), o.rows
+    rel = np.abs(rows - ref) / np.maximum(np.abs(ref), 1e-300)
+    rel[ref == 0] = np.abs(rows[ref == 0])
+    assert rel.max() < 1e-9, rel.max(axis=0)
+    assert np.abs(sol.U - o.U).max() < 1e-11

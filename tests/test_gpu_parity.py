@@ -401,6 +401,23 @@ def test_experiment_main_end_to_end(tmp_path, monkeypatch):
     assert "cv" in agg.columns and "mean" in agg.columns
     assert os.path.exists("exp-run3.solution.yaml") and os.path.exists("exp-run3.solution.E2.csv")
     assert os.path.exists("exp-metadata.csv")
+    # values, not only shapes: every member against its own single-Solver run and the oracle's run of the same member
+    import ch_oracle as orc
+    import chsimpy_b200 as ch
+    rows = df.sort_values("id").reset_index(drop=True)
+    for rid in (0, 3, 5):
+        f0, f1 = float(want[rid, 0]), float(want[rid, 1])
+        r = rows.iloc[rid]
+        assert abs(r["A0"] - ch.utils.A0(923.15) * f0) <= 1e-12 * abs(r["A0"]) and abs(r["A1"] - ch.utils.A1(923.15) * f1) <= 1e-12 * abs(r["A1"])
+        o = orc.run_default(N=64, c0=0.89, fac_A0=f0, fac_A1=f1, nsteps=400)
+        assert int(r["tau0"]) == int(o.tau0) and abs(r["t0"] - o.t0) <= 1e-12 * max(1.0, o.t0), (rid, r["tau0"], o.tau0)
+        assert int(r["tsep"]) == int(np.argmax(o.rows[:, 2]))
+        ca, cb = ch.utils.get_miscibility_gap(ch.Parameters().R, 923.15, ch.Parameters().B, r["A0"], r["A1"])
+        assert abs(r["ca"] - float(ca)) < 1e-12 and abs(r["cb"] - float(cb)) < 1e-12
+        e2 = ch.utils.csv_import_matrix(f"exp-run{rid}.solution.E2.csv")
+        ref = o.rows[:, 2]
+        assert e2.shape == ref.shape and np.abs(e2 - ref).max() <= 1e-9 * np.abs(ref).max()
+    assert abs(agg.loc["tau0", "mean"] - rows["tau0"].mean()) < 1e-9 and abs(agg.loc["ca", "cv"] - rows["ca"].std() / rows["ca"].mean()) < 1e-12
 
 
 def test_uinit_file_and_nan_field(tmp_path):
@@ -492,3 +509,28 @@ def test_device_lcg_n512_bitexact():
     assert np.array_equal(lcg_sample(be, 512, 512, 2023), mport.matlab_lcg_sample(512, 512, 2023))
     known0 = [0.5475444293336684, 0.29257702841077793, 0.3117376865408093, 0.9844947126621821]
     assert np.allclose(lcg_sample(be, 5, 4, 2023)[0], known0, rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("N,kw,steps", [(200, dict(), 120), (300, dict(jitter=0.003, adaptive_time=True, delt_max=3.4e-10), 524),
+                                        (768, dict(), 12), (105, dict(time_max=0.4), 60)])
+def test_arbitrary_n_path_vs_oracle(N, kw, steps):
+    """Any N (reference cli_parser.py:27): sizes the FFT kernels do not take run as FP64 tensor-core GEMMs
+    (chs_big.cuh, BigEngine), incl. jitter / adaptive dt / time limit, against the oracle with a re-entry."""
+    import ch_oracle as orc
+    import chsimpy_b200 as ch
+    from chsimpy_b200.slab import BigEngine
+    p = ch.Parameters()
+    p.N, p.no_gui, p.full_sim, p.kappa_tilde, p.seed, p.ntmax = N, True, True, 2.7e-4, 5, steps
+    for k, v in kw.items():
+        setattr(p, k, v)
+    s = ch.Solver(p)
+    assert isinstance(s._stepper, BigEngine)
+    s.prepare()
+    s.solve_or_resume(steps - 6)
+    sol = s.solve_or_resume(6)
+    o = orc.run_default(N=N, nsteps=steps - 6, seed=5, kappa_tilde=2.7e-4, full_sim=True, **kw)
+    o.run(6)
+    assert sol.computed_steps == o.computed_steps and sol.stop_reason == o.stop_reason
+    check_rows(sol.timedata.data(), o.rows, N)
+    assert np.abs(sol.U - o.U).max() <= U_TOL
+    assert abs(s.delt - o.delt) <= 1e-12 * o.delt
