@@ -1193,7 +1193,8 @@ static int big_blocks(const chs_slab* s) {
 extern "C" int chs_big_gemm(chs_slab* s, const double* A, const double* B, double* D, int32_t n8, int32_t ld) {
     if (!s || !A || !B || !D || n8 < 8 || n8 % 8 || ld < n8) return fail("chs_big_gemm: bad argument");
     const int nb = (n8 + BIG_TILE - 1) / BIG_TILE;
-    CHS_LAUNCH(k_big_gemm, dim3(nb, nb), dim3(128), 2 * BIG_TILE * (BIG_KS + 1) * sizeof(double), s->stream, A, B, D, (int)n8, (int)ld);
+    CHS_LAUNCH(k_big_gemm, dim3(nb, nb), dim3(256), (BIG_TILE * (BIG_KS + 1) + BIG_KS * (BIG_TILE + 1)) * sizeof(double), s->stream,
+               A, B, D, (int)n8, (int)ld);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());
     return 0;

@@ -16,57 +16,76 @@
 
 namespace chs {
 
-// D[M x Ncols] = A[M x K] . B[K x Ncols], all row-major with leading dimension ld (zero-padded to multiples of 8).
-// CTA = 128 threads = 4 warps, 32 x 32 output tile: warp w owns rows 8w .. 8w+7 of the tile, 4 DMMA column blocks.
-// The K loop is staged through shared memory in slabs of 32.
-constexpr int BIG_TILE = 32, BIG_KS = 32;
-CHS_KERNEL void __launch_bounds__(128) k_big_gemm(const double* A, const double* B, double* D, int n8, int ld) {
+// D = A . B for n8 x n8 row-major matrices with pitch ld (zero padded to multiples of 8).  CTA = 256 threads = 8
+// warps, 64 x 64 output tile: warp w owns rows 16 (w/2) .. +15 and columns 32 (w%2) .. +31 = 2 x 4 DMMA blocks
+// (8 accumulator pairs).  The K loop runs in slabs of 16 through shared memory; the next slab is fetched into
+// registers while the current one is multiplied (software double buffering).
+constexpr int BIG_TILE = 64, BIG_KS = 16;
+CHS_KERNEL void __launch_bounds__(256) k_big_gemm(const double* A, const double* B, double* D, int n8, int ld) {
     CHS_SMEM_DECL
-    double* sA = reinterpret_cast<double*>(CHS_SMEM_PTR);            // [32][33]
-    double* sB = sA + BIG_TILE * (BIG_KS + 1);                       // [32][33]
+    double* sA = reinterpret_cast<double*>(CHS_SMEM_PTR);            // [64][BIG_KS + 1]
+    double* sB = sA + BIG_TILE * (BIG_KS + 1);                       // [BIG_KS][64 + 1]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r0 = blockIdx.y * BIG_TILE, c0 = blockIdx.x * BIG_TILE;
-    double d[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-#ifdef CHS_EMU
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};                        // thread -> row warp*8 + lane/4, cols 8j + 2(lane%4) + e
-#endif
+    const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;
+    double d[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[i][j][0] = d[i][j][1] = 0.0;
+    // staging: thread -> 4 elements of the A slab (64 x 16) and 4 of the B slab (16 x 64)
+    double pa[4], pb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = tid + e * 256;
+            const int ar = i / BIG_KS, ac = i % BIG_KS, br = i / BIG_TILE, bc = i % BIG_TILE;
+            pa[e] = (r0 + ar < n8 && k0 + ac < n8) ? A[(size_t)(r0 + ar) * ld + k0 + ac] : 0.0;
+            pb[e] = (k0 + br < n8 && c0 + bc < n8) ? B[(size_t)(k0 + br) * ld + c0 + bc] : 0.0;
+        }
+    };
+    fetch(0);
     for (int k0 = 0; k0 < n8; k0 += BIG_KS) {
-        for (int i = tid; i < BIG_TILE * BIG_KS; i += 128) {
-            const int r = i / BIG_KS, c = i % BIG_KS;
-            sA[r * (BIG_KS + 1) + c] = (r0 + r < n8 && k0 + c < n8) ? A[(size_t)(r0 + r) * ld + k0 + c] : 0.0;
-            sB[r * (BIG_TILE + 1) + c] = (k0 + r < n8 && c0 + c < n8) ? B[(size_t)(k0 + r) * ld + c0 + c] : 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = tid + e * 256;
+            sA[(i / BIG_KS) * (BIG_KS + 1) + (i % BIG_KS)] = pa[e];
+            sB[(i / BIG_TILE) * (BIG_TILE + 1) + (i % BIG_TILE)] = pb[e];
         }
         __syncthreads();
+        if (k0 + BIG_KS < n8) fetch(k0 + BIG_KS);                    // in flight during the multiplication below
 #ifdef CHS_EMU
-        const int r = warp * 8 + lane / 4;
-        for (int j = 0; j < 4; ++j)
-            for (int e = 0; e < 2; ++e) {
-                const int c = 8 * j + 2 * (lane % 4) + e;
-                double s = 0;
-                for (int k = 0; k < BIG_KS; ++k) s += sA[r * (BIG_KS + 1) + k] * sB[k * (BIG_TILE + 1) + c];
-                acc[2 * j + e] += s;
-            }
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 4; ++j)
+                for (int e = 0; e < 2; ++e) {
+                    const int r = wr + 8 * i + lane / 4, c = wc + 8 * j + 2 * (lane % 4) + e;
+                    double acc = 0;
+                    for (int k = 0; k < BIG_KS; ++k) acc += sA[r * (BIG_KS + 1) + k] * sB[k * (BIG_TILE + 1) + c];
+                    d[i][j][e] += acc;
+                }
 #else
-        const double* ap = sA + (warp * 8 + lane / 4) * (BIG_KS + 1) + (lane % 4);
-        const double* bp = sB + (lane % 4) * (BIG_TILE + 1) + lane / 4;
 #pragma unroll
         for (int kk = 0; kk < BIG_KS; kk += 4) {
-            const double a = ap[kk];
+            double a[2], bb[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(d[j][0], d[j][1], a, bp[kk * (BIG_TILE + 1) + 8 * j]);
+            for (int i = 0; i < 2; ++i) a[i] = sA[(wr + 8 * i + lane / 4) * (BIG_KS + 1) + kk + (lane % 4)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb[j] = sB[(kk + (lane % 4)) * (BIG_TILE + 1) + wc + 8 * j + lane / 4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(d[i][j][0], d[i][j][1], a[i], bb[j]);
         }
 #endif
         __syncthreads();
     }
-    const int r = r0 + warp * 8 + lane / 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c0 + 8 * j + 2 * (lane % 4);
-#ifdef CHS_EMU
-        d[j][0] = acc[2 * j]; d[j][1] = acc[2 * j + 1];
-#endif
-        if (r < n8 && c < n8) { D[(size_t)r * ld + c] = d[j][0]; D[(size_t)r * ld + c + 1] = d[j][1]; }
-    }
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + wr + 8 * i + lane / 4, c = c0 + wc + 8 * j + 2 * (lane % 4);
+            if (r < n8 && c < n8) { D[(size_t)r * ld + c] = d[i][j][0]; D[(size_t)r * ld + c + 1] = d[i][j][1]; }
+        }
 }
 
 // H = (H + Seig*Mh)/CHeig, natural order (solver.py:201-206; multipliers from the 1-D table as everywhere)
