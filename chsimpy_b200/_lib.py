@@ -9,7 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libchs_b200.so")
-SOURCES = ("chs_api.cu", "chs_kernels.cuh", "chs_slab.cuh", "chs_big.cuh", "chs_gemm.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
+SOURCES = ("chs_api.cu", "chs_ll.cu", "chs_kernels.cuh", "chs_slab.cuh", "chs_big.cuh", "chs_gemm.cuh", "dct_core.cuh", "fastlog.cuh", "chs_rt.h")
+UNITS = ("chs_api.cu", "chs_ll.cu")          # translation units of the library
 # (no -split-compile: it builds 2x faster but the kernels measured 6 % slower on B200)
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -94,6 +95,8 @@ PROTOTYPES = {
     "chs_slab_sums": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "chs_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "chs_get_timing": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "chs_set_mix": (C.c_int, [C.c_void_p, C.c_int32]),
+    "chs_get_timing_mix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -120,7 +123,7 @@ def build(force=False, verbose=False):
             nvcc = os.environ.get("NVCC", "nvcc")
             fd, tmp = tempfile.mkstemp(prefix=".libchs_b200.", suffix=".so.tmp", dir=HERE)
             os.close(fd)
-            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "chs_api.cu")]
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, u) for u in UNITS]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             r = subprocess.run(cmd, capture_output=True, text=True)

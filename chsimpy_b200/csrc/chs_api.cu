@@ -52,6 +52,11 @@ struct chs_solver {
     int N8, LD;
     double *Cm, *Ct;
     int cap_col[3], cap_row[4];     // resident CTAs per kernel mode (persistent grids)
+    int cap_mix;
+    unsigned long long* trace;      // -DCHS_TRACE=1 builds only (chs_debug_trace)
+    int ll_max;                     // low-latency kernels when at most this many simulations run (0 = never)
+    int sub_sims;                   // L2 blocking: simulations per sub-batch of chs_steps (0 = off)
+    int mix_mode;                   // -1: mixed launches when enough simulations run (default), 0: never, 1: whenever possible
     // optional per-kernel timing (bench.py)
     bool timing;
     std::vector<cudaEvent_t> events;       // 4 per iteration: before col, after col, after row, after diag
@@ -59,6 +64,13 @@ struct chs_solver {
     bool ev_diag;
     double t_ms[3];
     long long t_iters;
+    // mixed launches (k_mix): events e0 L0 e1 L1 ... of every chs_steps call, and which launches were solo halves
+    std::vector<cudaEvent_t> mix_events;
+    size_t mix_used;
+    std::vector<std::pair<size_t, size_t>> mix_runs;      // (first event, launches) per call
+    double mix_ms[2];                                      // [0] mixed launches, [1] the solo half launches at both ends
+    long long mix_n[2];
+    long long mix_iters;
 };
 
 static cudaEvent_t next_event(chs_solver* s) {
@@ -70,16 +82,35 @@ static cudaEvent_t next_event(chs_solver* s) {
     return s->events[s->ev_used++];
 }
 
+static cudaEvent_t next_mix_event(chs_solver* s) {
+    if (s->mix_used == s->mix_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s->mix_events.push_back(e);
+    }
+    return s->mix_events[s->mix_used++];
+}
+
 static int drain_events(chs_solver* s) {
-    if (s->ev_used == 0) return 0;
+    if (s->ev_used == 0 && s->mix_used == 0) return 0;
     CHS_CUDA(cudaStreamSynchronize(s->stream));
+    for (const auto& run : s->mix_runs) {
+        for (size_t j = 0; j < run.second; ++j) {
+            float a = 0;
+            cudaEventElapsedTime(&a, s->mix_events[run.first + j], s->mix_events[run.first + j + 1]);
+            const int solo = (j == 0 || j + 1 == run.second) ? 1 : 0;
+            s->mix_ms[solo] += a;
+            s->mix_n[solo] += 1;
+        }
+    }
+    s->mix_runs.clear();
+    s->mix_used = 0;
     for (size_t i = 0; i + 4 <= s->ev_used; i += 4) {
         float a = 0, b = 0, c = 0;
         cudaEventElapsedTime(&a, s->events[i], s->events[i + 1]);
         cudaEventElapsedTime(&b, s->events[i + 1], s->events[i + 2]);
         cudaEventElapsedTime(&c, s->events[i + 2], s->events[i + 3]);
         s->t_ms[0] += a; s->t_ms[1] += b; s->t_ms[2] += c;
-        s->t_iters += 1;
     }
     s->ev_used = 0;
     return 0;
@@ -256,6 +287,7 @@ static int set_attrs(chs_solver* s) {
     CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_FWD_MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_mix<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_PREPARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_JITTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 #ifndef CHS_EMU
@@ -273,6 +305,7 @@ static int set_attrs(chs_solver* s) {
     s->cap_row[ROW_FWD_MU] = resident_ctas(k_row<N, ROW_FWD_MU>, nt, b, ns);
     s->cap_row[ROW_STEP] = resident_ctas(k_row<N, ROW_STEP>, nt, b, ns);
     s->cap_row[ROW_INV] = resident_ctas(k_row<N, ROW_INV>, nt, b, ns);
+    s->cap_mix = resident_ctas(k_mix<N>, nt, b, ns);
     return 0;
 }
 
@@ -290,6 +323,27 @@ static dim3 pgrid(int cap, int num_sms, int ntiles, int nsims) {
 #endif
 }
 
+// fewest running simulations for which a step runs as mixed launches (k_mix): below it a half batch no longer
+// fills the GPU for several waves and the two half-size launches at the ends of a call cost more than mixing gains
+#ifndef CHS_MIX_MIN_SIMS
+#define CHS_MIX_MIN_SIMS 32
+#endif
+
+// L2 blocking of chs_steps: simulations per sub-batch (0 = off), see do_steps
+static int default_sub_sims(int N) {
+    (void)N;
+    return 0;
+}
+
+// low-latency build of the step kernels (chs_ll.cu: 8 points per thread, 256 threads per tile)
+extern "C" int chs_ll_init(int N);
+extern "C" int chs_ll_launch(int N, int which, const void* kargs, int nsims, int pdl, void* stream);
+extern "C" int chs_ll_kargs_size(void);
+// most running simulations for which chs_steps uses it (N = 512): measured on B200 (profiles/r2c_lowlat.md)
+#ifndef CHS_LL_MAX_SIMS
+#define CHS_LL_MAX_SIMS 0
+#endif
+
 static KArgs base_args(chs_solver* s) {
     KArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -300,6 +354,7 @@ static KArgs base_args(chs_solver* s) {
     a.tw = s->tw; a.om = s->om; a.lam = s->lam; a.logtab = s->logtab;
     a.gsin = s->gsin; a.kof = s->kof; a.lamg = s->lamg;
     a.mean_host = s->mean;
+    a.trace = s->trace;
     return a;
 }
 
@@ -339,6 +394,11 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     s->launches = 0;
     s->timing = false; s->ev_used = 0; s->ev_diag = false; s->t_iters = 0;
     s->t_ms[0] = s->t_ms[1] = s->t_ms[2] = 0;
+    s->trace = nullptr;
+    s->ll_max = [] { const char* e = getenv("CHS_LL_MAX"); return e ? atoi(e) : CHS_LL_MAX_SIMS; }();
+    s->sub_sims = [N] { const char* e = getenv("CHS_SUB"); return e ? atoi(e) : default_sub_sims(N); }();
+    s->mix_mode = [] { const char* e = getenv("CHS_MIX"); return e ? atoi(e) : 0; }();
+    s->mix_used = 0; s->mix_ms[0] = s->mix_ms[1] = 0; s->mix_n[0] = s->mix_n[1] = 0; s->mix_iters = 0;
     // twiddle tables in extended precision, rounded once
     const int M = N / 2;
     std::vector<double2> tw(M), om(N + N / 4);
@@ -426,6 +486,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
 extern "C" void chs_destroy(chs_solver* s) {
     if (!s) return;
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->mix_events) cudaEventDestroy(e);
     delete s;
 }
 
@@ -443,6 +504,32 @@ extern "C" int chs_get_timing(chs_solver* s, double* ms3, int64_t* n_iters) {
     if (n_iters) *n_iters = s->t_iters;
     s->t_ms[0] = s->t_ms[1] = s->t_ms[2] = 0;
     s->t_iters = 0;
+    return 0;
+}
+
+// latency analysis (tools/trace_single.py, library built with -DCHS_TRACE=1): device buffer of >= 32 uint64 that
+// tile 0 of every step launch fills with %globaltimer phase stamps; not part of the public header
+extern "C" int chs_debug_trace(chs_solver* s, unsigned long long* dev_buf) {
+    if (!s) return fail("chs_debug_trace: null handle");
+    s->trace = dev_buf;
+    return 0;
+}
+
+extern "C" int chs_set_mix(chs_solver* s, int32_t mode) {
+    if (!s || mode < -1 || mode > 1) return fail("chs_set_mix: bad argument");
+    s->mix_mode = mode;
+    return 0;
+}
+
+extern "C" int chs_get_timing_mix(chs_solver* s, double* ms2, int64_t* n2, int64_t* n_iters) {
+    if (!s) return fail("chs_get_timing_mix: null handle");
+    if (drain_events(s)) return -1;
+    if (ms2) { ms2[0] = s->mix_ms[0]; ms2[1] = s->mix_ms[1]; }
+    if (n2) { n2[0] = s->mix_n[0]; n2[1] = s->mix_n[1]; }
+    if (n_iters) *n_iters = s->mix_iters;
+    s->mix_ms[0] = s->mix_ms[1] = 0;
+    s->mix_n[0] = s->mix_n[1] = 0;
+    s->mix_iters = 0;
     return 0;
 }
 
@@ -582,37 +669,108 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
     const dim3 block(G::NT);
     // programmatic dependent launch of the two step kernels (not while per-kernel events are recorded)
     static const bool pdl_env = [] { const char* e = getenv("CHS_PDL"); return !e || atoi(e) != 0; }();
-    const bool pdl = pdl_env && !s->timing;
+    // Only when the launch (nearly) fills the CTA slots: the dependents of a programmatic launch become resident while
+    // their predecessor still runs, and with a partly filled GPU they pile up on the SMs the predecessor left free --
+    // measured on B200, N=512: 2..4 simulations 47 us/step with, 29..36 us without (profiles/r2c_small_batches.md)
+    static const int pdl_min_pct = [] { const char* e = getenv("CHS_PDL_MIN_PCT"); return e ? atoi(e) : 80; }();
+    const bool pdl = pdl_env && !s->timing && ((long long)G::NTILES * s->n_running * 100 >= (long long)pdl_min_pct * s->cap_row[ROW_STEP] ||
+                                                2LL * G::NTILES * s->n_running <= s->num_sms);
     if (s->n_running == s->batch) a.sim_index = nullptr;
     // without noise the step kernels keep the field in spectral form only (U is materialised by chs_end);
     // with noise k_row stores the jittered U every step
     for (int i = 0; i < s->n_running; ++i) s->hstale[s->hindex[i]] = noise ? 0 : 1;
-    const dim3 grid(G::NTILES, s->n_running);
-    const dim3 gcol = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, a.nsims), grow = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, a.nsims);
+    // ---- mixed launches: the running simulations are split into halves A and B, B half a step behind A:
+    //   col(A,0) | row(A,0)+col(B,0) | col(A,1)+row(B,0) | ... | row(A,K-1)+col(B,K-1) | row(B,K-1)
+    // = 2K-1 k_mix launches with column and row CTAs resident together + one half-size launch at each end;
+    // the call still ends with every simulation exactly K steps further.
+    const bool mix = !noise && s->mix_mode != 0 && s->n_running >= (s->mix_mode > 0 ? 2 : CHS_MIX_MIN_SIMS) && n_iters >= 2;
+    if (mix) {
+        const int nA = (s->n_running + 1) / 2, nB = s->n_running - nA;
+        KArgs A = a, B = a;
+        A.sim_index = s->index; A.nsims = nA;                 // (the identity list is resident until the first compaction)
+        B.sim_index = s->index + nA; B.nsims = nB;
+        static const int period_env = [] { const char* e = getenv("CHS_MIX_PERIOD"); return e ? atoi(e) : 0; }();   // tuning experiment
+        const int period = period_env > 0 ? period_env : ((s->num_sms > 1) ? (s->num_sms & ~1) : 2);
+        const dim3 gA = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, nA), gB = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, nB);
+        const dim3 gmix = pgrid(s->cap_mix, s->num_sms, 2 * G::NTILES, nA);
+        const size_t ev0 = s->mix_used;
+        if (s->timing) cudaEventRecord(next_mix_event(s), s->stream);
+        A.last = 0;
+        if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP>), gA, block, G::SMEM_BYTES, s->stream, A);
+        else CHS_LAUNCH((k_col<N, COL_STEP>), gA, block, G::SMEM_BYTES, s->stream, A);
+        if (s->timing) cudaEventRecord(next_mix_event(s), s->stream);
+        for (long long it = 0; it < n_iters; ++it) {
+            const int lastf = (last && it == n_iters - 1) ? 1 : 0;
+            // row(A, it) + col(B, it)
+            A.last = lastf; B.last = 0;
+            if (pdl) CHS_LAUNCH_PDL((k_mix<N>), gmix, block, G::SMEM_BYTES, s->stream, B, A, period);
+            else CHS_LAUNCH((k_mix<N>), gmix, block, G::SMEM_BYTES, s->stream, B, A, period);
+            if (s->timing) cudaEventRecord(next_mix_event(s), s->stream);
+            if (it + 1 < n_iters) {                          // col(A, it+1) + row(B, it)
+                A.last = 0; B.last = 0;
+                if (pdl) CHS_LAUNCH_PDL((k_mix<N>), gmix, block, G::SMEM_BYTES, s->stream, A, B, period);
+                else CHS_LAUNCH((k_mix<N>), gmix, block, G::SMEM_BYTES, s->stream, A, B, period);
+                if (s->timing) cudaEventRecord(next_mix_event(s), s->stream);
+            }
+        }
+        B.last = last ? 1 : 0;
+        if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP>), gB, block, G::SMEM_BYTES, s->stream, B);
+        else CHS_LAUNCH((k_row<N, ROW_STEP>), gB, block, G::SMEM_BYTES, s->stream, B);
+        if (s->timing) {
+            cudaEventRecord(next_mix_event(s), s->stream);
+            s->mix_runs.push_back({ev0, (size_t)(2 * n_iters + 1)});
+            s->mix_iters += n_iters;
+            if (s->mix_used > 60000 && drain_events(s)) return -1;
+        }
+        s->launches += 2 * n_iters + 1;
+        CHS_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // ---- L2 blocking: the running simulations are stepped in sub-batches of `sub` simulations, each through ALL
+    // n_iters iterations before the next one starts: hat_U + T of a sub-batch (2 * 8 N^2 bytes per simulation)
+    // stay resident in the 126 MB L2 from one iteration to the next, so only the first and the last iteration of
+    // a call move the state through HBM.  Simulations are independent, so the order does not change any result.
+    // few simulations (fewer tiles than SMs): the low-latency build of the two kernels (chs_ll.cu)
+    const bool ll = s->ll_max > 0 && s->n_running <= s->ll_max && N == 512 && sizeof(KArgs) == (size_t)chs_ll_kargs_size() &&
+                    chs_ll_init(N) == 0;
+    const int sub_cfg = s->sub_sims;
+    const int sub = (sub_cfg > 0 && sub_cfg < s->n_running && n_iters >= 2) ? sub_cfg : s->n_running;
+    for (int sb0 = 0; sb0 < s->n_running; sb0 += sub) {
+    KArgs b = a;
+    if (sub < s->n_running) {
+        b.sim_index = s->index + sb0;             // (the identity list is resident until the first compaction)
+        b.nsims = (s->n_running - sb0 < sub) ? s->n_running - sb0 : sub;
+    }
+    const dim3 gcol_b = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, b.nsims), grow_b = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, b.nsims);
+    const dim3 grid_b(G::NTILES, b.nsims);
     for (long long it = 0; it < n_iters; ++it) {
-        a.last = (last && it == n_iters - 1) ? 1 : 0;
+        b.last = (last && it == n_iters - 1) ? 1 : 0;
         if (noise) {
-            a.noise = noise + (size_t)it * N * N;
-            a.noise_mean = noise_mean + it;
+            b.noise = noise + (size_t)it * N * N;
+            b.noise_mean = noise_mean + it;
         }
         if (s->timing) {
             if (s->ev_used + 4 > 65536 && drain_events(s)) return -1;
             cudaEventRecord(next_event(s), s->stream);
         }
-        if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP>), gcol, block, G::SMEM_BYTES, s->stream, a);
-        else CHS_LAUNCH((k_col<N, COL_STEP>), gcol, block, G::SMEM_BYTES, s->stream, a);
+        if (ll) { if (chs_ll_launch(N, 0, &b, b.nsims, pdl ? 1 : 0, (void*)s->stream)) return fail("chs_steps: low-latency launch failed"); }
+        else if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP>), gcol_b, block, G::SMEM_BYTES, s->stream, b);
+        else CHS_LAUNCH((k_col<N, COL_STEP>), gcol_b, block, G::SMEM_BYTES, s->stream, b);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
-        if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP>), grow, block, G::SMEM_BYTES, s->stream, a);
-        else CHS_LAUNCH((k_row<N, ROW_STEP>), grow, block, G::SMEM_BYTES, s->stream, a);
+        if (ll) { if (chs_ll_launch(N, 1, &b, b.nsims, pdl ? 1 : 0, (void*)s->stream)) return fail("chs_steps: low-latency launch failed"); }
+        else if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP>), grow_b, block, G::SMEM_BYTES, s->stream, b);
+        else CHS_LAUNCH((k_row<N, ROW_STEP>), grow_b, block, G::SMEM_BYTES, s->stream, b);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
         s->launches += 2;
         if (noise) {
-            if (pdl) CHS_LAUNCH_PDL((k_diag<N, DIAG_JITTER>), grid, block, G::SMEM_BYTES, s->stream, a);
-            else CHS_LAUNCH((k_diag<N, DIAG_JITTER>), grid, block, G::SMEM_BYTES, s->stream, a);
+            if (pdl) CHS_LAUNCH_PDL((k_diag<N, DIAG_JITTER>), grid_b, block, G::SMEM_BYTES, s->stream, b);
+            else CHS_LAUNCH((k_diag<N, DIAG_JITTER>), grid_b, block, G::SMEM_BYTES, s->stream, b);
             s->launches += 1;
         }
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
     }
+    }
+    if (s->timing) s->t_iters += n_iters;
     CHS_CUDA(cudaGetLastError());
     return 0;
 }

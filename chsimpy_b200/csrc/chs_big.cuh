@@ -14,7 +14,7 @@
 #pragma once
 #include "chs_slab.cuh"
 
-namespace chs {
+namespace CHS_NS {
 
 // D = A . B for n8 x n8 row-major matrices with pitch ld (zero padded to multiples of 8).  CTA = 256 threads = 8
 // warps, 64 x 64 output tile: warp w owns rows 16 (w/2) .. +15 and columns 32 (w%2) .. +31 = 2 x 4 DMMA blocks
@@ -163,4 +163,4 @@ CHS_KERNEL void k_big_phys(const double* Up, double* U, double* A, int N, int ld
     if (threadIdx.x == 5) { part[R_GE * gridDim.x + blockIdx.x] = 0; part[R_EDGE * gridDim.x + blockIdx.x] = 0; }
 }
 
-}  // namespace chs
+}  // namespace CHS_NS

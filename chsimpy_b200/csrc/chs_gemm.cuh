@@ -15,7 +15,7 @@
 #pragma once
 #include "chs_kernels.cuh"
 
-namespace chs {
+namespace CHS_NS {
 
 constexpr int GEMM_NT = 256;          // 8 warps
 constexpr int GEMM_MAX_N = 104;       // two N8 x LD fp64 matrices must fit in 227 KB of shared memory
@@ -324,4 +324,4 @@ CHS_KERNEL void __launch_bounds__(GEMM_NT, 1) k_gemm(GemmArgs a) {
     for (int i = tid; i < N * N; i += GEMM_NT) Ug[i] = X[(i / N) * LD + (i % N)];
 }
 
-}  // namespace chs
+}  // namespace CHS_NS

@@ -36,7 +36,7 @@
 #include "fastlog.cuh"
 #include "../../include/chs_b200.h"
 
-namespace chs {
+namespace CHS_NS {
 
 // per-CTA partial sums, reduced in fixed order by the last CTA (deterministic)
 //   P_GE : raw gradient sum (spectral main part, or the direct stencil sum of k_diag)
@@ -109,7 +109,22 @@ struct KArgs {
     int natural;                 // stand-alone transforms: natural column order on the far side
     int last;                    // no "pre" part after this iteration
     int nsims;                   // simulations in this launch (entries of sim_index)
+    unsigned long long* trace;   // -DCHS_TRACE=1 builds: phase timestamps of tile 0 (tools/trace_single.py), else unused
 };
+
+// phase timestamps of the first tile of a launch (latency analysis of a single simulation, tools/trace_single.py)
+#if defined(CHS_TRACE) && !defined(CHS_EMU)
+#define CHS_TRACE_PT(a, w, id)                                                                        \
+    do {                                                                                              \
+        if ((a).trace && threadIdx.x == 0 && (w) == 0) {                                              \
+            unsigned long long t_;                                                                    \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                     \
+            (a).trace[id] = t_;                                                                       \
+        }                                                                                             \
+    } while (0)
+#else
+#define CHS_TRACE_PT(a, w, id) ((void)0)
+#endif
 
 // one CTA per tile on the GPU (a resident-CTA loop measured slower and costs registers);
 // the host emulation keeps the loop so that few OS-thread blocks cover all tiles
@@ -242,7 +257,7 @@ CHS_DEV double thermo_acc(double u, const ThermoK& k, const double2* __restrict_
 // part/colpart of all CTAs are visible (threadfence + ticket).  rows: this sim's table.
 template <int N>
 CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, double* rows, long long rows_cap,
-                          int last, bool post, double* scratch, int tid, int nthreads) {
+                          int last, bool post, double* scratch, double* aux, int tid, int nthreads) {
     using G = Geo<N>;
     constexpr int NTILES = G::NTILES;
     // the test of solver.py:177-181 is made with the value computed_steps will have at the
@@ -271,6 +286,13 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
         }
         __syncthreads();
     }
+    // The two long scalar chains of the row -- pow (the cube root of the time) and the square root of ||mu||^2 -- only
+    // depend on state the previous iteration left: two other warps evaluate them while the partial sums are on their
+    // way from L2 (aux: two doubles of shared memory outside `scratch`); thread 0 picks them up after the barrier.
+    if (post) {
+        if (tid == nthreads - 1) aux[0] = pow(S->time_passed, 1.0 / 3.0);
+        if (tid == nthreads / 2) aux[1] = sqrt(S->mu2_pending);
+    }
     // the per-tile partial sums of all P_NSLOT slots, added by the whole CTA: every thread takes a strided share
     // (all loads of the CTA are in flight together -- one L2 latency instead of 7*NTILES dependent ones, which
     // was half of a single simulation's step time), then the fixed-order block reduction (deterministic)
@@ -298,9 +320,9 @@ CHS_DEV void step_control(Sim* S, const double* part, const double* colpart, dou
         // P_F holds sum f + RT B sum U (physics()); sum U = N^2 mean(U) is known exactly (Q4)
         const double E = p.Amr * L2sq * (acc[P_F] / N2 - p.RT * p.B * S->mean_u) + E2;
         const double PS = acc[P_ABS] / N2;
-        const double L2 = sqrt(S->mu2_pending) / N2;
+        const double L2 = aux[1] / N2;
         const double SA = acc[P_CNT] / N2;
-        const double domtime = pow(S->time_passed, 1.0 / 3.0);
+        const double domtime = aux[0];
         S->mu2_pending = acc[P_MU2];
         const long long rw = S->rows_written;
         if (rw < rows_cap) {
@@ -411,7 +433,7 @@ CHS_DEV void row_tile_pairs_io(double2* sc, double* __restrict__ gT /* simulatio
     // thread -> (line lam, points p = p0 + j TPL): p & 3 and the line are fixed per thread, and piece_flip(p)
     // is bit FB of j (p0 < TPL <= M/radix(0)): every address is base + compile-time offset
     constexpr int FB = ilog2c((M / Rad<M>::radix(0)) / TPL);
-    static_assert((M / Rad<M>::radix(0)) % TPL == 0 && CNT == 16, "piece_flip must be a bit of j");
+    static_assert((M / Rad<M>::radix(0)) % TPL == 0 && CNT % 8 == 0, "piece_flip must be a bit of j");
     const int lam = tid & 7, pi = lam & 3, h = lam >> 2, p0 = tid >> 3;
     double2* g0 = reinterpret_cast<double2*>(gT) + (size_t)pair_c<N>(r, pi) * 8 + (size_t)(p0 >> 2) * (M * 8) + 2 * (p0 & 3);
     double2* s0 = sc + p0 * 8 + lam;
@@ -787,6 +809,8 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
         }
         if (MODE == COL_STEP) {
             // the hat_U tile is consumed in the middle of the tile's work: pull it into L2 now
+            // (staging it in shared memory with a second bulk copy was measured for a single simulation: the fused
+            // pass stayed at 3.9 us -- it is bound by its dependent FP64 chain, not by the loads)
             const double* hp = a.hatU + off + (size_t)tile * N * LINES;          // contiguous 8*N*LINES bytes
             for (int i = tid * 16; i < N * LINES; i += NT * 16) CHS_PREFETCH_L2(hp + i);
         }
@@ -801,10 +825,13 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
             lamx = a.lam[kx];
             gxs = a.gsin[kx];
         }
+        CHS_TRACE_PT(a, w, 1);
         if (MODE != COL_INV) chs_mbar_wait(bar, phase);
+        CHS_TRACE_PT(a, w, 2);
         if (!halted) {
             // -------- forward column DCT-II up to the last stage
             if (MODE != COL_INV) fft_fwd_range<N, 0, NST - 1, true>(scl, t, s_tw);
+            CHS_TRACE_PT(a, w, 3);
             // -------- fused: last forward stage + post + spectral update + pre + first inverse stage
             ColMid<N, MODE> mid;
             mid.om = a.om; mid.lamg = a.lamg;
@@ -820,6 +847,7 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
             mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
             mid.hat00 = (MODE == COL_FWD && !a.dst && tile == 0 && l == 0) ? &S->k.hat00 : nullptr;
             fused_units<N, MODE != COL_INV, MODE != COL_FWD>(scl, t, mid);
+            CHS_TRACE_PT(a, w, 4);
             if (MODE != COL_FWD) {
                 if (MODE == COL_STEP) {
                     const double v[1] = {mid.ge};
@@ -828,6 +856,7 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
                 line_barrier<N, true>();
                 // -------- remaining inverse stages
                 fft_inv_range<N, 0, NST - 1, true>(scl, t, s_tw);
+                CHS_TRACE_PT(a, w, 5);
                 // -------- partial sums: spectral gradient energy + one-sided y-edge terms
                 if (MODE == COL_STEP && tid == 0) {
                     double v[1];
@@ -850,6 +879,7 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
                         chs_bulk_s2g(reinterpret_cast<char*>(gtile) + o, reinterpret_cast<const char*>(sm) + o, CHUNK);
                     chs_bulk_commit_wait();
                 }
+                CHS_TRACE_PT(a, w, 6);
             }
         }
 }
@@ -863,6 +893,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
     __syncthreads();
     CHS_PDL_TRIGGER();               // the next kernel of the stream may be scheduled from here on ...
     CHS_PDL_WAIT();                  // ... and this one touches global memory only after its predecessor is complete
+    CHS_TRACE_PT(a, blockIdx.x, 0);
     const int total = G::NTILES * a.nsims;
     unsigned phase = 0;
     CHS_TILE_LOOP(w, total) {
@@ -919,7 +950,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
     using G = Geo<N>;
     constexpr int M = G::M, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
-    constexpr int R0 = Rad<M>::radix(0), ST0 = M / R0, NB0 = 16 / R0;
+    constexpr int R0 = Rad<M>::radix(0), ST0 = M / R0, NB0 = G::PPT / R0;
     double2* sc = reinterpret_cast<double2*>(sm);
     const double2* __restrict__ s_tw = a.tw;
     const double2* __restrict__ s_om = a.om;
@@ -958,8 +989,10 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
             const double* src = (MODE == ROW_FWD_U && a.src) ? a.src : a.U;
             row_tile_load_phys<N, true>(sm, src + off + (size_t)row0 * N, tid);
         }
+        CHS_TRACE_PT(a, w, 9);
         chs_cp_async_wait_all();
         __syncthreads();
+        CHS_TRACE_PT(a, w, 10);
         if (!halted) {
             // ============= inverse half: T rows (slot order) -> U rows (Makhoul order in smem)
             if (MODE == ROW_STEP || MODE == ROW_INV) {
@@ -970,7 +1003,9 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     fused_units<N, false, true, RowPre<N>, true, false>(scl, t, pre);
                 }
                 line_barrier<N, true>();
+                CHS_TRACE_PT(a, w, 11);
                 fft_inv_range<N, 1, NST - 1, true>(scl, t, s_tw);
+                CHS_TRACE_PT(a, w, 12);
                 if (MODE == ROW_INV || slow) {
                     fft_stage<N, 0, true>(scl, t, s_tw);
                     __syncthreads();
@@ -1006,7 +1041,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     if (ra_tile) {                                              // mean of the jittered Ra row
                         if (ra_line) {
                             double s = 0;
-                            for (int i = 0; i < 16; ++i) {
+                            for (int i = 0; i < G::PPT; ++i) {
                                 const double2 v = scl[G::idx(t + i * TPL)];
                                 s += v.x + v.y;
                             }
@@ -1031,7 +1066,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     if (ra_line) {                                              // Ra = mean |U[r,:] - mean U[r,:]| (solver.py:226-227)
                         const double ra_mean = ra_scr[0];
                         double s = 0;
-                        for (int i = 0; i < 16; ++i) {
+                        for (int i = 0; i < G::PPT; ++i) {
                             const double2 v = scl[G::idx(t + i * TPL)];
                             s += fabs(v.x - ra_mean) + fabs(v.y - ra_mean);
                         }
@@ -1077,6 +1112,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
 #pragma unroll
                         for (int q = 0; q < R0; ++q) pj[q * G::step(ST0)] = make_double2(xr[q], xi[q]);
                     }
+                    CHS_TRACE_PT(a, w, 13);
                     const double v[4] = {chs_fma(pk.th.RT, acc.fa + acc.fb, acc.fp), acc.ab, acc.mu2, (double)acc.cnt};
                     reduce_stage<4>(v, sm + G::OFF_RED, tid);
                     __syncthreads();
@@ -1104,15 +1140,6 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                                 S->ra = s / (double)N;
                             }
                         }
-                        // Ticket now, not at the end of the tile: step_control() only needs every
-                        // CTA's partial sums, so the atomic's round trip hides behind the forward transform.
-                        if (!jit && !want_cols) {
-                            __threadfence();
-                            const unsigned prev = atomicAdd(&S->ticket, 1u);
-                            const int lastf = (prev == (unsigned)(G::NTILES - 1));
-                            if (lastf) S->ticket = 0;
-                            *flag = lastf;
-                        }
                     }
                     if (slow) {
                         // adaptive dt: column sums of delt_max/sqrt(1 + 62.5 mu^2) over this tile's rows (solver.py:182-183)
@@ -1138,24 +1165,46 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     __syncthreads();
                 }
                 // ============= forward half: remaining stages, fused last stage + post, store
+                CHS_TRACE_PT(a, w, 14);
                 fft_fwd_range<N, 1, NST - 1, true>(scl, t, s_tw);
+                CHS_TRACE_PT(a, w, 15);
                 {   // fused: last forward stage + post + 2x2 exchange into the piece form
                     RowPost<N> post{s_om};
                     fused_units<N, true, false, RowPost<N>, false, true>(scl, t, post);
                 }
                 __syncthreads();
+                CHS_TRACE_PT(a, w, 16);
+                // Ticket: step_control() needs every CTA's partial sums, which thread 0 wrote two passes ago -- the
+                // fence finds them performed, and the atomic's round trip runs behind the tile store (its result is
+                // first used after the store).  (With the ticket right after the sums, thread 0 -- and with it the
+                // CTA's next barrier -- waited 1.3 us for fence + atomic: tools/trace_single.py.)
+                unsigned prev_ticket = 0;
+                const bool early_ticket = control && !jit && !want_cols;
+                if (early_ticket && tid == 0) {
+                    __threadfence();
+                    prev_ticket = atomicAdd(&S->ticket, 1u);
+                }
                 row_tile_pairs_io<N, true>(sc, a.T + off, tile, tid);
+                if (early_ticket && tid == 0) {
+                    const int lastf = (prev_ticket == (unsigned)(G::NTILES - 1));
+                    if (lastf) S->ticket = 0;
+                    *flag = lastf;
+                }
+                CHS_TRACE_PT(a, w, 17);
                 // ============= control (with jitter k_diag finishes the iteration instead)
                 if (control && !jit) {
                     bool is_last;
                     if (want_cols) is_last = last_cta(S, G::NTILES, flag, tid, true);   // column sums were written by all threads
                     else { __syncthreads(); is_last = (*flag != 0); if (is_last) __threadfence(); }
                     if (is_last) {
+                        CHS_TRACE_PT(a, 0, 20);
                         step_control<N>(S, a.part + (size_t)sim * P_NSLOT * G::NTILES,
                                         a.colpart + (size_t)sim * G::NTILES * N,
                                         a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last,
-                                        MODE == ROW_STEP, sm, tid, NT);
+                                        MODE == ROW_STEP, sm, sm + G::OFF_EDGE, tid, NT);
+                        CHS_TRACE_PT(a, 0, 19);
                     }
+                    CHS_TRACE_PT(a, w, 18);
                 }
             }
         }
@@ -1168,10 +1217,46 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_row(KArgs a) {
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
     CHS_PDL_TRIGGER();               // the next kernel of the stream may be scheduled from here on ...
     CHS_PDL_WAIT();                  // ... and this one touches global memory only after its predecessor is complete
+    CHS_TRACE_PT(a, blockIdx.x, 8);
     const int total = G::NTILES * a.nsims;
     CHS_TILE_LOOP(w, total) {
         k_row_tile<N, MODE>(a, w, sm);
         __syncthreads();                 // the tile buffer (and flag / scratch) is reused by the next iteration
+    }
+    chs_cp_async_wait_all();
+}
+
+// =======================================================================================
+//  k_mix: one launch = the COLUMN half-step of one half of the batch (ac) and the ROW half-step of the other
+//  half (ar), CTAs alternating.  k_col<STEP> is bound by HBM (long-scoreboard waits on its bulk copies and the
+//  hat_U stream) and k_row<STEP> by FP64 issue and the shared-memory pipe: with both kinds of CTA resident
+//  on every SM at the same time the memory system and the arithmetic pipes are busy together instead of one
+//  after the other.  The host skews the two halves by half a step (do_steps): the simulations of one launch
+//  are disjoint, so the kernels' per-simulation ordering (ticket, step_control) is unchanged.
+// =======================================================================================
+template <int N>
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_mix(KArgs ac, KArgs ar, int period) {
+    using G = Geo<N>;
+    CHS_SMEM_DECL
+    double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
+    if (threadIdx.x == 0) chs_mbar_init(sm + G::OFF_FLAG + 1, 1);
+    __syncthreads();
+    CHS_PDL_TRIGGER();
+    CHS_PDL_WAIT();
+    const int ncol = G::NTILES * ac.nsims, nrow = G::NTILES * ar.nsims;
+    const int total = 2 * (ncol > nrow ? ncol : nrow);
+    unsigned phase = 0;
+    CHS_TILE_LOOP(w2, total) {
+        // CTAs are handed to the SMs round-robin: flipping the kind every `period` (= #SMs, even) CTAs gives
+        // every SM both kinds from the first wave on
+        const int w = w2 >> 1;
+        if ((w2 ^ (w2 / period)) & 1) {
+            if (w < nrow) k_row_tile<N, ROW_STEP>(ar, w, sm);
+        } else if (w < ncol) {
+            k_col_tile<N, COL_STEP>(ac, w, sm, phase);
+            phase ^= 1;
+        }
+        __syncthreads();
     }
     chs_cp_async_wait_all();
 }
@@ -1282,7 +1367,7 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
     if (!last_cta(S, G::NTILES, flag, tid, false)) return;
     if (MODE == DIAG_JITTER) {
         step_control<N>(S, a.part + (size_t)sim * P_NSLOT * G::NTILES, a.colpart + (size_t)sim * G::NTILES * N,
-                        a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last, true, sm, tid, NT);
+                        a.rows + (size_t)sim * a.rows_cap * CHS_NCOLS, a.rows_cap, a.last, true, sm, sm + G::OFF_EDGE, tid, NT);
         return;
     }
     if (tid != 0) return;
@@ -1332,7 +1417,7 @@ CHS_KERNEL void k_rewind(Sim* sims, int batch) {
     if (i < batch) sims[i].rows_written = 0;
 }
 
-}  // namespace chs
+}  // namespace CHS_NS
 
 // ---------------------------------------------------------------------------------------
 // Bit-exact numpy PCG64 on the device: the per-step jitter of solver.py:210-211 is
@@ -1341,7 +1426,7 @@ CHS_KERNEL void k_rewind(Sim* sims, int batch) {
 // Every thread jumps to its position with the O(log n) LCG skip-ahead and then produces a
 // run of PCG_RUN consecutive values, so a whole chunk of steps is one launch and nothing
 // crosses PCIe.
-namespace chs {
+namespace CHS_NS {
 typedef unsigned __int128 u128;
 constexpr int PCG_RUN = 32;
 CHS_DEV u128 pcg_mult() { return ((u128)0x2360ED051FC65DA4ULL << 64) | (u128)0x4385DF649FCCF645ULL; }
@@ -1410,4 +1495,4 @@ CHS_KERNEL void k_row_means(const double* in, long long cols, double* out) {
         out[blockIdx.x] = t / (double)cols;
     }
 }
-}  // namespace chs
+}  // namespace CHS_NS

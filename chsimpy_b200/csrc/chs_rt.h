@@ -6,6 +6,16 @@
 // never loads it and has no CPU fallback.
 #pragma once
 
+// The kernel headers are compiled twice into the library: as namespace chs with 16 points per thread and FFT
+// stage (the throughput geometry, chs_api.cu) and as namespace chs_ll with 8 (twice the threads per line: the
+// low-latency geometry of a single simulation / a few simulations, chs_ll.cu).
+#ifndef CHS_NS
+#define CHS_NS chs
+#endif
+#ifndef CHS_PPT
+#define CHS_PPT 16
+#endif
+
 #ifdef CHS_EMU
 #include "emu.h"
 #else

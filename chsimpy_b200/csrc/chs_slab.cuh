@@ -16,7 +16,7 @@
 #pragma once
 #include "chs_kernels.cuh"
 
-namespace chs {
+namespace CHS_NS {
 
 enum { S_FWD = 0, S_MU = 1, S_INV = 2, S_STEP = 3, S_YFWD = 4, S_YSTEP = 5 };
 // reduced vector layout (all-reduced over ranks)
@@ -554,4 +554,4 @@ CHS_KERNEL void k_slab_control(Sim* S, double* vec, double* rows, long long rows
     if (p.time_limit_s > 0.0 && S->time_passed > p.time_limit_s) { S->stop_reason = CHS_STOP_TIME; S->halted = 1; }
 }
 
-}  // namespace chs
+}  // namespace CHS_NS

@@ -20,7 +20,7 @@
 #pragma once
 #include "chs_rt.h"
 
-namespace chs {
+namespace CHS_NS {
 
 CHS_CX constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 
@@ -150,9 +150,12 @@ struct Geo {
         }
         return true;
     }
-    static constexpr int TPL = M / 16;                         // threads per line: 16 complex points each per stage
-    CHS_CX static constexpr int line_of(int tid) { return LINE_MAJOR ? tid / (M / 16) : tid % LINES; }
-    CHS_CX static constexpr int t_of(int tid) { return LINE_MAJOR ? tid % (M / 16) : tid / LINES; }
+    // complex points per thread and stage: 16 (throughput geometry), or CHS_PPT = 8 in the low-latency build
+    // (chs_ll.cu: twice the threads per line, half the serial work per thread)
+    static constexpr int PPT = LINE_MAJOR ? 16 : CHS_PPT;
+    static constexpr int TPL = M / PPT;                        // threads per line
+    CHS_CX static constexpr int line_of(int tid) { return LINE_MAJOR ? tid / TPL : tid % LINES; }
+    CHS_CX static constexpr int t_of(int tid) { return LINE_MAJOR ? tid % TPL : tid / LINES; }
     static constexpr int NT = LINES * TPL;                     // threads per CTA
     static constexpr int NTILES = N / LINES;
 #ifndef CHS_SEQ_STAGES
@@ -282,7 +285,8 @@ CHS_DEV void fft_stage(double2* scl, int t, const double2* __restrict__ tw) {
     using G = Geo<N>;
     constexpr int M = G::M, TPL = G::TPL;
     constexpr int r = Rad<M>::radix(S), Lb = Rad<M>::blocklen(S), st = Lb / r;
-    constexpr int NB = 16 / r;
+    constexpr int NB = G::PPT / r;
+    static_assert(NB >= 1, "a thread owns at least one butterfly per stage");
     if constexpr (G::SEQ) {
         // register-light form: one butterfly at a time (r points live)
 #pragma unroll 1
@@ -446,11 +450,11 @@ CHS_DEV void pre_special(const double2* __restrict__ om, const double (&c)[4], d
 template <int N>
 struct Pairing {
     static constexpr int M = N / 2, RL = Rad<M>::RL, Q = M / RL, H = RL / 2;
-    static constexpr int NU = 16 / (2 * RL), TPL = M / 16;
-    static_assert(NU * TPL == Q / 2, "units must cover all residues");
+    static constexpr int NU = Geo<N>::PPT / (2 * RL), TPL = Geo<N>::TPL;
+    static_assert(NU >= 1 && NU * TPL == Q / 2, "units must cover all residues");
 };
 
 // Column slot s (PERM order used by T and hat_U along the x-spectral axis) holds frequency:
 //   s = 2*pos(k) + 0 -> k ;  s = 2*pos(k) + 1 -> N-k  (k = 0: M).   Host table `kof`.
 
-}  // namespace chs
+}  // namespace CHS_NS

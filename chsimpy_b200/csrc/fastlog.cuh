@@ -17,7 +17,7 @@
 #pragma once
 #include "chs_rt.h"
 
-namespace chs {
+namespace CHS_NS {
 
 constexpr int LOG_TABLE_N = CHS_LOG_N;
 constexpr unsigned long long LOG_OFF = 0x3fe6000000000000ULL;
@@ -124,4 +124,4 @@ CHS_DEV double log_abs(double x, const double2* __restrict__ tab) {
     return log_abs_unchecked<1>(x, tab);
 }
 
-}  // namespace chs
+}  // namespace CHS_NS

@@ -181,6 +181,19 @@ class BatchStepper:
         _lib.check(self.lib, self.lib.chs_get_timing(self._h, ms, C.byref(n)), "chs_get_timing")
         return {"col": ms[0], "row": ms[1], "diag": ms[2]}, int(n.value)
 
+    def set_mix(self, mode):
+        """-1: mixed launches (k_mix) when enough members run (default), 0: never, 1: whenever >= 2 members run."""
+        _lib.check(self.lib, self.lib.chs_set_mix(self._h, int(mode)), "chs_set_mix")
+
+    def get_timing_mix(self):
+        """({'mix': ms, 'solo': ms}, {'mix': launches, 'solo': launches}, iterations) of the calls that ran as
+        mixed launches (k_mix) since the last call."""
+        ms = (C.c_double * 2)()
+        n2 = (C.c_int64 * 2)()
+        n = C.c_int64(0)
+        _lib.check(self.lib, self.lib.chs_get_timing_mix(self._h, ms, n2, C.byref(n)), "chs_get_timing_mix")
+        return {"mix": ms[0], "solo": ms[1]}, {"mix": int(n2[0]), "solo": int(n2[1])}, int(n.value)
+
     def pcg64_noise(self, bit_generator_state, n):
         """(noise [n][N][N], per-step means [n]) on the device: the next n*N*N doubles of a numpy
         PCG64 generator whose `bit_generator.state` is given -- bit-identical to rng.random()."""

@@ -155,6 +155,14 @@ int64_t chs_launch_count(const chs_solver*);
  * and the number of iterations they cover, then clears the accumulators. */
 int chs_set_timing(chs_solver*, int32_t enable);
 int chs_get_timing(chs_solver*, double* ms3, int64_t* n_iters);
+/* The same for calls that ran as mixed launches (k_mix: column half-step of one half of the batch + row
+ * half-step of the other half in ONE launch, see chs_steps): ms2/n2 = {accumulated ms, launches} of
+ * {the mixed launches, the two half-size launches at the ends of every call}; n_iters = iterations covered. */
+int chs_get_timing_mix(chs_solver*, double* ms2, int64_t* n2, int64_t* n_iters);
+/* Scheduling of chs_steps (results are identical either way): -1 = mixed launches when at least 32 simulations
+ * run and the call covers >= 2 iterations without noise (default; environment CHS_MIX overrides the default),
+ * 0 = always one column + one row launch per iteration, 1 = mixed whenever >= 2 simulations run. */
+int chs_set_mix(chs_solver*, int32_t mode);
 
 /* ---------------------------------------------------------------------------------------
  * Slab path: ONE large N x N simulation, row-slab decomposed over `world` ranks (world = 1:

@@ -23,7 +23,7 @@ def build_emu():
     if os.path.exists(EMU_LIB) and all(os.path.getmtime(s) <= os.path.getmtime(EMU_LIB) for s in srcs):
         return EMU_LIB
     cmd = ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-DCHS_EMU", "-x", "c++", "-shared", "-fPIC",
-           "-pthread", "-o", EMU_LIB, os.path.join(_lib.CSRC, "chs_api.cu")]
+           "-pthread", "-o", EMU_LIB] + [os.path.join(_lib.CSRC, u) for u in _lib.UNITS]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emu build failed:\n" + r.stderr)

@@ -57,9 +57,12 @@ def run_fixture(be, name, limit=None):
     return sol, z, m
 
 
-@pytest.mark.parametrize("name,steps", [("n256_k200", 6), ("n512_full2000", 3)])
-def test_step_n256_n512(be, name, steps):
-    """The tile geometry of the sizes that matter (N = 256, 512), a few steps against the fixtures."""
+@pytest.mark.parametrize("name,steps,env", [("n256_k200", 6, {}), ("n512_full2000", 3, {}), ("n512_full2000", 3, {"CHS_LL_MAX": "2"})])
+def test_step_n256_n512(be, name, steps, env, monkeypatch):
+    """The tile geometry of the sizes that matter (N = 256, 512), a few steps against the fixtures: the step kernels
+    of the throughput build and the optional 8-points-per-thread build (chs_ll.cu, CHS_LL_MAX: 256 threads per tile)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     sol, z, m = run_fixture(be, name, limit=steps)
     assert sol.computed_steps == steps
 
@@ -353,3 +356,43 @@ def test_arbitrary_n_path_vs_oracle(be, kw, steps):
     rel[ref == 0] = np.abs(rows[ref == 0])
     assert rel.max() < 1e-9, rel.max(axis=0)
     assert np.abs(sol.U - o.U).max() < 1e-11
+
+
+def test_mixed_launches_are_bit_identical(be):
+    """chs_steps as mixed launches (k_mix: column half-step of one half of the members + row half-step of the
+    other half per launch, the halves skewed by half a step) against one column + one row launch per iteration:
+    the same kernels on the same data in the same per-member order, so TimeData rows, fields and states must be
+    identical bit for bit -- with an odd member count, two calls in a row, the `last` flag and a member that
+    reaches its time limit in the middle of a call (device stop flag; its half keeps stepping)."""
+    N, B = 64, 5
+    structs = []
+    for i in range(B):
+        p = unit_params(N)
+        p.delt = 1e-8 * (1 + 0.1 * i)
+        p.A0 = 1 + 0.05 * i
+        p.full_sim = 1
+        if i == 3:
+            p.time_limit_s = 4.5e-8 * 1.3           # halts after its 4th accounting step
+        structs.append(p)
+    U0 = 0.5 + 0.2 * (np.random.default_rng(7).random((N, N)) - 0.5)
+    out = {}
+    for mode in (0, 1):
+        st = BatchStepper(N, structs, rows_cap=32, backend=be)
+        st.set_mix(mode)
+        st.set_U(U0)
+        st.prepare()
+        st.begin()
+        l0 = st.launch_count()
+        st.steps(4)
+        st.steps(5, last=True)
+        n_launch = st.launch_count() - l0
+        running, stop, cs, rw = st.poll()
+        rows = st.take_rows()
+        st.end()
+        out[mode] = (n_launch, stop.copy(), cs.copy(), rw.copy(), rows, np.stack([st.get_U(i) for i in range(B)]))
+    assert out[0][0] == 2 * 9 and out[1][0] == (2 * 4 + 1) + (2 * 5 + 1)
+    assert (out[0][1] == out[1][1]).all() and (out[0][2] == out[1][2]).all() and (out[0][3] == out[1][3]).all()
+    assert out[0][2][3] < 10 and out[0][2][0] == 10, out[0][2]        # (prepare counts as step 1) member 3 stopped early, the others ran on
+    for a, b in zip(out[0][4], out[1][4]):
+        assert a.shape == b.shape and (a.view(np.int64) == b.view(np.int64)).all()
+    assert (out[0][5].view(np.int64) == out[1][5].view(np.int64)).all()

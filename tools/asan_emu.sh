@@ -13,7 +13,7 @@ mkdir -p tests/_build
 [ -f tests/_build/libchs_emu.so ] && cp tests/_build/libchs_emu.so /tmp/libchs_emu.orig.so
 SAN=${SAN:-address}
 g++ -std=c++20 -O1 -g -fsanitize=$SAN -fno-omit-frame-pointer -ffp-contract=off -DCHS_EMU -x c++ \
-    -shared -fPIC -pthread -o tests/_build/libchs_emu.so chsimpy_b200/csrc/chs_api.cu
+    -shared -fPIC -pthread -o tests/_build/libchs_emu.so chsimpy_b200/csrc/chs_api.cu chsimpy_b200/csrc/chs_ll.cu
 RT=$([ "$SAN" = thread ] && echo libtsan.so || echo libasan.so)
 LD_PRELOAD=$(gcc -print-file-name=$RT) ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 \
     TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4 log_path=/tmp/chs_tsan.log" \
