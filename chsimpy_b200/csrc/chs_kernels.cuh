@@ -238,11 +238,13 @@ struct ThermoK { double RT, mBRT, A0, A1, m2A1, B; };
 template <int LS, bool BTERM>
 CHS_DEV double thermo_acc(double u, const ThermoK& k, const double2* __restrict__ ltab, double& fa, double& fb, double& fp) {
     const double ui = 1.0 - u;
-    double lu = log_abs_unchecked<LS>(u, ltab), li = log_abs_unchecked<LS>(ui, ltab);
-    if (!in_open_unit_interval(u)) {
-        lu = slow_log(u);
-        li = slow_log(ui);
-    }
+    double lu = log_abs_unchecked<LS>(u, ltab);
+    const double li = log_abs_unchecked<LS>(ui, ltab);
+    // u outside [2^-1022, 1): np.log of the reference gives nan / -inf for u or 1 - u there and E of that step is
+    // nan either way (0 * -inf, or nan), which is all that is observable (timedata.py:10 stops the run).  One select
+    // instead of a libm call site per value: a call in the loop costs the compiler its registers around it
+    // (32 call sites, ~20 % of the instructions of the physics block were moves and convergence barriers).
+    lu = in_open_unit_interval(u) ? lu : chs_ll2d(0x7ff8000000000000LL);
     const double d = ui - u;
     const double uui = u * ui;
     const double g = chs_fma(k.A1, d, k.A0);

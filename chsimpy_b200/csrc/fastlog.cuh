@@ -85,10 +85,17 @@ CHS_DEV double log_abs_unchecked(double x, const double2* __restrict__ tab) {
     constexpr double Ln2 = 0x1.62e42fefa39efp-1;
     const double w = chs_fma((double)k, Ln2, e.y);
     const double r2 = r * r;
-    // log1p(r) = r + r2*(-1/2 + r/3 + r2*(-1/4 + r/5 + r2*(-1/6 + r/7))),  |r| < 2^-7: the r^8/8 term is < 2^-59
-    const double p = chs_fma(r2, chs_fma(r, 1.0 / 7, -1.0 / 6), chs_fma(r, 1.0 / 5, -1.0 / 4));
-    const double q = chs_fma(r, 1.0 / 3, -0.5);
-    return w + chs_fma(r2, chs_fma(r2, p, q), r);
+    // log1p(r) = r + r2*(-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7),  |r| < 2^-7: the r^8/8 term is < 2^-59.
+    // Horner in r: every FMA but the first has ONE literal operand (an FP64 instruction takes one constant /
+    // immediate; a second literal is a register pair the compiler re-materialises with two moves per use -- the
+    // Estrin form had three such FMAs per logarithm = 12 moves per value in the hot loop).  Same FP64 count; the
+    // two logarithms of a value and the values of a butterfly give the scheduler its parallelism.
+    double h = chs_fma(r, 1.0 / 7, -1.0 / 6);
+    h = chs_fma(h, r, 1.0 / 5);
+    h = chs_fma(h, r, -0.25);
+    h = chs_fma(h, r, 1.0 / 3);
+    h = chs_fma(h, r, -0.5);
+    return w + chs_fma(r2, h, r);
 }
 
 // fast path only: the caller checks log_needs_slow_path() (garbage, but no trap, for such arguments)
