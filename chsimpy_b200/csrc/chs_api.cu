@@ -431,8 +431,8 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     }
     // fast_log table (fastlog.cuh): sub-interval centres of [0.6875, 1.375) in bit-pattern space
     for (int i = 0; i < LOG_TABLE_N; ++i) {
-        const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << 45);
-        const unsigned long long b1 = LOG_OFF + ((unsigned long long)(i + 1) << 45);
+        const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << LOG_SHIFT);
+        const unsigned long long b1 = LOG_OFF + ((unsigned long long)(i + 1) << LOG_SHIFT);
         double z0, z1;
         std::memcpy(&z0, &b0, 8);
         std::memcpy(&z1, &b1, 8);
@@ -1009,7 +1009,7 @@ extern "C" chs_slab* chs_slab_create(int32_t device, int32_t N, int32_t rows, in
     }
     for (int k = 0; k < N; ++k) { const long double sn = sinl(pi * k / N); gs[k] = (double)(sn * sn); }
     for (int i = 0; i < LOG_TABLE_N; ++i) {
-        const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << 45), b1 = LOG_OFF + ((unsigned long long)(i + 1) << 45);
+        const unsigned long long b0 = LOG_OFF + ((unsigned long long)i << LOG_SHIFT), b1 = LOG_OFF + ((unsigned long long)(i + 1) << LOG_SHIFT);
         double z0, z1; std::memcpy(&z0, &b0, 8); std::memcpy(&z1, &b1, 8);
         const double invc = (double)(1.0L / ((long double)z0 * 0.5L + (long double)z1 * 0.5L));
         lt[i] = make_double2(invc, (double)(-logl((long double)invc)));

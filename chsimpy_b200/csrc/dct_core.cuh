@@ -95,7 +95,8 @@ struct Rad {
 #define CHS_LINES 8
 #endif
 CHS_CX constexpr int geo_lines(int N) { return N <= 1024 ? CHS_LINES : 1; }   // lines (rows / columns) per tile
-#define CHS_LOG_N 128       // entries of the fast_log table (fastlog.cuh)
+#define CHS_LOG_N 256       // entries of the fast_log table (fastlog.cuh): 2^CHS_LOG_BITS
+#define CHS_LOG_BITS 8
 #define CHS_SIMK 16         // doubles of the per-simulation constants image staged in shared memory
 
 template <int N_>

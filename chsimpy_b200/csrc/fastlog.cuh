@@ -2,7 +2,7 @@
 // chsimpy/solver.py:173,220 call np.log three times per element; it is the largest single
 // consumer of FP64 issue slots in the step).
 //
-//   x = 2^k * z,  z in [0.6875, 1.375);  i = top 7 mantissa bits of (bits(x) - bits(0.6875))
+//   x = 2^k * z,  z in [0.6875, 1.375);  i = top LOG_BITS = 8 mantissa bits of (bits(x) - bits(0.6875))
 //   table[i] = { invc, logc }  with invc = double(1/c_i), c_i := 1/invc (c_i ~ centre of
 //   sub-interval i), logc = log(c_i) rounded to double
 //   r = fma(z, invc, -1)              exact to one rounding of a 2^-8-sized number
@@ -20,6 +20,9 @@
 namespace CHS_NS {
 
 constexpr int LOG_TABLE_N = CHS_LOG_N;
+constexpr int LOG_BITS = CHS_LOG_BITS;               // sub-interval index = top LOG_BITS mantissa bits
+constexpr int LOG_SHIFT = 52 - LOG_BITS;             // ... of the 64-bit pattern; 20 - LOG_BITS of the high word
+static_assert((1 << LOG_BITS) == LOG_TABLE_N, "table size");
 constexpr unsigned long long LOG_OFF = 0x3fe6000000000000ULL;
 
 #ifdef CHS_EMU
@@ -72,12 +75,12 @@ CHS_DEV bool in_open_unit_interval(double u) { return (unsigned)(chs_hiword(u) -
 // log x with a small ABSOLUTE error (<= ~1.5 ulp of max(|log x|, 2^-8); no hi/lo compensation, degree-7
 // log1p series): what the free energy and the chemical potential need -- log u and log(1-u) enter them
 // additively next to terms of size O(1), so the relative accuracy of fast_log near x = 1 buys nothing.
-// 11 FP64 instructions instead of 16.  tab entry i at tab[i * STRIDE].
+// 8 FP64 instructions (+ the int -> double conversion of k) instead of 16.  tab entry i at tab[i * STRIDE].
 template <int STRIDE = 1>
 CHS_DEV double log_abs_unchecked(double x, const double2* __restrict__ tab) {
     const int hx = chs_hiword(x);
     const int tmp = hx - 0x3fe60000;                                  // LOG_OFF >> 32
-    const int i = (tmp >> 13) & (LOG_TABLE_N - 1);
+    const int i = (tmp >> (20 - LOG_BITS)) & (LOG_TABLE_N - 1);
     const int k = tmp >> 20;                                          // arithmetic shift: floor
     const double z = chs_sethiword(x, hx - (int)((unsigned)tmp & 0xfff00000u));
     const double2 e = tab[i * STRIDE];
@@ -85,14 +88,13 @@ CHS_DEV double log_abs_unchecked(double x, const double2* __restrict__ tab) {
     constexpr double Ln2 = 0x1.62e42fefa39efp-1;
     const double w = chs_fma((double)k, Ln2, e.y);
     const double r2 = r * r;
-    // log1p(r) = r + r2*(-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7),  |r| < 2^-7: the r^8/8 term is < 2^-59.
-    // Horner in r: every FMA but the first has ONE literal operand (an FP64 instruction takes one constant /
-    // immediate; a second literal is a register pair the compiler re-materialises with two moves per use -- the
-    // Estrin form had three such FMAs per logarithm = 12 moves per value in the hot loop).  Same FP64 count; the
-    // two logarithms of a value and the values of a butterfly give the scheduler its parallelism.
-    double h = chs_fma(r, 1.0 / 7, -1.0 / 6);
-    h = chs_fma(h, r, 1.0 / 5);
-    h = chs_fma(h, r, -0.25);
+    // log1p(r) = r + r2*(-1/2 + r/3 - r^2/4 + r^3/5),  |r| < 2^-9 with the 256-entry table: the first dropped term
+    // r^6/6 is < 2^-56.5 = 1e-17 (with 128 entries, |r| < 2^-8, two more terms were needed: 4 FP64 instructions per
+    // value of the field).  Horner in r: every FMA but the first has ONE literal operand (an FP64 instruction takes one
+    // constant / immediate; a second literal is a register pair the compiler re-materialises with two moves per use
+    // -- an Estrin form has one such FMA per coefficient pair).  The two logarithms of a value and the values of a
+    // butterfly give the scheduler its parallelism.
+    double h = chs_fma(r, 1.0 / 5, -0.25);
     h = chs_fma(h, r, 1.0 / 3);
     h = chs_fma(h, r, -0.5);
     return w + chs_fma(r2, h, r);
@@ -104,7 +106,7 @@ CHS_DEV double fast_log_unchecked(double x, const double2* __restrict__ tab) {
     // all bit manipulation on the high 32-bit word (sign, exponent, 20 mantissa bits)
     const int hx = chs_hiword(x);
     const int tmp = hx - 0x3fe60000;                                  // LOG_OFF >> 32
-    const int i = (tmp >> 13) & (LOG_TABLE_N - 1);
+    const int i = (tmp >> (20 - LOG_BITS)) & (LOG_TABLE_N - 1);
     const int k = tmp >> 20;                                          // arithmetic shift: floor
     const double z = chs_sethiword(x, hx - (int)((unsigned)tmp & 0xfff00000u));
     const double2 e = tab[i * STRIDE];
