@@ -1178,10 +1178,25 @@ extern "C" int chs_slab_row_means(chs_slab* s, const double* in, int64_t rows, i
     return 0;
 }
 
+// 4096-element tiles + bulk stores (k_slab_transpose_bulk) when shape and alignment allow; CHS_SLAB_BULK=0 keeps the 32 x 32 kernels
+static bool slab_bulk_transpose(int R, int C, const double* in, const double* out, int in_ld, int out_ld) {
+    static const bool on = [] { const char* e = getenv("CHS_SLAB_BULK"); return !e || atoi(e) != 0; }();
+    return on && R % SLAB_TR == 0 && C % SLAB_TC == 0 && in_ld % 2 == 0 && out_ld % 2 == 0 &&
+           (uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0;
+}
+
 extern "C" int chs_slab_transpose(chs_slab* s, const double* in, double* out, int32_t R, int32_t C, int32_t in_ld, int32_t out_ld) {
     if (!s || !in || !out) return fail("chs_slab_transpose: bad argument");
-    CHS_LAUNCH_PDL(k_slab_transpose, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 32 * 33 * sizeof(double), s->stream,
-               in, out, (int)R, (int)C, (int)in_ld, (int)out_ld);
+    if (slab_bulk_transpose(R, C, in, out, in_ld, out_ld)) {
+        PeerPtrs pp;
+        for (int i = 0; i < 8; ++i) pp.p[i] = nullptr;
+        pp.p[0] = out;
+        CHS_LAUNCH_PDL(k_slab_transpose_bulk, dim3(C / SLAB_TC, R / SLAB_TR, 1), dim3(256), SLAB_TC * SLAB_TP * sizeof(double),
+                       s->stream, pp, in, (int)R, (int)C, (int)in_ld, (int)out_ld, 0, 1);
+    } else {
+        CHS_LAUNCH_PDL(k_slab_transpose, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 32 * 33 * sizeof(double), s->stream,
+                       in, out, (int)R, (int)C, (int)in_ld, (int)out_ld);
+    }
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());
     return 0;
@@ -1194,8 +1209,14 @@ extern "C" int chs_slab_transpose_peers(chs_slab* s, const double* in, const uin
     if (!s || !in || !dst || s->world < 1 || s->world > 8) return fail("chs_slab_transpose_peers: bad argument (at most 8 ranks)");
     PeerPtrs pp;
     for (int i = 0; i < 8; ++i) pp.p[i] = (i < s->world) ? (double*)(uintptr_t)dst[i] : nullptr;
-    CHS_LAUNCH_PDL(k_slab_transpose_peers, dim3((C + 31) / 32, (R + 31) / 32, s->world), dim3(256), 32 * 33 * sizeof(double),
-                   s->stream, pp, in, (int)R, (int)C, (int)in_ld, (int)out_ld, s->rank, s->world);
+    bool bulk = slab_bulk_transpose(R, C, in, pp.p[0], in_ld, out_ld);
+    for (int i = 1; i < s->world; ++i) bulk = bulk && ((uintptr_t)pp.p[i] % 16 == 0);
+    if (bulk)
+        CHS_LAUNCH_PDL(k_slab_transpose_bulk, dim3(C / SLAB_TC, R / SLAB_TR, s->world), dim3(256), SLAB_TC * SLAB_TP * sizeof(double),
+                       s->stream, pp, in, (int)R, (int)C, (int)in_ld, (int)out_ld, s->rank, s->world);
+    else
+        CHS_LAUNCH_PDL(k_slab_transpose_peers, dim3((C + 31) / 32, (R + 31) / 32, s->world), dim3(256), 32 * 33 * sizeof(double),
+                       s->stream, pp, in, (int)R, (int)C, (int)in_ld, (int)out_ld, s->rank, s->world);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());
     return 0;

@@ -282,6 +282,46 @@ CHS_KERNEL void k_slab_transpose_peers(PeerPtrs dst, const double* in, int R, in
         if (bx + k < C && by + tx < R) out[(size_t)(bx + k) * out_ld + by + tx] = tile[tx * 33 + k];
 }
 
+// The same exchange with 4096-element tiles whose transposed rows leave the SM as BULK asynchronous stores
+// (cp.async.bulk shared -> global, SASS UBLKCP): one 1 KB copy per output row segment instead of 8-byte stores of a
+// warp -- fewer, larger write packets on NVLink, and no LSU instruction for the remote side.  Needs R % SLAB_TR == 0
+// and C % SLAB_TC == 0.
+// Tile in shared memory: out row c at pitch TP doubles (16-byte aligned rows for the bulk copies; the 2-way bank
+// conflicts of the transposing 8-byte writes are far below what the links can take).
+// Tile: SLAB_TC input columns (= output rows) x SLAB_TR input rows (= bytes/8 of one bulk store).
+#ifndef CHS_SLAB_TR
+#define CHS_SLAB_TR 128
+#endif
+constexpr int SLAB_TR = CHS_SLAB_TR, SLAB_TC = 4096 / SLAB_TR, SLAB_TP = SLAB_TR + 2;
+static_assert(SLAB_TC >= 32 && SLAB_TC % 32 == 0 && SLAB_TR % 16 == 0, "tile shape");
+CHS_KERNEL void k_slab_transpose_bulk(PeerPtrs dst, const double* in, int R, int C, int in_ld, int out_ld, int rank, int P) {
+    CHS_PDL_TRIGGER();
+    CHS_PDL_WAIT();
+    CHS_SMEM_DECL
+    double* tile = reinterpret_cast<double*>(CHS_SMEM_PTR);       // SLAB_TC * SLAB_TP doubles
+    const int peer = (rank + (int)blockIdx.z) % P;
+    const double* src = in + (size_t)peer * C;
+    double* out = dst.p[peer];
+    const int bx = blockIdx.x * SLAB_TC, by = blockIdx.y * SLAB_TR;
+    const int tid = threadIdx.x;                                  // 256 threads
+    // in[by + r][bx + c]: a warp reads 32 consecutive columns of one row (256 contiguous bytes) and writes them to 32
+    // tile rows (pitch = 2 mod 32 doubles, i.e. 4 banks apart: 2-way conflicts); the 16 loads of a thread are in
+    // flight together
+    constexpr int RS = 256 / SLAB_TC;                             // rows covered by one pass of the CTA
+    const int c = tid % SLAB_TC, r0 = tid / SLAB_TC;
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = src[(size_t)(by + r0 + RS * k) * in_ld + bx + c];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tile[c * SLAB_TP + r0 + RS * k] = v[k];
+    chs_fence_async_smem();
+    __syncthreads();
+    if (tid < SLAB_TC) {
+        chs_bulk_s2g(out + (size_t)(bx + tid) * out_ld + by, tile + tid * SLAB_TP, SLAB_TR * 8);
+        chs_bulk_commit_wait();
+    }
+}
+
 // y-edge terms of the gradient energy from two stored rows of U: 3/4 * sum_x (U[r1][x]-U[r0][x])^2
 CHS_KERNEL void k_slab_yedge(const double* r0, const double* r1, int N, double* out, int accumulate) {
     CHS_SMEM_DECL
