@@ -239,6 +239,33 @@ def solve_ensemble(init_params, rand_values=None, A_list=None, run_ids=None, U_i
         raise TypeError("'NoneType' object is not callable")      # create_rand is None (quirk Q7)
     out = []
     t_dev = 0.0
+    be_probe = backend if backend is not None else None
+    lib_ = be_probe.lib if be_probe is not None else None
+    if lib_ is None:
+        from . import _lib as _libmod
+        lib_ = _libmod.load()
+    if not lib_.chs_supports_n(int(init_params.N)):
+        # Sizes the batched kernels do not cover (the reference accepts any N, cli_parser.py:27): the members run one
+        # after the other through the single-simulation engines of Solver (slab path / tensor-core GEMM path) -- the
+        # same device code a single `chsimpy -N <n>` run uses; only the lock-step batching is missing.
+        from .solver import Solver
+        for i, (p, f0, f1) in enumerate(members):
+            tw = time.perf_counter()
+            scal.append(next(scal_iter))
+            t_host += time.perf_counter() - tw
+            p.kappa_tilde = scal[i][0]
+            td = time.perf_counter()
+            slv = Solver(p, None if generated else U_init, _backend=backend)
+            slv.prepare()
+            sol = slv.solve_or_resume(init_params.ntmax)       # AssertionError on a NaN row, as the reference would
+            if not keep_fields:
+                sol.U = None
+            t_dev += time.perf_counter() - td
+            kappa, ca, cb, sa, sb = scal[i]
+            tup = (sol.A0, sol.A1, ca, cb, sa, sb, sol.tau0, sol.t0, int(np.argmax(sol.E2)), run_ids[i], f0, f1)
+            out.append({"tuple": tup, "solution": sol, "params": p, "run_id": run_ids[i]})
+            del slv
+        members = []
     for c0 in range(0, len(members), batch_max):
         chunk = list(range(c0, min(c0 + batch_max, len(members))))
         tw = time.perf_counter()

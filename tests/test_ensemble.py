@@ -178,3 +178,30 @@ def test_two_rank_gloo_equals_single_process():
         assert a == b                      # deterministic kernels: bit-identical regardless of the sharding
     # members differ only through A0/A1 (kappa is pinned here): tsep/tau0 columns are well-formed
     assert all(isinstance(t[8], int) for t in got)
+
+
+def test_ensemble_at_a_size_without_batched_kernels():
+    """The reference runs its ensemble at any N (cli_parser.py:27); N = 120 has no lock-step kernels here (neither a
+    power of two nor <= 104), so the members go one after the other through Solver's single-simulation engine
+    (BigEngine): every member must equal a stand-alone Solver run with that member's parameters."""
+    from emu_lib import EmuBackend
+    be = EmuBackend()
+    assert be.lib.chs_supports_n(120) == 0
+    p0 = _params()
+    p0.N, p0.ntmax = 120, 5
+    ep = ex.ExperimentParams()
+    ep.runs, ep.A_seed = 2, 85972
+    rv, A_list, n = ex.factor_table(ep)
+    res = ex.solve_ensemble(p0, rv, A_list, host_procs=1, backend=be)
+    assert [r["run_id"] for r in res] == [0, 1]
+    for r in res:
+        pm, f0, f1 = ex.member_params(p0, r["run_id"], rv, A_list)
+        pm.kappa_tilde = r["params"].kappa_tilde
+        s = ch.Solver(pm, _backend=be)
+        s.prepare()
+        ref = s.solve_or_resume(p0.ntmax)
+        assert r["solution"].computed_steps == ref.computed_steps == 5
+        assert np.array_equal(r["solution"].timedata.data(), ref.timedata.data())
+        assert np.array_equal(r["solution"].U, ref.U)
+        assert r["tuple"][0] == ref.A0 and r["tuple"][1] == ref.A1 and r["tuple"][9] == r["run_id"]
+    assert res[0]["tuple"][0] != res[1]["tuple"][0]           # the members really differ
