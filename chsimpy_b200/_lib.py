@@ -91,6 +91,8 @@ PROTOTYPES = {
     "chs_slab_get_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p]),
     "chs_slab_set_state": (C.c_int, [C.c_void_p, C.POINTER(State)]),
     "chs_slab_launch_count": (C.c_int64, [C.c_void_p]),
+    "chs_slab_transpose_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "chs_slab_copy_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "chs_slab_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "chs_slab_sums": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "chs_set_timing": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -1188,11 +1188,11 @@ static bool slab_bulk_transpose(int R, int C, const double* in, const double* ou
 extern "C" int chs_slab_transpose(chs_slab* s, const double* in, double* out, int32_t R, int32_t C, int32_t in_ld, int32_t out_ld) {
     if (!s || !in || !out) return fail("chs_slab_transpose: bad argument");
     if (slab_bulk_transpose(R, C, in, out, in_ld, out_ld)) {
-        PeerPtrs pp;
-        for (int i = 0; i < 8; ++i) pp.p[i] = nullptr;
-        pp.p[0] = out;
+        PeerDst pd;
+        for (int i = 0; i < 8; ++i) { pd.p[i] = nullptr; pd.ld[i] = 0; }
+        pd.p[0] = out; pd.ld[0] = out_ld;
         CHS_LAUNCH_PDL(k_slab_transpose_bulk, dim3(C / SLAB_TC, R / SLAB_TR, 1), dim3(256), SLAB_TC * SLAB_TP * sizeof(double),
-                       s->stream, pp, in, (int)R, (int)C, (int)in_ld, (int)out_ld, 0, 1);
+                       s->stream, pd, in, (int)R, (int)C, (int)in_ld, 0, 1);
     } else {
         CHS_LAUNCH_PDL(k_slab_transpose, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 32 * 33 * sizeof(double), s->stream,
                        in, out, (int)R, (int)C, (int)in_ld, (int)out_ld);
@@ -1211,14 +1211,53 @@ extern "C" int chs_slab_transpose_peers(chs_slab* s, const double* in, const uin
     for (int i = 0; i < 8; ++i) pp.p[i] = (i < s->world) ? (double*)(uintptr_t)dst[i] : nullptr;
     bool bulk = slab_bulk_transpose(R, C, in, pp.p[0], in_ld, out_ld);
     for (int i = 1; i < s->world; ++i) bulk = bulk && ((uintptr_t)pp.p[i] % 16 == 0);
-    if (bulk)
+    if (bulk) {
+        PeerDst pd;
+        for (int i = 0; i < 8; ++i) { pd.p[i] = pp.p[i]; pd.ld[i] = out_ld; }
         CHS_LAUNCH_PDL(k_slab_transpose_bulk, dim3(C / SLAB_TC, R / SLAB_TR, s->world), dim3(256), SLAB_TC * SLAB_TP * sizeof(double),
-                       s->stream, pp, in, (int)R, (int)C, (int)in_ld, (int)out_ld, s->rank, s->world);
-    else
+                       s->stream, pd, in, (int)R, (int)C, (int)in_ld, s->rank, s->world);
+    } else
         CHS_LAUNCH_PDL(k_slab_transpose_peers, dim3((C + 31) / 32, (R + 31) / 32, s->world), dim3(256), 32 * 33 * sizeof(double),
                        s->stream, pp, in, (int)R, (int)C, (int)in_ld, (int)out_ld, s->rank, s->world);
     s->launches += 1;
     CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Copy-engine exchange (slab.py, CHS_SLAB_CE): the transposed blocks of `R` local rows (a row chunk) go to a local
+// staging buffer -- block p = [C][R] row-major at stage + p*C*R -- except this rank's own block, which goes straight to
+// `own` (leading dimension own_ld); chs_slab_copy_blocks then moves block p into rank p's buffer as ONE pitched
+// device-to-device copy per peer on `copy_stream`: the copy engines drive NVLink while the SMs transform the next chunk.
+extern "C" int chs_slab_transpose_stage(chs_slab* s, const double* in, double* stage, double* own, int32_t own_ld,
+                                        int32_t R, int32_t C, int32_t in_ld) {
+    if (!s || !in || !stage || !own || s->world < 1 || s->world > 8) return fail("chs_slab_transpose_stage: bad argument");
+    if (R % SLAB_TR || C % SLAB_TC || in_ld % 2 || own_ld % 2 || (uintptr_t)in % 16 || (uintptr_t)stage % 16 || (uintptr_t)own % 16)
+        return fail("chs_slab_transpose_stage: shape / alignment");
+    PeerDst pd;
+    for (int i = 0; i < 8; ++i) { pd.p[i] = nullptr; pd.ld[i] = 0; }
+    for (int i = 0; i < s->world; ++i) { pd.p[i] = stage + (size_t)i * C * R; pd.ld[i] = R; }
+    pd.p[s->rank] = own; pd.ld[s->rank] = own_ld;
+    CHS_LAUNCH_PDL(k_slab_transpose_bulk, dim3(C / SLAB_TC, R / SLAB_TR, s->world), dim3(256), SLAB_TC * SLAB_TP * sizeof(double),
+                   s->stream, pd, in, (int)R, (int)C, (int)in_ld, s->rank, s->world);
+    s->launches += 1;
+    CHS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int chs_slab_copy_blocks(chs_slab* s, const uint64_t* dst, int64_t dst_pitch_bytes, const double* stage,
+                                    int32_t R, int32_t C, void* copy_stream) {
+    if (!s || !dst || !stage || s->world < 1 || s->world > 8) return fail("chs_slab_copy_blocks: bad argument");
+    for (int i = 1; i < s->world; ++i) {                  // nearest peer first, like the SM-driven exchange
+        const int p = (s->rank + i) % s->world;
+#ifdef CHS_EMU
+        for (int c = 0; c < C; ++c)
+            std::memcpy((char*)(uintptr_t)dst[p] + (size_t)c * dst_pitch_bytes, stage + (size_t)p * C * R + (size_t)c * R, (size_t)R * 8);
+        (void)copy_stream;
+#else
+        CHS_CUDA(cudaMemcpy2DAsync((void*)(uintptr_t)dst[p], (size_t)dst_pitch_bytes, stage + (size_t)p * C * R, (size_t)R * 8,
+                                   (size_t)R * 8, (size_t)C, cudaMemcpyDeviceToDevice, (cudaStream_t)copy_stream));
+#endif
+    }
     return 0;
 }
 

@@ -294,7 +294,8 @@ CHS_KERNEL void k_slab_transpose_peers(PeerPtrs dst, const double* in, int R, in
 #endif
 constexpr int SLAB_TR = CHS_SLAB_TR, SLAB_TC = 4096 / SLAB_TR, SLAB_TP = SLAB_TR + 2;
 static_assert(SLAB_TC >= 32 && SLAB_TC % 32 == 0 && SLAB_TR % 16 == 0, "tile shape");
-CHS_KERNEL void k_slab_transpose_bulk(PeerPtrs dst, const double* in, int R, int C, int in_ld, int out_ld, int rank, int P) {
+struct PeerDst { double* p[8]; int ld[8]; };                      // destination base and leading dimension per rank
+CHS_KERNEL void k_slab_transpose_bulk(PeerDst dst, const double* in, int R, int C, int in_ld, int rank, int P) {
     CHS_PDL_TRIGGER();
     CHS_PDL_WAIT();
     CHS_SMEM_DECL
@@ -302,6 +303,7 @@ CHS_KERNEL void k_slab_transpose_bulk(PeerPtrs dst, const double* in, int R, int
     const int peer = (rank + (int)blockIdx.z) % P;
     const double* src = in + (size_t)peer * C;
     double* out = dst.p[peer];
+    const int out_ld = dst.ld[peer];
     const int bx = blockIdx.x * SLAB_TC, by = blockIdx.y * SLAB_TR;
     const int tid = threadIdx.x;                                  // 256 threads
     // in[by + r][bx + c]: a warp reads 32 consecutive columns of one row (256 contiguous bytes) and writes them to 32

@@ -51,6 +51,7 @@ class SlabEngine:
         self.rows = self.be.empty((self.rows_cap, 9))
         self._peer = None                                # peer-mapped base pointers of the A|B exchange buffer
         self._nchunks = 1
+        self._ce = False                                 # copy-engine exchange (CHS_SLAB_CE, see _pass_ce)
         self._main = self._side = None
         if self.P > 1 and self.be.name == "cuda" and os.environ.get("CHS_SLAB_P2P", "1") != "0":
             self._setup_peer_buffers()
@@ -118,13 +119,19 @@ class SlabEngine:
             self._parity = 0
             hdl.barrier()
             n = int(os.environ.get("CHS_SLAB_CHUNKS", "1"))   # measured on 2 GPUs, N=8192: 1.59 / 1.67 / 1.66 ms for 1 / 2 / 4
+            ce = os.environ.get("CHS_SLAB_CE", "0") != "0"
             gran = self.lib.chs_slab_row_granularity(self.N)
-            if n > 1 and self.R % (n * gran) == 0 and self.R // n >= 64:
+            if (n > 1 or ce) and self.R % (n * gran) == 0 and self.R // n >= 128 and (self.R // n) % 128 == 0:
                 self._nchunks = n
                 self._main = torch.cuda.current_stream()
                 self._side = torch.cuda.Stream()
                 self._ev = [torch.cuda.Event() for _ in range(n)]
                 self._ev_done = torch.cuda.Event()
+                if ce:
+                    # copy-engine exchange: two staging buffers of one row chunk each (plain device memory)
+                    self._ce = True
+                    self._stage = [torch.empty((self.R // n) * self.N, dtype=torch.float64, device=self.U.device) for _ in range(2)]
+                    self._copied = [torch.cuda.Event() for _ in range(n)]
         except Exception as e:                           # noqa: BLE001 -- any failure: NCCL all-to-all path
             if self.rank == 0:
                 print(f"[chsimpy_b200.slab] peer-memory transposes unavailable ({type(e).__name__}: {e}); "
@@ -199,9 +206,37 @@ class SlabEngine:
         rc = self.R // n
         return [(k * rc, rc) for k in range(n)]
 
+    def _pass_ce(self, compute, src, dst, barrier=True):
+        """One direction of a step with the COPY ENGINES driving NVLink: per row chunk compute(r0, rc), then one
+        launch transposes the chunk's P blocks into a local staging buffer (this rank's own block straight into
+        `dst`), then one pitched device-to-device copy per peer on the side stream moves block p into rank p's
+        `dst` -- while the SMs already transform the next chunk.  Ends with the exchange barrier."""
+        lib, h, be, R, N, P = self.lib, self._h, self.be, self.R, self.N, self.P
+        main, side = self._main, self._side
+        doff = be.ptr(dst) - self._ab_base
+        chunks = self._chunks()
+        for k, (r0, rc) in enumerate(chunks):
+            compute(r0, rc)
+            if k >= 2:
+                main.wait_event(self._copied[k - 2])     # the copies out of this staging buffer are over
+            stage = self._stage[k % 2]
+            col0 = (self.rank * R + r0) * 8              # this rank's columns of the destination rows
+            self._ck(lib.chs_slab_transpose_stage(h, be.ptr(src) + r0 * N * 8, be.ptr(stage), be.ptr(dst) + col0, N, rc, R, N),
+                     "chs_slab_transpose_stage")
+            self._ev[k].record(main)
+            side.wait_event(self._ev[k])
+            dsts = (C.c_uint64 * P)(*[self._peer[p] + doff + col0 for p in range(P)])
+            self._ck(lib.chs_slab_copy_blocks(h, dsts, N * 8, be.ptr(stage), rc, R, side.cuda_stream), "chs_slab_copy_blocks")
+            self._copied[k].record(side)
+        main.wait_event(self._copied[len(chunks) - 1])   # the side stream is in order: the last copy implies all
+        if barrier:
+            self._hdl.barrier()
+
     def _pass(self, compute, src, dst):
         """One direction of a step: compute(r0, rc) on every row chunk of `src`, each followed by its
         transposes into `dst` (on the side stream when pipelined), then the exchange barrier."""
+        if self._ce:
+            return self._pass_ce(compute, src, dst)
         if self._nchunks == 1:
             compute(0, self.R)
             self._transpose(src, dst)
@@ -333,14 +368,18 @@ class SlabEngine:
         cols = be.ptr(self._cols) if (adaptive and self._cols is not None) else None
         edges = (0, 0) if jit else (int(self.rank == 0), int(self.rank == self.P - 1))
         self._pass(y_pass, self.B, self.A)
-        if self._peer is not None and self._nchunks == 1:
+        if self._peer is not None and (self._nchunks == 1 or self._ce):
             # peer-memory route: x pass, its exchange and the 7 sums (stored into every rank's gather buffer by
             # the sums kernel) share ONE device-side barrier; the control kernel adds the ranks' sums in rank
             # order -- 8 launches per step, no collective
-            x_pass(0, R)
-            after_x()
+            if self._ce:
+                self._pass_ce(x_pass, self.A, self.B, barrier=False)
+                after_x()
+            else:
+                x_pass(0, R)
+                after_x()
+                self._transpose(self.A, self.B, sync=False)
             cols = be.ptr(self._cols) if (adaptive and self._cols is not None) else None
-            self._transpose(self.A, self.B, sync=False)
             par = self._parity
             self._parity ^= 1
             goff = be.ptr(self._gather) - self._ab_base + (par * self.P + self.rank) * 64

@@ -189,6 +189,14 @@ int chs_slab_transpose(chs_slab*, const double* in, double* out, int32_t R, int3
  * straight into dst[p], the peer-mapped destination in rank p's buffer */
 int chs_slab_transpose_peers(chs_slab*, const double* in, const uint64_t* dst /*[world] device addresses*/, int32_t R, int32_t C,
                              int32_t in_ld, int32_t out_ld);
+/* Copy-engine exchange: chs_slab_transpose_stage transposes the blocks of `R` local rows (leading dimension in_ld,
+ * block for rank p = columns p*C .. p*C+C) into a local staging buffer (block p = [C][R] at stage + p*C*R), this
+ * rank's own block directly into `own` (leading dimension own_ld); chs_slab_copy_blocks queues one pitched
+ * device-to-device copy per peer on `copy_stream` (dst[p] = peer-mapped destination of block p, row pitch in bytes). */
+int chs_slab_transpose_stage(chs_slab*, const double* in, double* stage, double* own, int32_t own_ld,
+                             int32_t R, int32_t C, int32_t in_ld);
+int chs_slab_copy_blocks(chs_slab*, const uint64_t* dst, int64_t dst_pitch_bytes, const double* stage,
+                         int32_t R, int32_t C, void* copy_stream);
 /* the y pass of one step in one kernel: H = (H + Seig*rowDCT(B))/CHeig; B = rowIDCT(H)  (solver.py:201-208) */
 int chs_slab_update(chs_slab*, double* H, double* B, int32_t rows, int32_t slot_base);
 int chs_slab_yedge(chs_slab*, const double* row_a, const double* row_b, int32_t accumulate);

@@ -464,16 +464,16 @@ def test_plain_cpp_client_of_the_c_abi(tmp_path):
 @pytest.mark.gpu
 def test_slab_two_gpus_peer_memory_and_nccl():
     """Row-slab decomposition over two GPUs (needs a box with >= 2): tools/slab_check.py replays the
-    reference fixtures n2048_k10 and n8192_k4 on both ranks, once with the peer-memory transposes
-    and once with the NCCL all-to-all route."""
+    reference fixtures n2048_k10 and n8192_k4 on both ranks, once with the peer-memory transposes,
+    once with the NCCL all-to-all route and once with the copy-engine exchange (two row chunks)."""
     import subprocess
     import sys
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for p2p in ("1", "0"):
-        env = dict(os.environ, CHS_SLAB_P2P=p2p)
+    for extra in (dict(CHS_SLAB_P2P="1"), dict(CHS_SLAB_P2P="0"), dict(CHS_SLAB_CE="1", CHS_SLAB_CHUNKS="2")):
+        env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                             "--master-addr", "127.0.0.1", "--master-port", "29577",
                             os.path.join(root, "tools", "slab_check.py"), "2048", "5"],
