@@ -54,6 +54,7 @@ struct chs_solver {
     int cap_col[3], cap_row[4];     // resident CTAs per kernel mode (persistent grids)
     int cap_mix;
     unsigned long long* trace;      // -DCHS_TRACE=1 builds only (chs_debug_trace)
+    int one_mode;                   // COL/ROW_STEP_LL instantiations: -1 = when a launch is at most one tile per SM, 0 / 1 = forced (CHS_ONE_PER_SM)
     int ll_max;                     // low-latency kernels when at most this many simulations run (0 = never)
     int sub_sims;                   // L2 blocking: simulations per sub-batch of chs_steps (0 = off)
     int mix_mode;                   // -1: mixed launches when enough simulations run (default), 0: never, 1: whenever possible
@@ -277,6 +278,12 @@ static int resident_ctas(K kern, int threads, int smem, int num_sms) {
     return per_sm * num_sms;
 }
 
+// Dynamic shared memory of the *_LL launches: more than half of an SM's, so that no two of these CTAs -- of one
+// kernel, or a kernel and its programmatically launched dependents -- ever share an SM (both kernels ask for the same
+// amount: no carve-out change at the kernel boundaries).  With the tile's own 36 KB two column CTAs fitted one SM while
+// the dependents were resident, and a single simulation's step waited 4 us for the two tiles that shared an SM.
+static int ll_smem_bytes(int tile_bytes) { return tile_bytes > 116 * 1024 ? tile_bytes : 116 * 1024; }
+
 template <int N>
 static int set_attrs(chs_solver* s) {
     const int b = Geo<N>::SMEM_BYTES;
@@ -288,6 +295,8 @@ static int set_attrs(chs_solver* s) {
     CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_mix<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CHS_CUDA(cudaFuncSetAttribute(k_col<N, COL_STEP_LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ll_smem_bytes(b)));
+    CHS_CUDA(cudaFuncSetAttribute(k_row<N, ROW_STEP_LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ll_smem_bytes(b)));
     CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_PREPARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CHS_CUDA(cudaFuncSetAttribute(k_diag<N, DIAG_JITTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 #ifndef CHS_EMU
@@ -395,6 +404,7 @@ extern "C" chs_solver* chs_create(int32_t device, int32_t N, int32_t batch, doub
     s->timing = false; s->ev_used = 0; s->ev_diag = false; s->t_iters = 0;
     s->t_ms[0] = s->t_ms[1] = s->t_ms[2] = 0;
     s->trace = nullptr;
+    s->one_mode = [] { const char* e = getenv("CHS_ONE_PER_SM"); return e ? atoi(e) : -1; }();
     s->ll_max = [] { const char* e = getenv("CHS_LL_MAX"); return e ? atoi(e) : CHS_LL_MAX_SIMS; }();
     s->sub_sims = [N] { const char* e = getenv("CHS_SUB"); return e ? atoi(e) : default_sub_sims(N); }();
     s->mix_mode = [] { const char* e = getenv("CHS_MIX"); return e ? atoi(e) : 0; }();
@@ -741,6 +751,8 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
         b.sim_index = s->index + sb0;             // (the identity list is resident until the first compaction)
         b.nsims = (s->n_running - sb0 < sub) ? s->n_running - sb0 : sub;
     }
+    // at most one tile per SM: the unrolled / register-rich instantiations of the two kernels (COL_STEP_LL, ROW_STEP_LL)
+    const bool one_per_sm = s->one_mode >= 0 ? s->one_mode != 0 : ((long long)G::NTILES * b.nsims <= (long long)s->num_sms);
     const dim3 gcol_b = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, b.nsims), grow_b = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, b.nsims);
     const dim3 grid_b(G::NTILES, b.nsims);
     for (long long it = 0; it < n_iters; ++it) {
@@ -754,10 +766,18 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
             cudaEventRecord(next_event(s), s->stream);
         }
         if (ll) { if (chs_ll_launch(N, 0, &b, b.nsims, pdl ? 1 : 0, (void*)s->stream)) return fail("chs_steps: low-latency launch failed"); }
+        else if (one_per_sm) {
+            if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP_LL>), gcol_b, block, ll_smem_bytes(G::SMEM_BYTES), s->stream, b);
+            else CHS_LAUNCH((k_col<N, COL_STEP_LL>), gcol_b, block, ll_smem_bytes(G::SMEM_BYTES), s->stream, b);
+        }
         else if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP>), gcol_b, block, G::SMEM_BYTES, s->stream, b);
         else CHS_LAUNCH((k_col<N, COL_STEP>), gcol_b, block, G::SMEM_BYTES, s->stream, b);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
         if (ll) { if (chs_ll_launch(N, 1, &b, b.nsims, pdl ? 1 : 0, (void*)s->stream)) return fail("chs_steps: low-latency launch failed"); }
+        else if (one_per_sm) {
+            if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP_LL>), grow_b, block, ll_smem_bytes(G::SMEM_BYTES), s->stream, b);
+            else CHS_LAUNCH((k_row<N, ROW_STEP_LL>), grow_b, block, ll_smem_bytes(G::SMEM_BYTES), s->stream, b);
+        }
         else if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP>), grow_b, block, G::SMEM_BYTES, s->stream, b);
         else CHS_LAUNCH((k_row<N, ROW_STEP>), grow_b, block, G::SMEM_BYTES, s->stream, b);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);

@@ -80,8 +80,12 @@ CHS_HD void sim_derive(Sim& S) {
     sim_derive_lam(S);
 }
 
-enum { COL_FWD = 0, COL_STEP = 1, COL_INV = 2 };
-enum { ROW_FWD_U = 0, ROW_FWD_MU = 1, ROW_STEP = 2, ROW_INV = 3 };
+// *_LL: the step kernels for launches of at most one tile per SM (a single simulation, two at N=512): the same code
+// with the per-thread loops over pairing units / butterflies unrolled and up to 255 registers -- a tile then runs
+// alone on its SM with one warp per scheduler, and independent instructions from two units in flight are the only
+// latency hiding there is.  Same operations in the same order per value: bit-identical results.
+enum { COL_FWD = 0, COL_STEP = 1, COL_INV = 2, COL_STEP_LL = 3 };
+enum { ROW_FWD_U = 0, ROW_FWD_MU = 1, ROW_STEP = 2, ROW_INV = 3, ROW_STEP_LL = 4 };
 enum { DIAG_PREPARE = 0, DIAG_JITTER = 1 };
 
 struct KArgs {
@@ -622,7 +626,7 @@ CHS_DEV void store_block_x(double2* sc, int lam, int base, const double (&xr)[R]
 //   [FWD: last forward FFT stage] -> items (post / update / pre in registers, functor f) -> [INV: first
 //   inverse FFT stage], in place in the tile.  Units are processed one after the other (2 * RL complex
 //   points live).
-template <int N, bool FWD, bool INV, class F, bool XIN = false, bool XOUT = false>
+template <int N, bool FWD, bool INV, class F, bool XIN = false, bool XOUT = false, int UNR = 1>
 CHS_DEV void fused_units(double2* scl, int t, F& f) {
     using P = Pairing<N>;
     constexpr int M = N / 2, RL = P::RL;
@@ -630,7 +634,7 @@ CHS_DEV void fused_units(double2* scl, int t, F& f) {
     const int lam = (XIN || XOUT) ? (int)(threadIdx.x & 7) : 0;
     double2* sc0 = scl - lam;
     f.begin(t);
-#pragma unroll 1
+#pragma unroll UNR
     for (int i = 0; i < P::NU; ++i) {
         const int u = t + i * P::TPL;
         const int rho_a = u, rho_b = (u == 0) ? P::Q / 2 : P::Q - u;
@@ -787,8 +791,10 @@ struct ColMid {
 // =======================================================================================
 // one tile of the column kernel (out of line in the persistent build: the compiler then
 // allocates registers for the tile body alone)
-template <int N, int MODE>
+template <int N, int MODE_>
 CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
+    constexpr bool LL = (MODE_ == COL_STEP_LL);
+    constexpr int MODE = LL ? COL_STEP : MODE_;
     using G = Geo<N>;
     constexpr int M = G::M, LINES = G::LINES, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
@@ -848,7 +854,7 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
             mid.hat_in = ((MODE == COL_INV && a.src) ? a.src : a.hatU) + toff;
             mid.ge = 0; mid.lam1 = lam1; mid.lam2 = lam2; mid.lamx = lamx; mid.gx = gxs;
             mid.hat00 = (MODE == COL_FWD && !a.dst && tile == 0 && l == 0) ? &S->k.hat00 : nullptr;
-            fused_units<N, MODE != COL_INV, MODE != COL_FWD>(scl, t, mid);
+            fused_units<N, MODE != COL_INV, MODE != COL_FWD, ColMid<N, MODE>, false, false, LL ? Pairing<N>::NU : 1>(scl, t, mid);
             CHS_TRACE_PT(a, w, 4);
             if (MODE != COL_FWD) {
                 if (MODE == COL_STEP) {
@@ -887,7 +893,7 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
 }
 
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_COL) k_col(KArgs a) {
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, MODE == COL_STEP_LL ? 1 : Geo<N>::MINB_COL) k_col(KArgs a) {
     using G = Geo<N>;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);
@@ -925,6 +931,12 @@ CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const PhysK& k, co
     if (diag) {
         if (j == 0) { edge[0] = xr[0]; edge[3] = xr[R / 2]; }                 // U[0], U[N-1]
         if (j == st - 1) { edge[1] = xi[R - 1]; edge[2] = xi[R / 2 - 1]; }    // U[1], U[N-2]
+        // Ra (solver.py:226-227): one branch per butterfly, taken by the 16 threads of ONE line of one tile per
+        // simulation; summed in the order (butterfly, point) -- the unfused path of k_row_tile uses the same order
+        if (ra_line) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) acc.ra += fabs(xr[q] - ra_mean) + fabs(xi[q] - ra_mean);
+        }
     }
 #pragma unroll
     for (int q = 0; q < R; ++q) {
@@ -935,7 +947,6 @@ CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const PhysK& k, co
             if (diag) {
                 acc.ab += fabs(u - k.meanU);
                 acc.cnt += (u < k.threshold) ? 1 : 0;
-                if (ra_line) acc.ra += fabs(u - ra_mean);
             }
             acc.mu2 = chs_fma(mu, mu, acc.mu2);
             if (h) xi[q] = mu; else xr[q] = mu;
@@ -947,8 +958,10 @@ CHS_DEV void physics(double (&xr)[R], double (&xi)[R], int j, const PhysK& k, co
 //  row kernel
 // =======================================================================================
 // one tile of the row kernel
-template <int N, int MODE>
+template <int N, int MODE_>
 CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
+    constexpr bool LL = (MODE_ == ROW_STEP_LL);
+    constexpr int MODE = LL ? ROW_STEP : MODE_;
     using G = Geo<N>;
     constexpr int M = G::M, LINES = G::LINES, TPL = G::TPL, NT = G::NT;
     constexpr int NST = Rad<M>::nst;
@@ -983,9 +996,9 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
             halted = (MODE == ROW_STEP) ? S->halted : 0;
             const long long cs_next = S->computed_steps + (MODE == ROW_STEP ? 1 : 0);
             want_cols = S->p.adaptive_time && !a.last && cs_next > 500 && (cs_next % 2) == 0;
-            // the one tile per simulation that holds the Ra row also takes the unfused middle: Ra is
-            // summed from the field in shared memory, so the hot loop carries no per-value Ra work
-            slow = want_cols || jit || (MODE == ROW_FWD_MU) || ra_tile;
+            // (the tile that holds the Ra row used to take the unfused middle as well; a single simulation's step then
+            // waited 4 us for that one tile -- Ra is now one branch per butterfly in the fused pass, see physics())
+            slow = want_cols || jit || (MODE == ROW_FWD_MU);
         }
         if (MODE == ROW_FWD_U || MODE == ROW_FWD_MU) {
             const double* src = (MODE == ROW_FWD_U && a.src) ? a.src : a.U;
@@ -1002,7 +1015,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     ra_scr[0] = reinterpret_cast<const double*>(sc + (l & 3))[l >> 2] * sqrt(1.0 / N);   // (piece_flip(0) = 0)
                 {   // fused: 2x2 exchange out of the piece form + pre + first inverse stage
                     RowPre<N> pre{s_om};
-                    fused_units<N, false, true, RowPre<N>, true, false>(scl, t, pre);
+                    fused_units<N, false, true, RowPre<N>, true, false, LL ? Pairing<N>::NU : 1>(scl, t, pre);
                 }
                 line_barrier<N, true>();
                 CHS_TRACE_PT(a, w, 11);
@@ -1065,17 +1078,9 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                     pk.threshold = K[5];
                     // conserved mean (Q4); the jitter shifts it by jitter*(2*mean(noise) - 1)
                     pk.meanU = K[11] / (double)N + (jit ? K[7] * (2.0 * a.noise_mean[0] - 1.0) : 0.0);
-                    if (ra_line) {                                              // Ra = mean |U[r,:] - mean U[r,:]| (solver.py:226-227)
-                        const double ra_mean = ra_scr[0];
-                        double s = 0;
-                        for (int i = 0; i < G::PPT; ++i) {
-                            const double2 v = scl[G::idx(t + i * TPL)];
-                            s += fabs(v.x - ra_mean) + fabs(v.y - ra_mean);
-                        }
-                        ra_scr[2 + t] = s;
-                    }
+                    const double ra_mean = ra_line ? ra_scr[0] : 0.0;          // mean of the Ra row (C[0]/sqrt(N), or the jittered row's)
                     RowAcc acc = {0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 1
+#pragma unroll (LL ? NB0 : 1)
                     for (int i = 0; i < NB0; ++i) {
                         const int j = t + i * TPL;
                         double2* pj = scl + G::idx(j);
@@ -1100,7 +1105,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                             }
                             dft<R0, true>(xr, xi);
                         }
-                        physics<N, R0, G::LOG_STRIDE, false>(xr, xi, j, pk, ltab, sums, false, 0.0, acc, edge + 4 * l);
+                        physics<N, R0, G::LOG_STRIDE, false>(xr, xi, j, pk, ltab, sums, ra_line, ra_mean, acc, edge + 4 * l);
                         if (!slow) {
                             dft<R0, false>(xr, xi);
 #pragma unroll
@@ -1115,6 +1120,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                         for (int q = 0; q < R0; ++q) pj[q * G::step(ST0)] = make_double2(xr[q], xi[q]);
                     }
                     CHS_TRACE_PT(a, w, 13);
+                    if (ra_line) ra_scr[2 + t] = acc.ra;                       // Ra = mean |U[r,:] - mean U[r,:]| (solver.py:226-227)
                     const double v[4] = {chs_fma(pk.th.RT, acc.fa + acc.fb, acc.fp), acc.ab, acc.mu2, (double)acc.cnt};
                     reduce_stage<4>(v, sm + G::OFF_RED, tid);
                     __syncthreads();
@@ -1172,7 +1178,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
                 CHS_TRACE_PT(a, w, 15);
                 {   // fused: last forward stage + post + 2x2 exchange into the piece form
                     RowPost<N> post{s_om};
-                    fused_units<N, true, false, RowPost<N>, false, true>(scl, t, post);
+                    fused_units<N, true, false, RowPost<N>, false, true, LL ? Pairing<N>::NU : 1>(scl, t, post);
                 }
                 __syncthreads();
                 CHS_TRACE_PT(a, w, 16);
@@ -1213,7 +1219,7 @@ CHS_TILE_FN void k_row_tile(const KArgs& a, int w, double* sm) {
 }
 
 template <int N, int MODE>
-CHS_KERNEL void __launch_bounds__(Geo<N>::NT, Geo<N>::MINB_ROW) k_row(KArgs a) {
+CHS_KERNEL void __launch_bounds__(Geo<N>::NT, MODE == ROW_STEP_LL ? 1 : Geo<N>::MINB_ROW) k_row(KArgs a) {
     using G = Geo<N>;
     CHS_SMEM_DECL
     double* sm = reinterpret_cast<double*>(CHS_SMEM_PTR);

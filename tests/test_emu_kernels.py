@@ -57,10 +57,12 @@ def run_fixture(be, name, limit=None):
     return sol, z, m
 
 
-@pytest.mark.parametrize("name,steps,env", [("n256_k200", 6, {}), ("n512_full2000", 3, {}), ("n512_full2000", 3, {"CHS_LL_MAX": "2"})])
+@pytest.mark.parametrize("name,steps,env", [("n256_k200", 6, {}), ("n512_full2000", 3, {"CHS_ONE_PER_SM": "0"}),
+                                            ("n512_full2000", 3, {"CHS_ONE_PER_SM": "1"}), ("n512_full2000", 3, {"CHS_LL_MAX": "2"})])
 def test_step_n256_n512(be, name, steps, env, monkeypatch):
     """The tile geometry of the sizes that matter (N = 256, 512), a few steps against the fixtures: the step kernels
-    of the throughput build and the optional 8-points-per-thread build (chs_ll.cu, CHS_LL_MAX: 256 threads per tile)."""
+    of the throughput build, the instantiations a launch of at most one tile per SM gets on the GPU (CHS_ONE_PER_SM=1:
+    unrolled unit / butterfly loops), and the optional 8-points-per-thread build (chs_ll.cu, CHS_LL_MAX)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     sol, z, m = run_fixture(be, name, limit=steps)
