@@ -1207,7 +1207,10 @@ static bool slab_bulk_transpose(int R, int C, const double* in, const double* ou
 
 extern "C" int chs_slab_transpose(chs_slab* s, const double* in, double* out, int32_t R, int32_t C, int32_t in_ld, int32_t out_ld) {
     if (!s || !in || !out) return fail("chs_slab_transpose: bad argument");
-    if (slab_bulk_transpose(R, C, in, out, in_ld, out_ld)) {
+    // (local transposes: measured 4 % of a step SLOWER with the bulk-store tiles on one GPU -- N=8192 1.93 -> 2.01 ms,
+    // N=16384 9.34 -> 9.68 ms -- so the 32 x 33 tile kernel stays unless CHS_SLAB_BULK=2 asks for the experiment)
+    static const bool bulk_local = [] { const char* e = getenv("CHS_SLAB_BULK"); return e && atoi(e) == 2; }();
+    if (bulk_local && slab_bulk_transpose(R, C, in, out, in_ld, out_ld)) {
         PeerDst pd;
         for (int i = 0; i < 8; ++i) { pd.p[i] = nullptr; pd.ld[i] = 0; }
         pd.p[0] = out; pd.ld[0] = out_ld;
