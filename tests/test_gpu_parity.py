@@ -534,3 +534,13 @@ def test_arbitrary_n_path_vs_oracle(N, kw, steps):
     check_rows(sol.timedata.data(), o.rows, N)
     assert np.abs(sol.U - o.U).max() <= U_TOL
     assert abs(s.delt - o.delt) <= 1e-12 * o.delt
+
+
+@pytest.mark.gpu
+def test_mixed_launches_and_one_tile_per_sm_kernels_bit_identical_on_device():
+    """The scheduling variants of chs_steps on the device: mixed column+row launches (k_mix, throughput kernels) against
+    the default, which for 5 members of N=64 (40 tiles <= #SMs) runs the unrolled `_LL` instantiations on exclusive SMs --
+    TimeData rows, states and fields must agree bit for bit (same test body as on the host emulation)."""
+    from test_emu_kernels import test_mixed_launches_are_bit_identical
+    from chsimpy_b200.solver import _CudaBackend
+    test_mixed_launches_are_bit_identical(_CudaBackend(None))
