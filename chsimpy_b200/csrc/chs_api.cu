@@ -681,10 +681,14 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
     static const bool pdl_env = [] { const char* e = getenv("CHS_PDL"); return !e || atoi(e) != 0; }();
     // Only when the launch (nearly) fills the CTA slots: the dependents of a programmatic launch become resident while
     // their predecessor still runs, and with a partly filled GPU they pile up on the SMs the predecessor left free --
-    // measured on B200, N=512: 2..4 simulations 47 us/step with, 29..36 us without (profiles/r2c_small_batches.md)
+    // measured on B200, N=512: 2..4 simulations 47 us/step with, 29..36 us without (profiles/r2c_experiments.md, section 4).
+    // The _LL launches (at most one tile per SM, each CTA alone on its SM by its shared-memory footprint) cannot pile up.
     static const int pdl_min_pct = [] { const char* e = getenv("CHS_PDL_MIN_PCT"); return e ? atoi(e) : 80; }();
-    const bool pdl = pdl_env && !s->timing && ((long long)G::NTILES * s->n_running * 100 >= (long long)pdl_min_pct * s->cap_row[ROW_STEP] ||
-                                                2LL * G::NTILES * s->n_running <= s->num_sms);
+    auto pdl_for = [&](int nsims, bool exclusive) {
+        return pdl_env && !s->timing && (exclusive || (long long)G::NTILES * nsims * 100 >= (long long)pdl_min_pct * s->cap_row[ROW_STEP] ||
+                                         2LL * G::NTILES * nsims <= s->num_sms);
+    };
+    const bool pdl = pdl_for(s->n_running, false);                     // (mixed launches: whole batch)
     if (s->n_running == s->batch) a.sim_index = nullptr;
     // without noise the step kernels keep the field in spectral form only (U is materialised by chs_end);
     // with noise k_row stores the jittered U every step
@@ -752,7 +756,16 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
         b.nsims = (s->n_running - sb0 < sub) ? s->n_running - sb0 : sub;
     }
     // at most one tile per SM: the unrolled / register-rich instantiations of the two kernels (COL_STEP_LL, ROW_STEP_LL)
-    const bool one_per_sm = s->one_mode >= 0 ? s->one_mode != 0 : ((long long)G::NTILES * b.nsims <= (long long)s->num_sms);
+    // ... and up to two tiles per SM still run them (two CTAs of 244 / 255 registers fill an SM's register file, so no
+    // third CTA -- e.g. an early dependent -- can join), with the tile's own shared memory instead of the exclusive amount
+    // (128-thread tiles only, i.e. N = 512: measured 33.6 -> 30.2 us/step for 3 and 4 members; smaller tiles fit more than two
+    // CTAs per SM and N = 1024's 256-thread tiles only one: N=256 x 8 members 26.7 -> 28.5 us, N=1024 x 2 48.9 -> 55.1 us)
+    static const int ll_tiles_env = [] { const char* e = getenv("CHS_LL_TILES_PER_SM"); return e ? atoi(e) : 0; }();
+    const int ll_tiles = ll_tiles_env > 0 ? ll_tiles_env : (G::NT == 128 ? 2 : 1);
+    const long long ctas_b = (long long)G::NTILES * b.nsims;
+    const bool one_per_sm = s->one_mode >= 0 ? s->one_mode != 0 : (ctas_b <= (long long)ll_tiles * s->num_sms);
+    const int ll_smem = (ctas_b <= (long long)s->num_sms) ? ll_smem_bytes(G::SMEM_BYTES) : G::SMEM_BYTES;
+    const bool pdl = pdl_for(b.nsims, one_per_sm && !ll);
     const dim3 gcol_b = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, b.nsims), grow_b = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, b.nsims);
     const dim3 grid_b(G::NTILES, b.nsims);
     for (long long it = 0; it < n_iters; ++it) {
@@ -767,16 +780,16 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
         }
         if (ll) { if (chs_ll_launch(N, 0, &b, b.nsims, pdl ? 1 : 0, (void*)s->stream)) return fail("chs_steps: low-latency launch failed"); }
         else if (one_per_sm) {
-            if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP_LL>), gcol_b, block, ll_smem_bytes(G::SMEM_BYTES), s->stream, b);
-            else CHS_LAUNCH((k_col<N, COL_STEP_LL>), gcol_b, block, ll_smem_bytes(G::SMEM_BYTES), s->stream, b);
+            if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP_LL>), gcol_b, block, ll_smem, s->stream, b);
+            else CHS_LAUNCH((k_col<N, COL_STEP_LL>), gcol_b, block, ll_smem, s->stream, b);
         }
         else if (pdl) CHS_LAUNCH_PDL((k_col<N, COL_STEP>), gcol_b, block, G::SMEM_BYTES, s->stream, b);
         else CHS_LAUNCH((k_col<N, COL_STEP>), gcol_b, block, G::SMEM_BYTES, s->stream, b);
         if (s->timing) cudaEventRecord(next_event(s), s->stream);
         if (ll) { if (chs_ll_launch(N, 1, &b, b.nsims, pdl ? 1 : 0, (void*)s->stream)) return fail("chs_steps: low-latency launch failed"); }
         else if (one_per_sm) {
-            if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP_LL>), grow_b, block, ll_smem_bytes(G::SMEM_BYTES), s->stream, b);
-            else CHS_LAUNCH((k_row<N, ROW_STEP_LL>), grow_b, block, ll_smem_bytes(G::SMEM_BYTES), s->stream, b);
+            if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP_LL>), grow_b, block, ll_smem, s->stream, b);
+            else CHS_LAUNCH((k_row<N, ROW_STEP_LL>), grow_b, block, ll_smem, s->stream, b);
         }
         else if (pdl) CHS_LAUNCH_PDL((k_row<N, ROW_STEP>), grow_b, block, G::SMEM_BYTES, s->stream, b);
         else CHS_LAUNCH((k_row<N, ROW_STEP>), grow_b, block, G::SMEM_BYTES, s->stream, b);
