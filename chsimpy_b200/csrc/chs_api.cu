@@ -758,13 +758,15 @@ static int do_steps(chs_solver* s, long long n_iters, const double* noise, const
     // at most one tile per SM: the unrolled / register-rich instantiations of the two kernels (COL_STEP_LL, ROW_STEP_LL)
     // ... and up to two tiles per SM still run them (two CTAs of 244 / 255 registers fill an SM's register file, so no
     // third CTA -- e.g. an early dependent -- can join), with the tile's own shared memory instead of the exclusive amount
-    // (128-thread tiles only, i.e. N = 512: measured 33.6 -> 30.2 us/step for 3 and 4 members; smaller tiles fit more than two
-    // CTAs per SM and N = 1024's 256-thread tiles only one: N=256 x 8 members 26.7 -> 28.5 us, N=1024 x 2 48.9 -> 55.1 us)
+    // (measured: N=512 x 3..4 members 33.6 -> 30.2 us/step, N=256 x 5..8 26.6 -> 23.9, N=128 x 10..16 26.7 -> 21.7, N=64 x 20..36
+    // 25.6 -> 21.7; not N = 1024: its 256-thread tiles fit only one such CTA per SM, 2 members 48.9 -> 55.1 us)
     static const int ll_tiles_env = [] { const char* e = getenv("CHS_LL_TILES_PER_SM"); return e ? atoi(e) : 0; }();
-    const int ll_tiles = ll_tiles_env > 0 ? ll_tiles_env : (G::NT == 128 ? 2 : 1);
+    const int ll_tiles = ll_tiles_env > 0 ? ll_tiles_env : (G::NT <= 128 ? 2 : 1);
     const long long ctas_b = (long long)G::NTILES * b.nsims;
     const bool one_per_sm = s->one_mode >= 0 ? s->one_mode != 0 : (ctas_b <= (long long)ll_tiles * s->num_sms);
-    const int ll_smem = (ctas_b <= (long long)s->num_sms) ? ll_smem_bytes(G::SMEM_BYTES) : G::SMEM_BYTES;
+    // two per SM: 100 KB each, so that a third never fits (tiles of fewer than 128 threads would fit by registers)
+    const int ll_smem = (ctas_b <= (long long)s->num_sms) ? ll_smem_bytes(G::SMEM_BYTES)
+                                                          : (G::SMEM_BYTES > 100 * 1024 ? G::SMEM_BYTES : 100 * 1024);
     const bool pdl = pdl_for(b.nsims, one_per_sm && !ll);
     const dim3 gcol_b = pgrid(s->cap_col[COL_STEP], s->num_sms, G::NTILES, b.nsims), grow_b = pgrid(s->cap_row[ROW_STEP], s->num_sms, G::NTILES, b.nsims);
     const dim3 grid_b(G::NTILES, b.nsims);
