@@ -1205,7 +1205,7 @@ extern "C" int chs_slab_row_means(chs_slab* s, const double* in, int64_t rows, i
 #ifdef CHS_EMU
     const int nt = 32;
 #else
-    const int nt = 256;
+    const int nt = 1024;            // one block per row of the noise chunk: 64 blocks read 128 MiB -- the bytes in flight per block are what counts
 #endif
     CHS_LAUNCH(k_row_means, dim3((unsigned)rows), dim3(nt), nt * sizeof(double), s->stream, in, (long long)cols, out);
     s->launches += 1;
@@ -1525,7 +1525,7 @@ extern "C" int chs_row_means(chs_solver* s, const double* in, int64_t rows, int6
 #ifdef CHS_EMU
     const int nt = 32;
 #else
-    const int nt = 256;
+    const int nt = 1024;            // one block per row of the noise chunk: 64 blocks read 128 MiB -- the bytes in flight per block are what counts
 #endif
     CHS_LAUNCH(k_row_means, dim3((unsigned)rows), dim3(nt), nt * sizeof(double), s->stream, in, (long long)cols, out);
     s->launches += 1;

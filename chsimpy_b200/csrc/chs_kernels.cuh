@@ -1299,7 +1299,8 @@ CHS_KERNEL void __launch_bounds__(Geo<N>::NT) k_diag(KArgs a) {
     double v[4] = {0, 0, 0, 0};                    // raw grad^2 (x h^2), F, ABS, CNT
     // all loads of a batch of UNR values are issued before the first use (one simulation is only
     // NTILES CTAs: the kernel is bound by the latency of these loads, not by their bandwidth)
-    constexpr int CNT = LINES * N / NT, UNR = (CNT % 8 == 0) ? 8 : 1;
+    // (DIAG_JITTER runs once per step of a jittered simulation: 16 values = 80 loads per batch, two batches for N=512)
+    constexpr int CNT = LINES * N / NT, UNR = (MODE == DIAG_JITTER && CNT % 16 == 0) ? 16 : ((CNT % 8 == 0) ? 8 : 1);
 #pragma unroll 1
     for (int j0 = 0; j0 < CNT; j0 += UNR) {
         double c[UNR], up[UNR], dn[UNR], lf[UNR], rt[UNR];
