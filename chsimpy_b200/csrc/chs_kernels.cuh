@@ -815,13 +815,6 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
             for (unsigned o = 0; o < TILE_BYTES; o += CHUNK)
                 chs_bulk_g2s(reinterpret_cast<char*>(sm) + o, reinterpret_cast<const char*>(gtile) + o, CHUNK, bar);
         }
-        if (MODE == COL_STEP) {
-            // the hat_U tile is consumed in the middle of the tile's work: pull it into L2 now
-            // (staging it in shared memory with a second bulk copy was measured for a single simulation: the fused
-            // pass stayed at 3.9 us -- it is bound by its dependent FP64 chain, not by the loads)
-            const double* hp = a.hatU + off + (size_t)tile * N * LINES;          // contiguous 8*N*LINES bytes
-            for (int i = tid * 16; i < N * LINES; i += NT * 16) CHS_PREFETCH_L2(hp + i);
-        }
         const int col = (MODE != COL_STEP && a.natural) ? a.kof[kx0 + l] : kx0 + l;   // far-side column
         double lam1 = 0, lam2 = 0, lamx = 0, gxs = 0;
         int halted = 0;
@@ -832,6 +825,15 @@ CHS_TILE_FN void k_col_tile(const KArgs& a, int w, double* sm, unsigned phase) {
             const int kx = a.kof[kx0 + l];
             lamx = a.lam[kx];
             gxs = a.gsin[kx];
+            // the hat_U tile is consumed in the middle of the tile's work: pull it into L2 now -- unless the simulation
+            // has stopped: between two polls a stopped member's tiles still launch, and in this HBM-bound kernel the
+            // T tile (already on its way) plus this prefetch were half of a live tile's traffic
+            // (staging it in shared memory with a second bulk copy was measured for a single simulation: the fused
+            // pass stayed at 3.9 us -- it is bound by its dependent FP64 chain, not by the loads)
+            if (!halted) {
+                const double* hp = a.hatU + off + (size_t)tile * N * LINES;      // contiguous 8*N*LINES bytes
+                for (int i = tid * 16; i < N * LINES; i += NT * 16) CHS_PREFETCH_L2(hp + i);
+            }
         }
         CHS_TRACE_PT(a, w, 1);
         if (MODE != COL_INV) chs_mbar_wait(bar, phase);
